@@ -1,0 +1,67 @@
+"""Preallocated KV cache honouring the HF past_key_values contract the reference relies on
+(codes/open_flamingo/src/vlm.py:463-468 reads past_key_values[0][0].shape[2];
+codes/open_flamingo/src/aki_generation.py:45-47,80): per layer (K, V), each (B, H, T_kv, D), K stored post-RoPE,
+appended along dim 2.  Instead of DynamicCache's torch.cat per step, prefill and decode write rows in place into
+(B, H, t_cap, D) buffers (layout chosen so one (b,h) stream is contiguous for TMA and for the decode kernel)."""
+from __future__ import annotations
+
+from typing import List, Optional, Tuple
+
+import torch
+
+
+class AkiKVCache:
+    def __init__(self, num_layers: int, batch: int, num_heads: int, head_dim: int, t_cap: int, device,
+                 dtype=torch.bfloat16):
+        self.t_cap = int(t_cap)
+        self.k: List[torch.Tensor] = [torch.zeros(batch, num_heads, t_cap, head_dim, dtype=dtype, device=device)
+                                      for _ in range(num_layers)]
+        self.v: List[torch.Tensor] = [torch.zeros_like(self.k[0]) for _ in range(num_layers)]
+        self._len = [0] * num_layers
+        self.kv_len = torch.zeros(batch, dtype=torch.int32, device=device)   # device copy for the decode kernel
+
+    # ---- HF Cache surface --------------------------------------------------------------------------
+    def get_seq_length(self, layer_idx: int = 0) -> int:
+        return self._len[layer_idx]
+
+    def get_max_cache_shape(self) -> int:
+        return self.t_cap
+
+    def __len__(self) -> int:
+        return len(self.k)
+
+    def __getitem__(self, layer_idx: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        n = self._len[layer_idx]
+        return self.k[layer_idx][:, :, :n], self.v[layer_idx][:, :, :n]
+
+    def __iter__(self):
+        for i in range(len(self.k)):
+            yield self[i]
+
+    def update(self, key_states: torch.Tensor, value_states: torch.Tensor, layer_idx: int, cache_kwargs=None):
+        """DynamicCache-compatible append of already rotated (B,H,T,D) states (used by foreign callers; the
+        drop-in module writes through reserve()/commit() instead so RoPE and the copy are one kernel)."""
+        n, t = self._len[layer_idx], key_states.shape[2]
+        self.reserve(layer_idx, t)
+        self.k[layer_idx][:, :, n:n + t].copy_(key_states)
+        self.v[layer_idx][:, :, n:n + t].copy_(value_states)
+        self.commit(layer_idx, t)
+        return self[layer_idx]
+
+    # ---- in-place protocol used by AkiMMAAttention -------------------------------------------------
+    def reserve(self, layer_idx: int, t: int) -> int:
+        n = self._len[layer_idx]
+        self._check(n + t)
+        if layer_idx == 0:            # one tiny fill per step; every layer then reads the same device scalar(s)
+            self.kv_len.fill_(n + t)
+        return n
+
+    def commit(self, layer_idx: int, t: int) -> None:
+        self._len[layer_idx] += t
+
+    def _check(self, need: int) -> None:
+        if need > self.t_cap:
+            raise ValueError(f"KV cache capacity {self.t_cap} exceeded (need {need})")
+
+    def to_legacy_cache(self):
+        return tuple(self[i] for i in range(len(self.k)))

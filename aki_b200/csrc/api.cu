@@ -1,0 +1,28 @@
+// Status strings / diagnostics of the C ABI (include/aki_mma.h).
+#include <string.h>
+#include "api_common.cuh"
+
+namespace aki {
+static thread_local char g_last_cuda_error[256] = "";
+void set_last_cuda_error(const char* msg) {
+  strncpy(g_last_cuda_error, msg ? msg : "", sizeof(g_last_cuda_error) - 1);
+  g_last_cuda_error[sizeof(g_last_cuda_error) - 1] = 0;
+}
+}  // namespace aki
+
+extern "C" int aki_mma_abi_version(void) { return AKI_MMA_ABI_VERSION; }
+
+extern "C" const char* aki_mma_strerror(int status) {
+  switch (status) {
+    case AKI_OK: return "ok";
+    case AKI_ERR_NULL: return "required pointer is NULL";
+    case AKI_ERR_BAD_SHAPE: return "bad or inconsistent shape";
+    case AKI_ERR_UNSUPPORTED: return "unsupported configuration (head_dim must be 96; strides multiples of 8 elements)";
+    case AKI_ERR_MISALIGNED: return "pointer not 16-byte aligned";
+    case AKI_ERR_CUDA: return "CUDA error (see aki_mma_last_cuda_error)";
+    case AKI_ERR_NO_DEVICE: return "no sm_100 device";
+    default: return "unknown status";
+  }
+}
+
+extern "C" const char* aki_mma_last_cuda_error(void) { return aki::g_last_cuda_error; }

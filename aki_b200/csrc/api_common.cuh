@@ -1,0 +1,28 @@
+// Shared host-side helpers for the C-ABI entry points.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/aki_mma.h"
+
+namespace aki {
+
+void set_last_cuda_error(const char* msg);
+
+inline int check_launch() {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_last_cuda_error(cudaGetErrorString(e));
+    return AKI_ERR_CUDA;
+  }
+  return AKI_OK;
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+#define AKI_REQUIRE(cond, code) \
+  do {                          \
+    if (!(cond)) return (code); \
+  } while (0)
+
+}  // namespace aki

@@ -1,0 +1,477 @@
+// Modality-mutual attention backward for sm_100a (tcgen05 / TMEM / TMA).
+//
+// Gradient of softmax_fp32(QK^T*scale + mask) V (the eager core of Phi3Attention.forward; installed equivalent
+// transformers/models/phi3/modeling_phi3.py:153-175; the reference obtains it from autograd over five passes
+// on a (B,32,T,T) tensor).  One CTA owns one 128-key tile of one (batch, head) and walks the query tiles that
+// can see it (kv_tile_q_start .. end), with everything transposed so that keys sit on TMEM lanes:
+//     S^T  = K Q_i^T                      (SS)        P^T = exp2(S^T*c - LSE_i)      -> TMEM (bf16, aliases S^T)
+//     dP^T = V dO_i^T                     (SS)        dS^T = P^T o (dP^T - delta_i) * scale -> smem (bf16)
+//     dV  += P^T dO_i                     (TS)
+//     dK  += dS^T Q_i                     (SS, A K-major = dS^T, B MN-major = Q_i)
+//     dQ_i = dS K                         (SS, A MN-major = the same dS^T buffer, B MN-major = K)  -> fp32 red.add
+// dK / dV accumulate in TMEM over the whole loop; dQ_i is drained to a fp32 accumulator in HBM with vector
+// reductions (aki_mma_attn_bwd's finalize kernel applies the inverse RoPE and casts).  The MMA predicate is the
+// same as in the forward, evaluated only on tiles that are not fully visible.
+//
+// 12 warps: 0 TMA producer, 1 MMA issuer, 2 TMEM allocator, 3 idle, 4-11 compute (thread <-> key row r = tid%128;
+// the two warpgroups split the 128 query columns of a tile in halves).
+// TMEM columns: S^T/P^T [0,128)  dP^T/dQ [128,256)  dV [256,352)  dK [352,448).
+// Shared memory: K, V 24 KB each (resident), Q ring 3x24 KB, dO ring 2x24 KB, dS^T 32 KB, per-tile row stats.
+#include <math.h>
+#include "attn_aux.cuh"
+#include "sm100_ptx.cuh"
+
+namespace aki {
+
+namespace bwd {
+constexpr int BN = 128, BM = 128, HD = 96;
+constexpr int ATOM_BYTES = 128 * 64;
+constexpr int TILE_BYTES = 3 * ATOM_BYTES;
+constexpr int Q_STAGES = 3, DO_STAGES = 2;
+constexpr int THREADS = 384;
+constexpr int SMEM_K = 0;
+constexpr int SMEM_V = SMEM_K + TILE_BYTES;
+constexpr int SMEM_Q = SMEM_V + TILE_BYTES;
+constexpr int SMEM_DO = SMEM_Q + Q_STAGES * TILE_BYTES;
+constexpr int SMEM_DS = SMEM_DO + DO_STAGES * TILE_BYTES;   // 4 atoms [128][64 B]
+constexpr int SMEM_STATS = SMEM_DS + 4 * ATOM_BYTES;        // 2 stages x {lse2, delta, lo, hi} x 128 x 4 B
+constexpr int SMEM_TOTAL = SMEM_STATS + 2 * 4 * 128 * 4;
+constexpr int SMEM_ALLOC = SMEM_TOTAL + 1024;
+constexpr uint32_t TM_S = 0, TM_DP = 128, TM_DV = 256, TM_DK = 352;
+constexpr int REGS_CTRL = 64, REGS_COMPUTE = 216;
+}  // namespace bwd
+
+struct BwdKernelParams {
+  TensorView d_k, d_v;
+  const float* lse;
+  const float* delta;
+  float* dq_accum;
+  const float* rope_cos;
+  const float* rope_sin;
+  int64_t rope_stride_b;
+  MaskMeta mm;
+  int B, H, T, n_t;
+  float scale_log2, scale;
+};
+
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ float4 lds_v4(uint32_t addr) {
+  float4 r;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(addr));
+  return r;
+}
+__device__ __forceinline__ int4 lds_v4i(uint32_t addr) {
+  int4 r;
+  asm volatile("ld.shared.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
+  return r;
+}
+
+__global__ void __launch_bounds__(bwd::THREADS, 1)
+attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
+                      const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_do,
+                      const BwdKernelParams P) {
+  using namespace bwd;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  constexpr int KV_FULL = 0, Q_FULL = 1, Q_EMPTY = Q_FULL + Q_STAGES, DO_FULL = Q_EMPTY + Q_STAGES,
+                DO_EMPTY = DO_FULL + DO_STAGES, S_FULL = DO_EMPTY + DO_STAGES, P_READY = S_FULL + 1,
+                DP_FULL = P_READY + 1, DS_READY = DP_FULL + 1, DQ_FULL = DS_READY + 1, DQ_DRAINED = DQ_FULL + 1,
+                N_BARS = DQ_DRAINED + 1;
+  __shared__ __align__(8) uint64_t bars[N_BARS];
+  __shared__ uint32_t tmem_base_s;
+  const uint32_t bar0 = smem_u32(bars);
+  auto BAR = [&](int i) { return bar0 + 8u * i; };
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int bh = blockIdx.x / P.n_t, kt = blockIdx.x % P.n_t;   // key tiles ascending: heaviest first
+  const int b = bh / P.H, h = bh % P.H;
+  const int len = meta_len(P.mm, b, P.T);
+  const int j0 = kt * BN;
+  const int n_qt_live = (len + BM - 1) / BM;                      // query tiles holding at least one live row
+  int q_start = P.mm.kv_tile_q_start ? P.mm.kv_tile_q_start[(size_t)b * P.n_t + kt] : kt;
+  if (j0 >= len) q_start = n_qt_live;
+  const int n_q = max(0, n_qt_live - q_start);
+
+  if (tid == 0) {
+    mbar_init(BAR(KV_FULL), 1);
+    for (int i = 0; i < Q_STAGES; ++i) { mbar_init(BAR(Q_FULL + i), 1); mbar_init(BAR(Q_EMPTY + i), 1); }
+    for (int i = 0; i < DO_STAGES; ++i) { mbar_init(BAR(DO_FULL + i), 1); mbar_init(BAR(DO_EMPTY + i), 1); }
+    mbar_init(BAR(S_FULL), 1); mbar_init(BAR(P_READY), 256); mbar_init(BAR(DP_FULL), 1);
+    mbar_init(BAR(DS_READY), 256); mbar_init(BAR(DQ_FULL), 1); mbar_init(BAR(DQ_DRAINED), 256);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<512>(smem_u32(&tmem_base_s));
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_k); tma_prefetch_desc(&map_v); tma_prefetch_desc(&map_do);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    setmaxnreg_dec<REGS_CTRL>();
+    if (elect_one() && n_q > 0) {
+      mbar_arrive_expect_tx(BAR(KV_FULL), 2 * TILE_BYTES);
+      for (int a = 0; a < 3; ++a) {
+        tma_load_4d(smem_base + SMEM_K + a * ATOM_BYTES, &map_k, BAR(KV_FULL), a * 32, j0, h, b);
+        tma_load_4d(smem_base + SMEM_V + a * ATOM_BYTES, &map_v, BAR(KV_FULL), a * 32, j0, h, b);
+      }
+      for (int it = 0; it < n_q; ++it) {
+        const int i0 = (q_start + it) * BM;
+        const int sq = it % Q_STAGES, sd = it % DO_STAGES;
+        mbar_wait(BAR(Q_EMPTY + sq), ((it / Q_STAGES) & 1) ^ 1);
+        mbar_arrive_expect_tx(BAR(Q_FULL + sq), TILE_BYTES);
+        for (int a = 0; a < 3; ++a)
+          tma_load_4d(smem_base + SMEM_Q + sq * TILE_BYTES + a * ATOM_BYTES, &map_q, BAR(Q_FULL + sq), a * 32, i0, h, b);
+        mbar_wait(BAR(DO_EMPTY + sd), ((it / DO_STAGES) & 1) ^ 1);
+        mbar_arrive_expect_tx(BAR(DO_FULL + sd), TILE_BYTES);
+        for (int a = 0; a < 3; ++a)
+          tma_load_4d(smem_base + SMEM_DO + sd * TILE_BYTES + a * ATOM_BYTES, &map_do, BAR(DO_FULL + sd), a * 32, i0, h, b);
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    setmaxnreg_dec<REGS_CTRL>();
+    if (elect_one() && n_q > 0) {
+      constexpr uint32_t IDESC_SS_KK = umma_idesc_bf16(128, 128, 0, 0);   // S^T, dP^T
+      constexpr uint32_t IDESC_N96_BMN = umma_idesc_bf16(128, 96, 0, 1);  // dV (TS), dK (SS)
+      constexpr uint32_t IDESC_N96_AMN_BMN = umma_idesc_bf16(128, 96, 1, 1);  // dQ
+      const uint32_t sK = smem_base + SMEM_K, sV = smem_base + SMEM_V, sDS = smem_base + SMEM_DS;
+      auto kmajor = [](uint32_t base, int k) {  // 16-element K step k of a [rows][96|128] K-major SW64 tile
+        return umma_smem_desc(base + (k >> 1) * ATOM_BYTES + (k & 1) * 32, 16, 512, UMMA_SW64);
+      };
+      auto mnmajor = [](uint32_t base, int k) {  // 16-row K step k of a tile read as MN-major
+        return umma_smem_desc(base + k * 1024, ATOM_BYTES, 512, UMMA_SW64);
+      };
+      auto issue_s = [&](int it) {
+        const uint32_t sQ = smem_base + SMEM_Q + (it % Q_STAGES) * TILE_BYTES;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) umma_ss(tmem + TM_S, kmajor(sK, k), kmajor(sQ, k), IDESC_SS_KK, k > 0);
+      };
+      auto issue_dp = [&](int it) {
+        const uint32_t sDO = smem_base + SMEM_DO + (it % DO_STAGES) * TILE_BYTES;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) umma_ss(tmem + TM_DP, kmajor(sV, k), kmajor(sDO, k), IDESC_SS_KK, k > 0);
+      };
+      mbar_wait(BAR(KV_FULL), 0);
+      mbar_wait(BAR(Q_FULL + 0), 0);
+      tc_fence_after();
+      issue_s(0);
+      umma_commit(BAR(S_FULL));
+      mbar_wait(BAR(DO_FULL + 0), 0);
+      tc_fence_after();
+      issue_dp(0);
+      umma_commit(BAR(DP_FULL));
+      for (int it = 0; it < n_q; ++it) {
+        const uint32_t sQ = smem_base + SMEM_Q + (it % Q_STAGES) * TILE_BYTES;
+        const uint32_t sDO = smem_base + SMEM_DO + (it % DO_STAGES) * TILE_BYTES;
+        // dV += P^T dO_it
+        mbar_wait(BAR(P_READY), it & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          umma_ts(tmem + TM_DV, tmem + TM_S + 8 * k, mnmajor(sDO, k), IDESC_N96_BMN, (it > 0 || k > 0));
+        umma_commit(BAR(DO_EMPTY + it % DO_STAGES));
+        // S^T of the next query tile (the S region is free once dV has consumed P^T: in-order pipe)
+        if (it + 1 < n_q) {
+          mbar_wait(BAR(Q_FULL + (it + 1) % Q_STAGES), ((it + 1) / Q_STAGES) & 1);
+          tc_fence_after();
+          issue_s(it + 1);
+          umma_commit(BAR(S_FULL));
+        }
+        // dK += dS^T Q_it ;  dQ_it = dS K
+        mbar_wait(BAR(DS_READY), it & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          umma_ss(tmem + TM_DK, kmajor(sDS, k), mnmajor(sQ, k), IDESC_N96_BMN, (it > 0 || k > 0));
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          umma_ss(tmem + TM_DP, mnmajor(sDS, k), mnmajor(sK, k), IDESC_N96_AMN_BMN, k > 0);
+        umma_commit(BAR(DQ_FULL));
+        umma_commit(BAR(Q_EMPTY + it % Q_STAGES));
+        // dP^T of the next query tile overwrites the dQ region: wait until it has been drained
+        if (it + 1 < n_q) {
+          mbar_wait(BAR(DQ_DRAINED), it & 1);
+          mbar_wait(BAR(DO_FULL + (it + 1) % DO_STAGES), ((it + 1) / DO_STAGES) & 1);
+          tc_fence_after();
+          issue_dp(it + 1);
+          umma_commit(BAR(DP_FULL));
+        }
+      }
+    }
+  } else if (warp < 4) {
+    setmaxnreg_dec<REGS_CTRL>();
+  } else {
+    // ------------------------------------------------------------------ compute warps
+    setmaxnreg_inc<REGS_COMPUTE>();
+    const int ct = tid - 128;                 // 0..255
+    const int r = ct & 127;                   // key row within the tile == TMEM lane
+    const int hq = ct >> 7;                   // which half of the query columns / output columns
+    const int j = j0 + r;                     // key index
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    const uint32_t stats = smem_base + SMEM_STATS;
+    const size_t bhT = ((size_t)b * P.H + h) * P.T;
+
+    // key-side predicate bits
+    bool k_valid = (j < len), k_mutual = (j < len);
+    if (j < len && P.mm.vbits) k_valid = (P.mm.vbits[(size_t)b * P.mm.bits_pitch + (j >> 5)] >> (j & 31)) & 1u;
+    if (j < len && P.mm.mbits) k_mutual = (P.mm.mbits[(size_t)b * P.mm.bits_pitch + (j >> 5)] >> (j & 31)) & 1u;
+
+    // per-tile row statistics are fetched one tile ahead into registers, then published to smem
+    float pre_a = 0.f, pre_b = 0.f;           // hq==0: (lse*log2e, delta) ; hq==1: (row_lo, row_hi) as int bits
+    auto prefetch = [&](int it) {
+      const int i = (q_start + it) * BM + r;
+      if (hq == 0) {
+        pre_a = (i < len) ? P.lse[bhT + i] * 1.4426950408889634f : INFINITY;
+        pre_b = (i < len) ? P.delta[bhT + i] : 0.f;
+      } else {
+        int lo = 0, hi = 0;
+        if (i < len && P.mm.row_lo) {
+          lo = P.mm.row_lo[(size_t)b * P.mm.meta_pitch + i];
+          hi = P.mm.row_hi[(size_t)b * P.mm.meta_pitch + i];
+        }
+        pre_a = __int_as_float(lo); pre_b = __int_as_float(hi);
+      }
+    };
+    auto publish = [&](int it) {
+      const uint32_t base = stats + (it & 1) * 2048 + hq * 1024 + r * 4;
+      asm volatile("st.shared.f32 [%0], %1;" ::"r"(base), "f"(pre_a) : "memory");
+      asm volatile("st.shared.f32 [%0], %1;" ::"r"(base + 512), "f"(pre_b) : "memory");
+    };
+
+    float p[64];   // P^T row half, kept from phase a to phase b
+
+    auto phase_a = [&](int it) {
+      publish(it);
+      if (it + 1 < n_q) prefetch(it + 1);
+      named_bar_sync(1, 256);
+      const int qt = q_start + it, i0 = qt * BM;
+      const uint32_t st = stats + (it & 1) * 2048;
+      mbar_wait(BAR(S_FULL), it & 1);
+      tc_fence_after();
+      uint32_t sraw[64];
+      tmem_ld_x32(tmem + TM_S + lane_base + 64 * hq, sraw);
+      tmem_ld_x32(tmem + TM_S + lane_base + 64 * hq + 32, sraw + 32);
+      tmem_wait_ld();
+      // fully visible tile: every key of the tile precedes every (live) query of the tile and is valid
+      const bool full = (qt > kt) && (i0 + BM <= len) && __all_sync(0xffffffffu, k_valid);
+      // NB `full` must be uniform across the 256 threads only for speed, not for correctness
+#pragma unroll
+      for (int c4 = 0; c4 < 16; ++c4) {
+        const float4 l4 = lds_v4(st + (64 * hq + 4 * c4) * 4);
+        const float lse4[4] = {l4.x, l4.y, l4.z, l4.w};
+        int lo4[4] = {0, 0, 0, 0}, hi4[4] = {0, 0, 0, 0};
+        if (!full) {
+          const int4 a4 = lds_v4i(st + 1024 + (64 * hq + 4 * c4) * 4);
+          const int4 e4 = lds_v4i(st + 1536 + (64 * hq + 4 * c4) * 4);
+          lo4[0] = a4.x; lo4[1] = a4.y; lo4[2] = a4.z; lo4[3] = a4.w;
+          hi4[0] = e4.x; hi4[1] = e4.y; hi4[2] = e4.z; hi4[3] = e4.w;
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int c = 4 * c4 + e;
+          float val = ex2_approx(fmaf(__uint_as_float(sraw[c]), P.scale_log2, -lse4[e]));
+          if (!full) {
+            const int i = i0 + 64 * hq + c;
+            const bool ok = (i < len) && ((j <= i && k_valid) || (j >= lo4[e] && j < hi4[e] && k_mutual));
+            val = ok ? val : 0.f;
+          }
+          p[c] = val;
+        }
+      }
+      uint32_t pk[32];
+#pragma unroll
+      for (int x = 0; x < 32; ++x) pk[x] = pack_bf16x2(p[2 * x], p[2 * x + 1]);
+      tmem_st_x32(tmem + TM_S + lane_base + 32 * hq, pk);
+      tmem_wait_st();
+      tc_fence_before();
+      mbar_arrive(BAR(P_READY));
+    };
+
+    auto phase_b = [&](int it) {
+      const uint32_t st = stats + (it & 1) * 2048;
+      mbar_wait(BAR(DP_FULL), it & 1);
+      tc_fence_after();
+      uint32_t draw[64];
+      tmem_ld_x32(tmem + TM_DP + lane_base + 64 * hq, draw);
+      tmem_ld_x32(tmem + TM_DP + lane_base + 64 * hq + 32, draw + 32);
+      tmem_wait_ld();
+      const uint32_t ds_base = smem_base + SMEM_DS;
+#pragma unroll
+      for (int c8 = 0; c8 < 8; ++c8) {   // 8 query columns -> one 16-byte chunk of the dS^T row
+        const float4 d0 = lds_v4(st + 512 + (64 * hq + 8 * c8) * 4);
+        const float4 d1 = lds_v4(st + 512 + (64 * hq + 8 * c8 + 4) * 4);
+        const float dl[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+        uint32_t w[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int c = 8 * c8 + 2 * e;
+          const float ds0 = p[c] * (__uint_as_float(draw[c]) - dl[2 * e]) * P.scale;
+          const float ds1 = p[c + 1] * (__uint_as_float(draw[c + 1]) - dl[2 * e + 1]) * P.scale;
+          w[e] = pack_bf16x2(ds0, ds1);
+        }
+        const int col = 64 * hq + 8 * c8;          // query column of this chunk
+        const uint32_t addr = ds_base + (col >> 5) * ATOM_BYTES + sw64_offset(r, (col & 31) >> 3);
+        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(BAR(DS_READY));
+    };
+
+    auto phase_c = [&](int it) {   // drain dQ_it: lane r is now QUERY row r of the tile; this half owns 48 columns
+      const int i = (q_start + it) * BM + r;
+      mbar_wait(BAR(DQ_FULL), it & 1);
+      tc_fence_after();
+      uint32_t dq[48];
+      tmem_ld_x32(tmem + TM_DP + lane_base + 48 * hq, dq);
+      tmem_ld_x16(tmem + TM_DP + lane_base + 48 * hq + 32, dq + 32);
+      tmem_wait_ld();
+      tc_fence_before();
+      mbar_arrive(BAR(DQ_DRAINED));
+      if (i < len) {
+        float* dst = P.dq_accum + (bhT + i) * HD + 48 * hq;
+#pragma unroll
+        for (int x = 0; x < 12; ++x)
+          red_add_v4(dst + 4 * x, __uint_as_float(dq[4 * x]), __uint_as_float(dq[4 * x + 1]),
+                     __uint_as_float(dq[4 * x + 2]), __uint_as_float(dq[4 * x + 3]));
+      }
+    };
+
+    if (n_q > 0) {
+      prefetch(0);
+      phase_a(0);
+      for (int it = 0; it < n_q; ++it) {
+        phase_b(it);
+        if (it + 1 < n_q) phase_a(it + 1);
+        phase_c(it);
+      }
+    }
+
+    // ---- epilogue: dV, dK (inverse RoPE) -> bf16 -> global.  tcgen05.ld is warp-collective: the loads are
+    // unconditional, only the global stores are predicated on the row being inside the tensor.
+    {
+      const bool store_row = (j < P.T);
+      const int js = store_row ? j : 0;
+      __nv_bfloat16* dvrow = P.d_v.row(b, js, h) + 48 * hq;
+      __nv_bfloat16* dkrow = P.d_k.row(b, js, h);
+      if (n_q > 0) {
+        // DQ_FULL of the last iteration was committed after the last dK MMA (and dV before it): already waited
+        uint32_t acc[48];
+        tmem_ld_x32(tmem + TM_DV + lane_base + 48 * hq, acc);
+        tmem_ld_x16(tmem + TM_DV + lane_base + 48 * hq + 32, acc + 32);
+        tmem_wait_ld();
+#pragma unroll
+        for (int x = 0; x < 6; ++x) {
+          uint4 u;
+          u.x = pack_bf16x2(__uint_as_float(acc[8 * x]), __uint_as_float(acc[8 * x + 1]));
+          u.y = pack_bf16x2(__uint_as_float(acc[8 * x + 2]), __uint_as_float(acc[8 * x + 3]));
+          u.z = pack_bf16x2(__uint_as_float(acc[8 * x + 4]), __uint_as_float(acc[8 * x + 5]));
+          u.w = pack_bf16x2(__uint_as_float(acc[8 * x + 6]), __uint_as_float(acc[8 * x + 7]));
+          if (store_row) *reinterpret_cast<uint4*>(dvrow + 8 * x) = u;
+        }
+        // dK: this half owns columns [24hq, 24hq+24) and their RoPE partners [48+24hq, 48+24hq+24)
+        uint32_t lo[24], hi[24];
+        tmem_ld_x16(tmem + TM_DK + lane_base + 24 * hq, lo);
+        tmem_ld_x8(tmem + TM_DK + lane_base + 24 * hq + 16, *reinterpret_cast<uint32_t(*)[8]>(lo + 16));
+        tmem_ld_x16(tmem + TM_DK + lane_base + 48 + 24 * hq, hi);
+        tmem_ld_x8(tmem + TM_DK + lane_base + 48 + 24 * hq + 16, *reinterpret_cast<uint32_t(*)[8]>(hi + 16));
+        tmem_wait_ld();
+        float flo[24], fhi[24];
+#pragma unroll
+        for (int x = 0; x < 24; ++x) {
+          float a = __uint_as_float(lo[x]), e = __uint_as_float(hi[x]);
+          if (P.rope_cos) {   // g = R^T g'
+            const float c = __ldg(P.rope_cos + (size_t)b * P.rope_stride_b + (size_t)js * 48 + 24 * hq + x);
+            const float sn = __ldg(P.rope_sin + (size_t)b * P.rope_stride_b + (size_t)js * 48 + 24 * hq + x);
+            const float a2 = a * c + e * sn, e2 = e * c - a * sn;
+            a = a2; e = e2;
+          }
+          flo[x] = a; fhi[x] = e;
+        }
+#pragma unroll
+        for (int x = 0; x < 3; ++x) {
+          uint4 u, w;
+          u.x = pack_bf16x2(flo[8 * x], flo[8 * x + 1]); u.y = pack_bf16x2(flo[8 * x + 2], flo[8 * x + 3]);
+          u.z = pack_bf16x2(flo[8 * x + 4], flo[8 * x + 5]); u.w = pack_bf16x2(flo[8 * x + 6], flo[8 * x + 7]);
+          w.x = pack_bf16x2(fhi[8 * x], fhi[8 * x + 1]); w.y = pack_bf16x2(fhi[8 * x + 2], fhi[8 * x + 3]);
+          w.z = pack_bf16x2(fhi[8 * x + 4], fhi[8 * x + 5]); w.w = pack_bf16x2(fhi[8 * x + 6], fhi[8 * x + 7]);
+          if (store_row) {
+            *reinterpret_cast<uint4*>(dkrow + 24 * hq + 8 * x) = u;
+            *reinterpret_cast<uint4*>(dkrow + 48 + 24 * hq + 8 * x) = w;
+          }
+        }
+      } else if (store_row) {
+        const uint4 z = make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int x = 0; x < 6; ++x) *reinterpret_cast<uint4*>(dvrow + 8 * x) = z;
+#pragma unroll
+        for (int x = 0; x < 3; ++x) {
+          *reinterpret_cast<uint4*>(dkrow + 24 * hq + 8 * x) = z;
+          *reinterpret_cast<uint4*>(dkrow + 48 + 24 * hq + 8 * x) = z;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<512>(tmem);
+}
+
+}  // namespace aki
+
+using namespace aki;
+
+extern "C" int aki_mma_attn_bwd(const AkiMmaAttnBwdParams* p, aki_stream_t stream) {
+  AKI_REQUIRE(p, AKI_ERR_NULL);
+  const AkiMmaAttnParams& f = p->fwd;
+  int rc = check_attn_params(f);
+  if (rc) return rc;
+  if ((rc = check_tensor(p->d_o)) || (rc = check_tensor(p->d_q)) || (rc = check_tensor(p->d_k)) ||
+      (rc = check_tensor(p->d_v)))
+    return rc;
+  AKI_REQUIRE(f.lse && p->workspace, AKI_ERR_NULL);
+  AKI_REQUIRE(p->workspace_bytes >= aki_mma_attn_bwd_workspace_bytes(f.B, f.H, f.T, f.D), AKI_ERR_BAD_SHAPE);
+  AKI_REQUIRE((reinterpret_cast<uintptr_t>(p->workspace) & 255u) == 0, AKI_ERR_MISALIGNED);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  BwdWorkspace w = carve_bwd_workspace(p->workspace, f.B, f.H, f.T, f.D);
+  if ((rc = launch_bwd_preprocess(*p, w, st))) return rc;
+  if (cudaMemsetAsync(w.dq_accum, 0, (size_t)f.B * f.H * f.T * f.D * sizeof(float), st) != cudaSuccess) {
+    set_last_cuda_error(cudaGetErrorString(cudaGetLastError()));
+    return AKI_ERR_CUDA;
+  }
+  AkiMmaTensor4 qrot{w.q_rot, (int64_t)f.H * f.T * f.D, (int64_t)f.D, (int64_t)f.T * f.D};
+  CUtensorMap mq, mk, mv, mdo;
+  if ((rc = make_tile_map(&mq, qrot, f.B, f.H, f.T, bwd::BM))) return rc;
+  if ((rc = make_tile_map(&mk, f.k, f.B, f.H, f.T, bwd::BN))) return rc;
+  if ((rc = make_tile_map(&mv, f.v, f.B, f.H, f.T, bwd::BN))) return rc;
+  if ((rc = make_tile_map(&mdo, p->d_o, f.B, f.H, f.T, bwd::BM))) return rc;
+  BwdKernelParams kp;
+  kp.d_k = view_of(p->d_k); kp.d_v = view_of(p->d_v);
+  kp.lse = f.lse; kp.delta = w.delta; kp.dq_accum = w.dq_accum;
+  kp.rope_cos = f.rope_cos; kp.rope_sin = f.rope_sin; kp.rope_stride_b = f.rope_stride_b;
+  kp.mm = mask_meta_from(f);
+  kp.B = f.B; kp.H = f.H; kp.T = f.T;
+  kp.n_t = (f.T + bwd::BN - 1) / bwd::BN;
+  kp.scale = f.scale;
+  kp.scale_log2 = f.scale * 1.4426950408889634f;
+  const long long grid = (long long)kp.n_t * f.H * f.B;
+  AKI_REQUIRE(grid > 0 && grid < (1ll << 31), AKI_ERR_BAD_SHAPE);
+  static bool attr_done = false;
+  if (!attr_done) {
+    if (cudaFuncSetAttribute(attn_bwd_sm100_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd::SMEM_ALLOC) !=
+        cudaSuccess) {
+      set_last_cuda_error(cudaGetErrorString(cudaGetLastError()));
+      return AKI_ERR_CUDA;
+    }
+    attr_done = true;
+  }
+  attn_bwd_sm100_kernel<<<(unsigned)grid, bwd::THREADS, bwd::SMEM_ALLOC, st>>>(mq, mk, mv, mdo, kp);
+  if ((rc = check_launch())) return rc;
+  return launch_dq_finalize(*p, w, st);
+}

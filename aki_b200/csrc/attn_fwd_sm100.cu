@@ -1,0 +1,439 @@
+// Modality-mutual attention forward for sm_100a: QK^T, online softmax and PV on tcgen05 tensor cores with
+// TMEM accumulators, operands staged by TMA, mbarrier pipelines, warp-specialised roles.
+//
+// Replaces the eager core of Phi3Attention.forward (softmax_fp32(QK^T/sqrt(96) + mask) V; installed
+// equivalent transformers/models/phi3/modeling_phi3.py:153-175) fed by the reference's materialised
+// (B,1,T,T) mask (codes/open_flamingo/src/vlm.py:410-443).  No mask is read from HBM: the predicate
+//   allowed(i,j) = (j<=i & valid[j]) | (row_lo[i]<=j<row_hi[i] & mutual_ok[j])
+// is evaluated in registers on the few tiles that are not fully visible, and tiles beyond
+// q_tile_kv_end[b][qt] are never visited.  RoPE is applied to Q in shared memory right after the TMA load.
+//
+// CTA = 2 query tiles x 128 rows of one (batch, head); 12 warps:
+//   warp 0      TMA producer (Q once, then K_j / V_j through two 3-deep rings)
+//   warp 1      MMA issuer (one elected lane): S_t = Q_t K_j^T (SS), O_t += P_t V_j (TS, P read from TMEM)
+//   warp 2      TMEM allocator;   warp 3 idle
+//   warps 4-7   softmax of tile 0 (thread r <-> row r <-> TMEM lane r)
+//   warps 8-11  softmax of tile 1
+// TMEM columns: S0 [0,128) S1 [128,256) O0 [256,352) O1 [352,448); P_t (bf16 pairs) aliases S_t[0,64).
+// Shared memory: Q 2x24 KB, K ring 3x24 KB, V ring 3x24 KB; every tile is 3 SWIZZLE_64B atoms [128][64 B]
+// (head_dim 96 = 3 x 32), the layout both the TMA boxes and the UMMA descriptors use (validated by
+// tools/umma_probe.cu).
+#include <math.h>
+#include "attn_aux.cuh"
+#include "sm100_ptx.cuh"
+
+namespace aki {
+
+namespace fwd {
+constexpr int BM = 128, BN = 128, HD = 96;
+constexpr int ATOM_BYTES = 128 * 64;
+constexpr int TILE_BYTES = 3 * ATOM_BYTES;  // 24576
+constexpr int STAGES = 3;
+constexpr int THREADS = 384;
+constexpr int SMEM_Q = 0;
+constexpr int SMEM_K = SMEM_Q + 2 * TILE_BYTES;
+constexpr int SMEM_V = SMEM_K + STAGES * TILE_BYTES;
+constexpr int SMEM_TOTAL = SMEM_V + STAGES * TILE_BYTES;  // 196608
+constexpr int SMEM_ALLOC = SMEM_TOTAL + 1024;             // slack for 1024-byte alignment
+constexpr uint32_t TM_S0 = 0, TM_S1 = 128, TM_O0 = 256, TM_O1 = 352;
+constexpr int REGS_CTRL = 64, REGS_SOFTMAX = 216;  // setmaxnreg budgets: 128*64 + 256*216 = 63488 <= 65536
+constexpr float RESCALE_THRESHOLD = 8.0f;  // log2 units: P may grow to 2^8 before O is rescaled
+}  // namespace fwd
+
+struct FwdKernelParams {
+  TensorView q, o;
+  float* lse;
+  const float* rope_cos;
+  const float* rope_sin;
+  int64_t rope_stride_b;
+  MaskMeta mm;
+  int B, H, T, n_qt, n_qp;
+  float scale_log2, scale;
+};
+
+__device__ __forceinline__ uint32_t low_mask(int n) {  // n low bits set, n clamped to [0,32]
+  return n <= 0 ? 0u : (n >= 32 ? 0xffffffffu : ((1u << n) - 1u));
+}
+
+template <bool ROPE>
+__global__ void __launch_bounds__(fwd::THREADS, 1)
+attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
+                      const __grid_constant__ CUtensorMap map_v, const FwdKernelParams P) {
+  using namespace fwd;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  __shared__ __align__(8) uint64_t bars[2 + 2 + 4 * STAGES + 6];
+  __shared__ uint32_t tmem_base_s;
+  const uint32_t bar0 = smem_u32(bars);
+  auto BAR = [&](int i) { return bar0 + 8u * i; };
+  // barrier indices
+  constexpr int Q_FULL = 0, Q_READY = 2, K_FULL = 4, K_EMPTY = K_FULL + STAGES, V_FULL = K_EMPTY + STAGES,
+                V_EMPTY = V_FULL + STAGES, S_FULL = V_EMPTY + STAGES, P_FULL = S_FULL + 2, O_FULL = P_FULL + 2;
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  // work decomposition: consecutive CTAs share (b,h) so K/V stay in L2; heaviest query tiles first
+  const int bh = blockIdx.x / P.n_qp;
+  const int qp = P.n_qp - 1 - (blockIdx.x % P.n_qp);
+  const int b = bh / P.H, h = bh % P.H;
+  const int n_kt = (P.T + BN - 1) / BN;
+  int n_kv[2];
+#pragma unroll
+  for (int t = 0; t < 2; ++t) {
+    const int qt = 2 * qp + t;
+    if (qt >= P.n_qt) n_kv[t] = 0;
+    else if (P.mm.q_tile_kv_end) n_kv[t] = min(P.mm.q_tile_kv_end[(size_t)b * P.n_qt + qt], n_kt);
+    else n_kv[t] = min(qt + 1, n_kt);
+  }
+  const int n_max = max(n_kv[0], n_kv[1]);
+
+  if (tid == 0) {
+    for (int i = 0; i < 2; ++i) { mbar_init(BAR(Q_FULL + i), 1); mbar_init(BAR(Q_READY + i), 128); }
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(BAR(K_FULL + i), 1); mbar_init(BAR(K_EMPTY + i), 1);
+      mbar_init(BAR(V_FULL + i), 1); mbar_init(BAR(V_EMPTY + i), 1);
+    }
+    for (int i = 0; i < 2; ++i) { mbar_init(BAR(S_FULL + i), 1); mbar_init(BAR(P_FULL + i), 128); mbar_init(BAR(O_FULL + i), 1); }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<512>(smem_u32(&tmem_base_s));
+  if (warp == 0 && elect_one()) { tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_k); tma_prefetch_desc(&map_v); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    setmaxnreg_dec<REGS_CTRL>();
+    if (elect_one()) {
+      for (int t = 0; t < 2; ++t) {
+        if (n_kv[t] == 0) continue;
+        mbar_arrive_expect_tx(BAR(Q_FULL + t), TILE_BYTES);
+        for (int a = 0; a < 3; ++a)
+          tma_load_4d(smem_base + SMEM_Q + t * TILE_BYTES + a * ATOM_BYTES, &map_q, BAR(Q_FULL + t), a * 32,
+                      (2 * qp + t) * BM, h, b);
+      }
+      for (int j = 0; j < n_max; ++j) {
+        const int s = j % STAGES;
+        const uint32_t ph = (j / STAGES) & 1;
+        mbar_wait(BAR(K_EMPTY + s), ph ^ 1);
+        mbar_arrive_expect_tx(BAR(K_FULL + s), TILE_BYTES);
+        for (int a = 0; a < 3; ++a)
+          tma_load_4d(smem_base + SMEM_K + s * TILE_BYTES + a * ATOM_BYTES, &map_k, BAR(K_FULL + s), a * 32, j * BN, h, b);
+        mbar_wait(BAR(V_EMPTY + s), ph ^ 1);
+        mbar_arrive_expect_tx(BAR(V_FULL + s), TILE_BYTES);
+        for (int a = 0; a < 3; ++a)
+          tma_load_4d(smem_base + SMEM_V + s * TILE_BYTES + a * ATOM_BYTES, &map_v, BAR(V_FULL + s), a * 32, j * BN, h, b);
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    setmaxnreg_dec<REGS_CTRL>();
+    if (elect_one()) {
+      constexpr uint32_t IDESC_QK = umma_idesc_bf16(BM, BN, 0, 0);
+      constexpr uint32_t IDESC_PV = umma_idesc_bf16(BM, HD, 0, 1);
+      const uint32_t tm_s[2] = {tmem + TM_S0, tmem + TM_S1};
+      const uint32_t tm_o[2] = {tmem + TM_O0, tmem + TM_O1};
+      auto issue_qk = [&](int t, int j) {
+        const uint32_t qa = smem_base + SMEM_Q + t * TILE_BYTES;
+        const uint32_t ka = smem_base + SMEM_K + (j % STAGES) * TILE_BYTES;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+          const uint32_t off = (k >> 1) * ATOM_BYTES + (k & 1) * 32;
+          umma_ss(tm_s[t], umma_smem_desc(qa + off, 16, 512, UMMA_SW64), umma_smem_desc(ka + off, 16, 512, UMMA_SW64),
+                  IDESC_QK, k > 0);
+        }
+      };
+      auto issue_pv = [&](int t, int j) {
+        const uint32_t va = smem_base + SMEM_V + (j % STAGES) * TILE_BYTES;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          umma_ts(tm_o[t], tm_s[t] + 8 * k, umma_smem_desc(va + k * 1024, ATOM_BYTES, 512, UMMA_SW64), IDESC_PV,
+                  (j > 0 || k > 0));
+      };
+      for (int t = 0; t < 2; ++t)
+        if (n_kv[t] > 0) mbar_wait(BAR((ROPE ? Q_READY : Q_FULL) + t), 0);
+      if (n_max > 0) {
+        mbar_wait(BAR(K_FULL + 0), 0);
+        tc_fence_after();
+        for (int t = 0; t < 2; ++t)
+          if (n_kv[t] > 0) { issue_qk(t, 0); umma_commit(BAR(S_FULL + t)); }
+        umma_commit(BAR(K_EMPTY + 0));
+      }
+      for (int j = 0; j < n_max; ++j) {
+        const int sv = j % STAGES;
+        bool v_waited = false;
+        for (int t = 0; t < 2; ++t) {
+          if (j >= n_kv[t]) continue;
+          mbar_wait(BAR(P_FULL + t), j & 1);
+          if (!v_waited) { mbar_wait(BAR(V_FULL + sv), (j / STAGES) & 1); v_waited = true; }
+          tc_fence_after();
+          issue_pv(t, j);
+          umma_commit(BAR(O_FULL + t));
+          const bool last_v = (t == 1) || (j >= n_kv[1]);
+          if (last_v) umma_commit(BAR(V_EMPTY + sv));
+          const int jn = j + 1;
+          if (jn < n_kv[t]) {
+            const bool first_k = (t == 0) || (jn >= n_kv[0]);
+            const bool last_k = (t == 1) || (jn >= n_kv[1]);
+            if (first_k) { mbar_wait(BAR(K_FULL + jn % STAGES), (jn / STAGES) & 1); tc_fence_after(); }
+            issue_qk(t, jn);
+            umma_commit(BAR(S_FULL + t));
+            if (last_k) umma_commit(BAR(K_EMPTY + jn % STAGES));
+          }
+        }
+      }
+    }
+  } else if (warp < 4) {
+    setmaxnreg_dec<REGS_CTRL>();
+  } else {
+    // ------------------------------------------------------------------ softmax / correction / epilogue
+    setmaxnreg_inc<REGS_SOFTMAX>();
+    const int t = (warp - 4) >> 2;
+    const int r = tid - 128 - t * 128;           // row within the tile == TMEM lane
+    const int qt = 2 * qp + t;
+    const int i = qt * BM + r;                    // query index in mask coordinates
+    const int len = meta_len(P.mm, b, P.T);
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    const uint32_t tm_s = tmem + (t ? TM_S1 : TM_S0) + lane_base;
+    const uint32_t tm_o = tmem + (t ? TM_O1 : TM_O0) + lane_base;
+    const int nk = n_kv[t];
+
+    if (ROPE && nk > 0) {
+      mbar_wait(BAR(Q_FULL + t), 0);
+      if (i < P.T) {
+        const uint32_t qa = smem_base + SMEM_Q + t * TILE_BYTES;
+        const float* cr = P.rope_cos + (size_t)b * P.rope_stride_b + (size_t)i * 48;
+        const float* sr = P.rope_sin + (size_t)b * P.rope_stride_b + (size_t)i * 48;
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+          const uint32_t a_lo = qa + (c >> 2) * ATOM_BYTES + sw64_offset(r, c & 3);
+          const uint32_t a_hi = qa + ((c + 6) >> 2) * ATOM_BYTES + sw64_offset(r, (c + 6) & 3);
+          uint4 lo, hi;
+          asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w) : "r"(a_lo));
+          asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w) : "r"(a_hi));
+          float cs[8], sn[8];
+          *reinterpret_cast<float4*>(cs) = __ldg(reinterpret_cast<const float4*>(cr + c * 8));
+          *reinterpret_cast<float4*>(cs + 4) = __ldg(reinterpret_cast<const float4*>(cr + c * 8 + 4));
+          *reinterpret_cast<float4*>(sn) = __ldg(reinterpret_cast<const float4*>(sr + c * 8));
+          *reinterpret_cast<float4*>(sn + 4) = __ldg(reinterpret_cast<const float4*>(sr + c * 8 + 4));
+          const __nv_bfloat162* l2 = reinterpret_cast<const __nv_bfloat162*>(&lo);
+          const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&hi);
+          uint4 lo_o, hi_o;
+          uint32_t* lo_w = reinterpret_cast<uint32_t*>(&lo_o);
+          uint32_t* hi_w = reinterpret_cast<uint32_t*>(&hi_o);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 lf = __bfloat1622float2(l2[e]), hf = __bfloat1622float2(h2[e]);
+            lo_w[e] = pack_bf16x2(lf.x * cs[2 * e] - hf.x * sn[2 * e], lf.y * cs[2 * e + 1] - hf.y * sn[2 * e + 1]);
+            hi_w[e] = pack_bf16x2(hf.x * cs[2 * e] + lf.x * sn[2 * e], hf.y * cs[2 * e + 1] + lf.y * sn[2 * e + 1]);
+          }
+          asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a_lo), "r"(lo_o.x), "r"(lo_o.y), "r"(lo_o.z), "r"(lo_o.w) : "memory");
+          asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a_hi), "r"(hi_o.x), "r"(hi_o.y), "r"(hi_o.z), "r"(hi_o.w) : "memory");
+        }
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(BAR(Q_READY + t));
+    }
+
+    int row_lo = 0, row_hi = 0;
+    const bool row_live = (i < len);
+    if (row_live && P.mm.row_lo) {
+      row_lo = P.mm.row_lo[(size_t)b * P.mm.meta_pitch + i];
+      row_hi = P.mm.row_hi[(size_t)b * P.mm.meta_pitch + i];
+    }
+    float m_used = -INFINITY;  // running max (raw score units) the accumulators are expressed against
+    float l = 0.f;
+
+    for (int j = 0; j < nk; ++j) {
+      mbar_wait(BAR(S_FULL + t), j & 1);
+      tc_fence_after();
+      float s[128];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tmem_ld_x32(tm_s + 32 * c, reinterpret_cast<uint32_t*>(s) + 32 * c);
+      tmem_wait_ld();
+
+      // ---- tile classification (warp-uniform): fully visible tiles skip the predicate
+      const int j0 = j * BN;
+      uint32_t vw[4], mw[4];
+      bool full = (j < qt) && (j0 + BN <= len);
+#pragma unroll
+      for (int w = 0; w < 4; ++w) {
+        const int jw = j0 + 32 * w;
+        const uint32_t in_len = low_mask(len - jw);
+        vw[w] = P.mm.vbits ? (__ldg(P.mm.vbits + (size_t)b * P.mm.bits_pitch + (jw >> 5)) & in_len) : in_len;
+        mw[w] = P.mm.mbits ? (__ldg(P.mm.mbits + (size_t)b * P.mm.bits_pitch + (jw >> 5)) & in_len) : in_len;
+        full = full && (vw[w] == 0xffffffffu);
+      }
+      if (!full) {
+        const int d = row_live ? (i - j0) : -1;             // causal: column c visible iff c <= d
+        const int a = row_lo - j0, e = row_hi - j0;         // mutual: a <= c < e
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+          const uint32_t causal = low_mask(d + 1 - 32 * w) & vw[w];
+          const uint32_t mutual = row_live ? (low_mask(e - 32 * w) & ~low_mask(a - 32 * w) & mw[w]) : 0u;
+          const uint32_t ok = causal | mutual;
+#pragma unroll
+          for (int c = 0; c < 32; ++c)
+            if (!((ok >> c) & 1u)) s[32 * w + c] = -INFINITY;
+        }
+      }
+      float mx0 = s[0], mx1 = s[1], mx2 = s[2], mx3 = s[3];
+#pragma unroll
+      for (int c = 4; c < 128; c += 4) {
+        mx0 = fmaxf(mx0, s[c]); mx1 = fmaxf(mx1, s[c + 1]); mx2 = fmaxf(mx2, s[c + 2]); mx3 = fmaxf(mx3, s[c + 3]);
+      }
+      const float m_new = fmaxf(m_used, fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)));
+      // ---- lazy rescale of O (correction merged into the softmax warps; rare after the first tiles)
+      if (j == 0) {
+        m_used = m_new;
+      } else {
+        const bool need = (m_new - m_used) * P.scale_log2 > RESCALE_THRESHOLD || (m_used == -INFINITY && m_new > -INFINITY);
+        if (__any_sync(0xffffffffu, need)) {
+          const float alpha = (m_used == -INFINITY) ? 0.f : ex2_approx((m_used - m_new) * P.scale_log2);
+          m_used = m_new;
+          l *= alpha;
+          mbar_wait(BAR(O_FULL + t), (j - 1) & 1);
+          tc_fence_after();
+          uint32_t o[32];
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            tmem_ld_x32(tm_o + 32 * c, o);
+            tmem_wait_ld();
+#pragma unroll
+            for (int x = 0; x < 32; ++x) o[x] = __float_as_uint(__uint_as_float(o[x]) * alpha);
+            tmem_st_x32(tm_o + 32 * c, o);
+          }
+          tmem_wait_st();
+        }
+      }
+      // ---- P = exp2((S - m) * scale*log2e), row sum, bf16 pack, store to TMEM (aliases S)
+      const float neg_m = (m_used == -INFINITY) ? 0.f : -m_used * P.scale_log2;
+      float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int x = 0; x < 16; ++x) {
+          const float p0 = ex2_approx(fmaf(s[32 * c + 2 * x], P.scale_log2, neg_m));
+          const float p1 = ex2_approx(fmaf(s[32 * c + 2 * x + 1], P.scale_log2, neg_m));
+          sum0 += p0; sum1 += p1;
+          pk[x] = pack_bf16x2(p0, p1);
+        }
+        tmem_st_x16(tm_s + 16 * c, pk);
+      }
+      l += sum0 + sum1;
+      tmem_wait_st();
+      tc_fence_before();
+      mbar_arrive(BAR(P_FULL + t));
+    }
+
+    // ---- epilogue: O / l -> bf16 -> global; LSE
+    if (qt < P.n_qt) {
+      float inv_l = 0.f;
+      if (nk > 0) {
+        mbar_wait(BAR(O_FULL + t), (nk - 1) & 1);
+        tc_fence_after();
+        inv_l = (row_live && l > 0.f) ? 1.f / l : 0.f;  // batch-padding rows: zeros
+      }
+      // tcgen05.ld is warp-collective (.sync.aligned): load unconditionally, predicate only the global stores
+      const bool store_row = (i < P.T);
+      {
+        __nv_bfloat16* orow = P.o.row(b, store_row ? i : 0, h);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          uint32_t o[32];
+          if (nk > 0) {
+            tmem_ld_x32(tm_o + 32 * c, o);
+            tmem_wait_ld();
+          }
+#pragma unroll
+          for (int x = 0; x < 4; ++x) {
+            uint4 u;
+            uint32_t* w = reinterpret_cast<uint32_t*>(&u);
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              w[e] = (inv_l > 0.f) ? pack_bf16x2(__uint_as_float(o[8 * x + 2 * e]) * inv_l,
+                                                   __uint_as_float(o[8 * x + 2 * e + 1]) * inv_l)
+                                   : 0u;
+            if (store_row) *reinterpret_cast<uint4*>(orow + 32 * c + 8 * x) = u;
+          }
+        }
+        if (P.lse && store_row)
+          P.lse[((size_t)b * P.H + h) * P.T + i] = (inv_l > 0.f) ? (m_used * P.scale + __logf(l)) : INFINITY;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<512>(tmem);
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = []() -> EncodeTiledFn {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess) return nullptr;
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+
+// (D=96, T, H, B) bf16 view -> tensor map with [32 x 128 x 1 x 1] SWIZZLE_64B boxes
+int make_tile_map(CUtensorMap* m, const AkiMmaTensor4& t, int B, int H, int T, int box_rows) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) { set_last_cuda_error("cuTensorMapEncodeTiled entry point not found"); return AKI_ERR_CUDA; }
+  cuuint64_t dims[4] = {96, (cuuint64_t)T, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)t.stride_t * 2, (cuuint64_t)t.stride_h * 2, (cuuint64_t)t.stride_b * 2};
+  cuuint32_t box[4] = {32, (cuuint32_t)box_rows, 1, 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, t.ptr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_last_cuda_error("cuTensorMapEncodeTiled failed"); return AKI_ERR_CUDA; }
+  return AKI_OK;
+}
+
+}  // namespace aki
+
+using namespace aki;
+
+extern "C" int aki_mma_attn_fwd(const AkiMmaAttnParams* p, aki_stream_t stream) {
+  AKI_REQUIRE(p, AKI_ERR_NULL);
+  int rc = check_attn_params(*p);
+  if (rc) return rc;
+  CUtensorMap mq, mk, mv;
+  if ((rc = make_tile_map(&mq, p->q, p->B, p->H, p->T, fwd::BM))) return rc;
+  if ((rc = make_tile_map(&mk, p->k, p->B, p->H, p->T, fwd::BN))) return rc;
+  if ((rc = make_tile_map(&mv, p->v, p->B, p->H, p->T, fwd::BN))) return rc;
+  FwdKernelParams kp;
+  kp.q = view_of(p->q); kp.o = view_of(p->o);
+  kp.lse = p->lse; kp.rope_cos = p->rope_cos; kp.rope_sin = p->rope_sin; kp.rope_stride_b = p->rope_stride_b;
+  kp.mm = mask_meta_from(*p);
+  kp.B = p->B; kp.H = p->H; kp.T = p->T;
+  kp.n_qt = (p->T + fwd::BM - 1) / fwd::BM;
+  kp.n_qp = (kp.n_qt + 1) / 2;
+  kp.scale = p->scale;
+  kp.scale_log2 = p->scale * 1.4426950408889634f;
+  const long long grid = (long long)kp.n_qp * p->H * p->B;
+  AKI_REQUIRE(grid > 0 && grid < (1ll << 31), AKI_ERR_BAD_SHAPE);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  static bool attr_done = false;
+  if (!attr_done) {
+    if (cudaFuncSetAttribute(attn_fwd_sm100_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd::SMEM_ALLOC) != cudaSuccess ||
+        cudaFuncSetAttribute(attn_fwd_sm100_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd::SMEM_ALLOC) != cudaSuccess) {
+      set_last_cuda_error(cudaGetErrorString(cudaGetLastError()));
+      return AKI_ERR_CUDA;
+    }
+    attr_done = true;
+  }
+  if (p->rope_cos)
+    attn_fwd_sm100_kernel<true><<<(unsigned)grid, fwd::THREADS, fwd::SMEM_ALLOC, st>>>(mq, mk, mv, kp);
+  else
+    attn_fwd_sm100_kernel<false><<<(unsigned)grid, fwd::THREADS, fwd::SMEM_ALLOC, st>>>(mq, mk, mv, kp);
+  return check_launch();
+}

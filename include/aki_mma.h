@@ -1,0 +1,186 @@
+/* aki_mma.h -- C ABI of libaki_mma.so: B200 (sm_100a) kernels for AKI's modality-mutual attention (MMA).
+ *
+ * This is the drop-in boundary for the one hot path of sony/aki: the attention inside the Phi-3.5-mini
+ * decoder layers, where the reference materialises a (B,1,T,T) int64 0/1 mask
+ * (codes/open_flamingo/src/vlm.py:410-443, :445-603; utils.py:99-108), has transformers 4.41.2 turn it into
+ * an additive fp32 mask and runs eager softmax(QK^T/sqrt(96) + mask) V (Phi-3 remote code).  Every entry
+ * point below names the reference interface it replaces.
+ *
+ * Conventions
+ *   - plain pointers + sizes; every pointer is a DEVICE pointer unless stated otherwise.
+ *   - the caller allocates every buffer (outputs, workspace); the library never allocates or frees device
+ *     memory and never synchronises the device.  All work is enqueued on `stream` (a cudaStream_t).
+ *   - return value: AKI_OK (0) or a negative AkiStatus; no exceptions, no abort, no stdout.
+ *   - stateless and re-entrant; one process per GPU.
+ *   - bf16 tensors have a contiguous last dimension; strides are in ELEMENTS.
+ *   - head_dim must be 96 (Phi-3.5-mini: 32 heads x 96); anything else returns AKI_ERR_UNSUPPORTED.
+ */
+#ifndef AKI_MMA_H_
+#define AKI_MMA_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AKI_MMA_ABI_VERSION 1
+#define AKI_MMA_HEAD_DIM 96
+#define AKI_MMA_TILE 128 /* query / key tile edge used by the attention kernels and by tile_bounds */
+
+typedef void* aki_stream_t; /* cudaStream_t */
+
+typedef enum AkiStatus {
+  AKI_OK = 0,
+  AKI_ERR_NULL = -1,        /* a required pointer is NULL */
+  AKI_ERR_BAD_SHAPE = -2,   /* negative / zero / inconsistent sizes */
+  AKI_ERR_UNSUPPORTED = -3, /* head_dim != 96, stride not a multiple of 8 elements, ... */
+  AKI_ERR_MISALIGNED = -4,  /* pointer not 16-byte aligned */
+  AKI_ERR_CUDA = -5,        /* CUDA runtime / driver error (launch, tensor-map encode) */
+  AKI_ERR_NO_DEVICE = -6    /* no sm_100 device visible */
+} AkiStatus;
+
+int aki_mma_abi_version(void);
+const char* aki_mma_strerror(int status);
+/* Last CUDA error string seen by this thread (diagnostics for AKI_ERR_CUDA). Host pointer, never NULL. */
+const char* aki_mma_last_cuda_error(void);
+
+/* ------------------------------------------------------------------------------------------------------
+ * (1) Segment metadata  -- replaces the per-sample Python loop of
+ *     VLMWithLanguageStream._prepare_inputs_for_forward (vlm.py:486-577: torch.where for <image> and the
+ *     first <|assistant|> id 32001, splice bookkeeping) and _make_modality_mutual_mask (vlm.py:410-443).
+ *     Instead of a (B,1,T,T) int64 tensor it emits O(B*T) integers from which
+ *        allowed(i,j) = i<len & j<len & ( (j<=i & valid[j]) | (row_lo[i]<=j<row_hi[i] & mutual_ok[j]) )
+ *     reproduces the reference mask bit-for-bit (single image) and defines >=2 images per sample, which the
+ *     reference cannot run (vlm.py:547-554 raises).  Mask coordinates are top-left aligned as in
+ *     stack_with_padding_2D_attention (utils.py:99-108).
+ *
+ *     lang_x, attention_mask : (B, L) int64.   N = vision tokens per <image> (AKI: 144, aki.py:20).
+ *     t_cap                  : row pitch of the (B, t_cap) outputs; must be >= max_b T_b
+ *                              (T_b = L + n_img_b*(N-1)); entries t >= T_b are filled as padding.
+ *     text_only              : 0 = "contiguous" (an image span sees every later key of another segment up to
+ *                              and including <|assistant|>; == reference for one image), 1 = later TEXT keys only.
+ *     outputs: seq_len (B) int32 = T_b | q_end (B) int32 = post-splice index of first <|assistant|> + 1, else 0
+ *              seg (B,t_cap) int32: 0 text, k>=1 vision tokens of the k-th image, -1 padding
+ *              row_lo,row_hi (B,t_cap) int32 | src (B,t_cap) int32: l>=0 text token, -1-(k*N+v) vision, INT32_MIN pad
+ *              kv_valid_bits, kv_mutual_bits (B, ceil(t_cap/32)) uint32: bit j = key j visible causally /
+ *              through the mutual block.   Any output pointer except seq_len may be NULL (skipped).
+ *     status (1) int32, optional: set to 1 on device if some T_b > t_cap (outputs truncated). */
+int aki_mma_segments(const int64_t* lang_x, const int64_t* attention_mask, int B, int L, int N,
+                     int64_t media_token_id, int64_t assistant_token_id, int t_cap, int text_only,
+                     int32_t* seq_len, int32_t* q_end, int32_t* seg, int32_t* row_lo, int32_t* row_hi,
+                     int32_t* src, uint32_t* kv_valid_bits, uint32_t* kv_mutual_bits, int32_t* status,
+                     aki_stream_t stream);
+
+/* Per-tile loop bounds for AKI_MMA_TILE-row tiles (derived data the attention kernels consume so that fully
+ * masked tiles are never visited):
+ *   q_tile_kv_end  (B, ceil(T/128)) : number of key tiles query tile qt must visit (0 = tile is all padding)
+ *   kv_tile_q_start(B, ceil(T/128)) : first query tile that sees any key of key tile kt (backward) */
+int aki_mma_tile_bounds(const int32_t* seq_len, const int32_t* row_lo, const int32_t* row_hi, int B, int T,
+                        int t_cap, int32_t* q_tile_kv_end, int32_t* kv_tile_q_start, aki_stream_t stream);
+
+/* Debug / parity helper: expand the compact description to the reference's (B,1,T,T) int64 0/1 tensor
+ * (what _prepare_inputs_for_forward returns under "attention_mask", vlm.py:589-603). */
+int aki_mma_expand_mask(const int32_t* seq_len, const int32_t* row_lo, const int32_t* row_hi,
+                        const uint32_t* kv_valid_bits, const uint32_t* kv_mutual_bits, int B, int T, int t_cap,
+                        int64_t* mask4d, aki_stream_t stream);
+
+/* Splice ("next" row f-2): inputs_embeds / labels of vlm.py:516-588 as one gather driven by `src`.
+ *   lang_embeds (B,L,E) bf16, vision_tokens (B,n_img_max,N,E) bf16, labels_in (B,L) int64 or NULL
+ *   out_embeds (B,T,E) bf16, labels_out (B,T) int64 or NULL.  Padding rows: embeds = pad_value (the reference
+ *   fills embedding rows with the scalar pad_token_id, vlm.py:584-588), labels = -100.
+ *   pad_left != 0 shifts every sample right by T - T_b (padding_side="left", utils.py:62-96). */
+int aki_mma_splice(const void* lang_embeds, const void* vision_tokens, const int64_t* labels_in,
+                   const int32_t* src, const int32_t* seq_len, int B, int L, int N, int n_img_max, int E, int T,
+                   int t_cap, float pad_value, int pad_left, void* out_embeds, int64_t* labels_out,
+                   aki_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * (2) Phi-3 longrope tables -- replaces Phi3RotaryEmbedding.forward (remote code; installed equivalent
+ *     models/phi3/modeling_phi3.py:118-131): cos/sin(pos * inv_freq) * attention_factor, fp32.
+ *     position_ids (B,T) int64; inv_freq (D/2) fp32 (= 1/(ext_factor * theta^(2k/D)), the caller picks
+ *     short/long factors as modeling_rope_utils.py:47-80 does); outputs cos,sin (B,T,D/2) fp32. */
+int aki_mma_rope_table(const int64_t* position_ids, const float* inv_freq, float attention_factor, int B, int T,
+                       int half_dim, float* cos_out, float* sin_out, aki_stream_t stream);
+
+/* (3) RoPE + KV-cache write -- replaces apply_rotary_pos_emb on K and DynamicCache.update's torch.cat
+ *     (modeling_phi3.py:248-251; KV contract vlm.py:463-468, aki_generation.py:45-47,80).
+ *     Reads the packed projection qkv (B,T,3*H*D) bf16 (strides given), rotates K, and writes K (post-RoPE)
+ *     and V into caches laid out (B,H,t_cap,D) at rows [past_len, past_len+T).  v_cache may be NULL (training:
+ *     V is consumed in place).  q_rot (B,H,T,D) bf16 may be non-NULL to also emit rotated Q (decode path).
+ *     cos/sin: (B or 1, T, D/2) fp32, rope_stride_b = 0 broadcasts over batch. */
+int aki_mma_rope_kv_write(const void* qkv, int64_t qkv_stride_b, int64_t qkv_stride_t, const float* cos,
+                          const float* sin, int64_t rope_stride_b, int B, int T, int H, int D, void* k_cache,
+                          void* v_cache, int64_t cache_stride_b, int64_t cache_stride_h, int past_len, void* q_rot,
+                          aki_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * (4) Attention core -- replaces the eager path of Phi3Attention.forward: QK^T/sqrt(D) + additive mask,
+ *     softmax in fp32, P V (modeling_phi3.py:153-175) together with the 4-D mask inversion of transformers
+ *     4.41.2 (_prepare_4d_causal_attention_mask) -- no mask is read from HBM, the predicate is evaluated per
+ *     128x128 tile from row_lo/row_hi and the two key bit-vectors.
+ *     Rows with no visible key (batch padding) produce zeros (the reference produces a uniform average over
+ *     all keys; see DESIGN.md "fully masked rows"). */
+typedef struct AkiMmaTensor4 { /* logical (B, T, H, D) bf16 view, last dim contiguous */
+  void* ptr;
+  int64_t stride_b, stride_t, stride_h; /* elements; multiples of 8 */
+} AkiMmaTensor4;
+
+typedef struct AkiMmaAttnParams {
+  int32_t B, H, T, D; /* queries == keys == T (prefill / training); D == 96 */
+  float scale;        /* softmax scale, 1/sqrt(96) */
+  AkiMmaTensor4 q;    /* pre-RoPE if rope_cos != NULL, else used as is */
+  AkiMmaTensor4 k;    /* post-RoPE keys (cache layout or any strided view) */
+  AkiMmaTensor4 v;
+  AkiMmaTensor4 o;    /* output, (B,T,H,D) view */
+  float* lse;         /* (B,H,T) fp32 natural-log sum-exp of scaled scores; may be NULL (inference) */
+  const float* rope_cos; /* (B or 1, T, D/2) fp32 or NULL: rotate Q while loading it */
+  const float* rope_sin;
+  int64_t rope_stride_b;
+  /* MMA description; all NULL => plain causal over T keys */
+  const int32_t* seq_len;          /* (B) */
+  const int32_t* row_lo;           /* (B, meta_pitch) */
+  const int32_t* row_hi;           /* (B, meta_pitch) */
+  const uint32_t* kv_valid_bits;   /* (B, bits_pitch) */
+  const uint32_t* kv_mutual_bits;  /* (B, bits_pitch) */
+  const int32_t* q_tile_kv_end;    /* (B, ceil(T/128)) */
+  const int32_t* kv_tile_q_start;  /* (B, ceil(T/128)); backward only */
+  int32_t meta_pitch, bits_pitch;
+} AkiMmaAttnParams;
+
+int aki_mma_attn_fwd(const AkiMmaAttnParams* p, aki_stream_t stream);
+
+typedef struct AkiMmaAttnBwdParams {
+  AkiMmaAttnParams fwd;   /* same q/k/v/o/lse/metadata as the forward call (lse required) */
+  AkiMmaTensor4 d_o;      /* (B,T,H,D) bf16 */
+  AkiMmaTensor4 d_q;      /* outputs; gradients w.r.t. the PRE-RoPE q / k when rope tables are given */
+  AkiMmaTensor4 d_k;
+  AkiMmaTensor4 d_v;
+  void* workspace;        /* aki_mma_attn_bwd_workspace_bytes() bytes, 256-byte aligned */
+  size_t workspace_bytes;
+  int32_t deterministic;  /* reserved; dQ is accumulated with fp32 atomics when 0 */
+} AkiMmaAttnBwdParams;
+
+size_t aki_mma_attn_bwd_workspace_bytes(int B, int H, int T, int D);
+int aki_mma_attn_bwd(const AkiMmaAttnBwdParams* p, aki_stream_t stream);
+
+/* (5) Decode -- the generate loop after prefill (aki_generation.py:56-84): a 2-D all-ones mask, i.e. one
+ *     query per sequence sees every cached key [0, kv_len[b]).  Memory-bound split-KV kernel.
+ *     q (B,H,D) bf16 post-RoPE; caches (B,H,t_cap,D); out (B,H,D) bf16; workspace from
+ *     aki_mma_decode_workspace_bytes(). kv_len (B) int32 device array. */
+size_t aki_mma_decode_workspace_bytes(int B, int H, int D, int max_kv_len);
+int aki_mma_decode(const void* q, const void* k_cache, const void* v_cache, int64_t cache_stride_b,
+                   int64_t cache_stride_h, const int32_t* kv_len, int max_kv_len, int B, int H, int D, float scale,
+                   void* out, void* workspace, size_t workspace_bytes, aki_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * Verification kernels (tests only): the same maths as (4) written as plain SIMT CUDA with no tensor cores,
+ * used to cross-check the tcgen05 kernels on-device at sizes the CPU oracle cannot reach. */
+int aki_mma_attn_fwd_simt(const AkiMmaAttnParams* p, aki_stream_t stream);
+int aki_mma_attn_bwd_simt(const AkiMmaAttnBwdParams* p, aki_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AKI_MMA_H_ */
