@@ -9,8 +9,10 @@
 //     dV  += P^T dO_i                     (TS)
 //     dK  += dS^T Q_i                     (SS, A K-major = dS^T, B MN-major = Q_i)
 //     dQ_i = dS K                         (SS, A MN-major = the same dS^T buffer, B MN-major = K)  -> fp32 red.add
-// dK / dV accumulate in TMEM over the whole loop; dQ_i is drained to a fp32 accumulator in HBM with vector
-// reductions (aki_mma_attn_bwd's finalize kernel applies the inverse RoPE and casts).  The MMA predicate is the
+// dK / dV accumulate in TMEM over the whole loop; dQ_i is staged in shared memory (fp32, SWIZZLE_128B) and added
+// to a fp32 accumulator in HBM by TMA tensor reductions (cp.reduce.async.bulk.tensor .add) -- per-lane global
+// atomics cost ~1.3 cycles per lane per SM and were 10x slower.  aki_mma_attn_bwd's finalize kernel applies the
+// inverse RoPE and casts.  The MMA predicate is the
 // same as in the forward, evaluated only on tiles that are not fully visible.
 //
 // 12 warps: 0 TMA producer, 1 MMA issuer, 2 TMEM allocator, 3 idle, 4-11 compute (thread <-> key row r = tid%128;
@@ -34,7 +36,9 @@ constexpr int SMEM_V = SMEM_K + TILE_BYTES;
 constexpr int SMEM_Q = SMEM_V + TILE_BYTES;
 constexpr int SMEM_DO = SMEM_Q + Q_STAGES * TILE_BYTES;
 constexpr int SMEM_DS = SMEM_DO + DO_STAGES * TILE_BYTES;   // 4 atoms [128][64 B]
-constexpr int SMEM_STATS = SMEM_DS + 4 * ATOM_BYTES;        // 2 stages x {lse2, delta, lo, hi} x 128 x 4 B
+constexpr int DQ_ATOM_BYTES = 128 * 128;                    // fp32 staging atom: [128 rows][32 floats], SWIZZLE_128B
+constexpr int SMEM_DQ2 = SMEM_DS + 4 * ATOM_BYTES;          // third dQ staging atom (atoms 0,1 alias the dS^T buffer)
+constexpr int SMEM_STATS = SMEM_DQ2 + DQ_ATOM_BYTES;        // 2 stages x {lse2, delta, lo, hi} x 128 x 4 B
 constexpr int SMEM_TOTAL = SMEM_STATS + 2 * 4 * 128 * 4;
 constexpr int SMEM_ALLOC = SMEM_TOTAL + 1024;
 constexpr uint32_t TM_S = 0, TM_DP = 128, TM_DV = 256, TM_DK = 352;
@@ -71,7 +75,7 @@ __device__ __forceinline__ int4 lds_v4i(uint32_t addr) {
 __global__ void __launch_bounds__(bwd::THREADS, 1)
 attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                       const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_do,
-                      const BwdKernelParams P) {
+                      const __grid_constant__ CUtensorMap map_dq, const BwdKernelParams P) {
   using namespace bwd;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -105,6 +109,7 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
   if (warp == 2) tmem_alloc<512>(smem_u32(&tmem_base_s));
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_k); tma_prefetch_desc(&map_v); tma_prefetch_desc(&map_do);
+    tma_prefetch_desc(&map_dq);
   }
   tc_fence_before();
   __syncthreads();
@@ -302,6 +307,11 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
       tmem_ld_x32(tmem + TM_DP + lane_base + 64 * hq + 32, draw + 32);
       tmem_wait_ld();
       const uint32_t ds_base = smem_base + SMEM_DS;
+      // the dS^T buffer doubles as dQ staging: the TMA reduction of the previous tile must have read it
+      if (it > 0) {
+        if (ct == 0) tma_store_wait_read<0>();
+        named_bar_sync(2, 256);
+      }
 #pragma unroll
       for (int c8 = 0; c8 < 8; ++c8) {   // 8 query columns -> one 16-byte chunk of the dS^T row
         const float4 d0 = lds_v4(st + 512 + (64 * hq + 8 * c8) * 4);
@@ -325,7 +335,7 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
     };
 
     auto phase_c = [&](int it) {   // drain dQ_it: lane r is now QUERY row r of the tile; this half owns 48 columns
-      const int i = (q_start + it) * BM + r;
+      const int i0 = (q_start + it) * BM;
       mbar_wait(BAR(DQ_FULL), it & 1);
       tc_fence_after();
       uint32_t dq[48];
@@ -334,12 +344,24 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
       tmem_wait_ld();
       tc_fence_before();
       mbar_arrive(BAR(DQ_DRAINED));
-      if (i < len) {
-        float* dst = P.dq_accum + (bhT + i) * HD + 48 * hq;
+      // stage as three [128][32 x fp32] SWIZZLE_128B atoms (atoms 0,1 in the dS^T buffer, which the MMAs have
+      // finished reading once DQ_FULL fired), then one thread issues the TMA reductions
 #pragma unroll
-        for (int x = 0; x < 12; ++x)
-          red_add_v4(dst + 4 * x, __uint_as_float(dq[4 * x]), __uint_as_float(dq[4 * x + 1]),
-                     __uint_as_float(dq[4 * x + 2]), __uint_as_float(dq[4 * x + 3]));
+      for (int x = 0; x < 12; ++x) {
+        const int col = 48 * hq + 4 * x;
+        const int atom = col >> 5, chunk = (col & 31) >> 2;
+        const uint32_t abase = (atom < 2) ? (smem_base + SMEM_DS + atom * DQ_ATOM_BYTES) : (smem_base + SMEM_DQ2);
+        const uint32_t addr = abase + r * 128 + ((chunk ^ (r & 7)) << 4);
+        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(dq[4 * x]), "r"(dq[4 * x + 1]),
+                     "r"(dq[4 * x + 2]), "r"(dq[4 * x + 3]) : "memory");
+      }
+      fence_proxy_async_smem();
+      named_bar_sync(3, 256);
+      if (ct == 0) {
+        tma_reduce_add_4d(&map_dq, smem_base + SMEM_DS, 0, i0, h, b);
+        tma_reduce_add_4d(&map_dq, smem_base + SMEM_DS + DQ_ATOM_BYTES, 32, i0, h, b);
+        tma_reduce_add_4d(&map_dq, smem_base + SMEM_DQ2, 64, i0, h, b);
+        tma_store_commit();
       }
     };
 
@@ -351,6 +373,7 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
         if (it + 1 < n_q) phase_a(it + 1);
         phase_c(it);
       }
+      if (ct == 0) tma_store_wait<0>();   // all dQ reductions have landed before the CTA retires its smem
     }
 
     // ---- epilogue: dV, dK (inverse RoPE) -> bf16 -> global.  tcgen05.ld is warp-collective: the loads are
@@ -446,11 +469,12 @@ extern "C" int aki_mma_attn_bwd(const AkiMmaAttnBwdParams* p, aki_stream_t strea
     return AKI_ERR_CUDA;
   }
   AkiMmaTensor4 qrot{w.q_rot, (int64_t)f.H * f.T * f.D, (int64_t)f.D, (int64_t)f.T * f.D};
-  CUtensorMap mq, mk, mv, mdo;
+  CUtensorMap mq, mk, mv, mdo, mdq;
   if ((rc = make_tile_map(&mq, qrot, f.B, f.H, f.T, bwd::BM))) return rc;
   if ((rc = make_tile_map(&mk, f.k, f.B, f.H, f.T, bwd::BN))) return rc;
   if ((rc = make_tile_map(&mv, f.v, f.B, f.H, f.T, bwd::BN))) return rc;
   if ((rc = make_tile_map(&mdo, p->d_o, f.B, f.H, f.T, bwd::BM))) return rc;
+  if ((rc = make_dq_accum_map(&mdq, w.dq_accum, f.B, f.H, f.T))) return rc;
   BwdKernelParams kp;
   kp.d_k = view_of(p->d_k); kp.d_v = view_of(p->d_v);
   kp.lse = f.lse; kp.delta = w.delta; kp.dq_accum = w.dq_accum;
@@ -471,7 +495,7 @@ extern "C" int aki_mma_attn_bwd(const AkiMmaAttnBwdParams* p, aki_stream_t strea
     }
     attr_done = true;
   }
-  attn_bwd_sm100_kernel<<<(unsigned)grid, bwd::THREADS, bwd::SMEM_ALLOC, st>>>(mq, mk, mv, mdo, kp);
+  attn_bwd_sm100_kernel<<<(unsigned)grid, bwd::THREADS, bwd::SMEM_ALLOC, st>>>(mq, mk, mv, mdo, mdq, kp);
   if ((rc = check_launch())) return rc;
   return launch_dq_finalize(*p, w, st);
 }

@@ -19,6 +19,8 @@
 // (head_dim 96 = 3 x 32), the layout both the TMA boxes and the UMMA descriptors use (validated by
 // tools/umma_probe.cu).
 #include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
 #include "attn_aux.cuh"
 #include "sm100_ptx.cuh"
 
@@ -49,11 +51,16 @@ struct FwdKernelParams {
   MaskMeta mm;
   int B, H, T, n_qt, n_qp;
   float scale_log2, scale;
+  unsigned long long* trace;  // debug: per-iteration clock64 stamps of one CTA (AKI_MMA_FWD_TRACE=<cta>)
+  int trace_cta;
+  int debug;   // perf experiments only (AKI_MMA_FWD_DEBUG): 1 skip exp, 2 skip S load, 4 skip P store, 8 skip max
 };
 
 __device__ __forceinline__ uint32_t low_mask(int n) {  // n low bits set, n clamped to [0,32]
   return n <= 0 ? 0u : (n >= 32 ? 0xffffffffu : ((1u << n) - 1u));
 }
+
+#define TR(slot, j, k) do { if (tracing) P.trace[((slot) * 128 + (j)) * 8 + (k)] = clock64(); } while (0)
 
 template <bool ROPE>
 __global__ void __launch_bounds__(fwd::THREADS, 1)
@@ -116,20 +123,28 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
       for (int j = 0; j < n_max; ++j) {
         const int s = j % STAGES;
         const uint32_t ph = (j / STAGES) & 1;
+        const bool skip_tma = (P.debug & 16) && j >= STAGES;
         mbar_wait(BAR(K_EMPTY + s), ph ^ 1);
-        mbar_arrive_expect_tx(BAR(K_FULL + s), TILE_BYTES);
-        for (int a = 0; a < 3; ++a)
-          tma_load_4d(smem_base + SMEM_K + s * TILE_BYTES + a * ATOM_BYTES, &map_k, BAR(K_FULL + s), a * 32, j * BN, h, b);
+        if (skip_tma) mbar_arrive(BAR(K_FULL + s));
+        else {
+          mbar_arrive_expect_tx(BAR(K_FULL + s), TILE_BYTES);
+          for (int a = 0; a < 3; ++a)
+            tma_load_4d(smem_base + SMEM_K + s * TILE_BYTES + a * ATOM_BYTES, &map_k, BAR(K_FULL + s), a * 32, j * BN, h, b);
+        }
         mbar_wait(BAR(V_EMPTY + s), ph ^ 1);
-        mbar_arrive_expect_tx(BAR(V_FULL + s), TILE_BYTES);
-        for (int a = 0; a < 3; ++a)
-          tma_load_4d(smem_base + SMEM_V + s * TILE_BYTES + a * ATOM_BYTES, &map_v, BAR(V_FULL + s), a * 32, j * BN, h, b);
+        if (skip_tma) mbar_arrive(BAR(V_FULL + s));
+        else {
+          mbar_arrive_expect_tx(BAR(V_FULL + s), TILE_BYTES);
+          for (int a = 0; a < 3; ++a)
+            tma_load_4d(smem_base + SMEM_V + s * TILE_BYTES + a * ATOM_BYTES, &map_v, BAR(V_FULL + s), a * 32, j * BN, h, b);
+        }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     setmaxnreg_dec<REGS_CTRL>();
     if (elect_one()) {
+      const bool tracing = P.trace && (int)blockIdx.x == P.trace_cta;
       constexpr uint32_t IDESC_QK = umma_idesc_bf16(BM, BN, 0, 0);
       constexpr uint32_t IDESC_PV = umma_idesc_bf16(BM, HD, 0, 1);
       const uint32_t tm_s[2] = {tmem + TM_S0, tmem + TM_S1};
@@ -137,6 +152,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
       auto issue_qk = [&](int t, int j) {
         const uint32_t qa = smem_base + SMEM_Q + t * TILE_BYTES;
         const uint32_t ka = smem_base + SMEM_K + (j % STAGES) * TILE_BYTES;
+        if (P.debug & 32) return;
 #pragma unroll
         for (int k = 0; k < 6; ++k) {
           const uint32_t off = (k >> 1) * ATOM_BYTES + (k & 1) * 32;
@@ -146,6 +162,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
       };
       auto issue_pv = [&](int t, int j) {
         const uint32_t va = smem_base + SMEM_V + (j % STAGES) * TILE_BYTES;
+        if (P.debug & 32) return;
 #pragma unroll
         for (int k = 0; k < 8; ++k)
           umma_ts(tm_o[t], tm_s[t] + 8 * k, umma_smem_desc(va + k * 1024, ATOM_BYTES, 512, UMMA_SW64), IDESC_PV,
@@ -165,11 +182,15 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
         bool v_waited = false;
         for (int t = 0; t < 2; ++t) {
           if (j >= n_kv[t]) continue;
+          if (j < 128) TR(2 + t, j, 0);
           mbar_wait(BAR(P_FULL + t), j & 1);
+          if (j < 128) TR(2 + t, j, 1);
           if (!v_waited) { mbar_wait(BAR(V_FULL + sv), (j / STAGES) & 1); v_waited = true; }
           tc_fence_after();
+          if (j < 128) TR(2 + t, j, 2);
           issue_pv(t, j);
           umma_commit(BAR(O_FULL + t));
+          if (j < 128) TR(2 + t, j, 3);
           const bool last_v = (t == 1) || (j >= n_kv[1]);
           if (last_v) umma_commit(BAR(V_EMPTY + sv));
           const int jn = j + 1;
@@ -177,9 +198,11 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
             const bool first_k = (t == 0) || (jn >= n_kv[0]);
             const bool last_k = (t == 1) || (jn >= n_kv[1]);
             if (first_k) { mbar_wait(BAR(K_FULL + jn % STAGES), (jn / STAGES) & 1); tc_fence_after(); }
+            if (j < 128) TR(2 + t, j, 4);
             issue_qk(t, jn);
             umma_commit(BAR(S_FULL + t));
             if (last_k) umma_commit(BAR(K_EMPTY + jn % STAGES));
+            if (j < 128) TR(2 + t, j, 5);
           }
         }
       }
@@ -242,17 +265,26 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
       row_lo = P.mm.row_lo[(size_t)b * P.mm.meta_pitch + i];
       row_hi = P.mm.row_hi[(size_t)b * P.mm.meta_pitch + i];
     }
+    const bool tracing = P.trace && (int)blockIdx.x == P.trace_cta && r == 0;
     float m_used = -INFINITY;  // running max (raw score units) the accumulators are expressed against
     float l = 0.f;
 
     for (int j = 0; j < nk; ++j) {
+      if (j < 128) TR(t, j, 0);
       mbar_wait(BAR(S_FULL + t), j & 1);
       tc_fence_after();
+      if (j < 128) TR(t, j, 1);
       float s[128];
+      if (!(P.debug & 2)) {
 #pragma unroll
-      for (int c = 0; c < 4; ++c) tmem_ld_x32(tm_s + 32 * c, reinterpret_cast<uint32_t*>(s) + 32 * c);
-      tmem_wait_ld();
+        for (int c = 0; c < 4; ++c) tmem_ld_x32(tm_s + 32 * c, reinterpret_cast<uint32_t*>(s) + 32 * c);
+        tmem_wait_ld();
+      } else {
+#pragma unroll
+        for (int c = 0; c < 128; ++c) s[c] = (float)(c + r) * 0.01f;
+      }
 
+      if (j < 128) TR(t, j, 2);
       // ---- tile classification (warp-uniform): fully visible tiles skip the predicate
       const int j0 = j * BN;
       uint32_t vw[4], mw[4];
@@ -283,7 +315,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
       for (int c = 4; c < 128; c += 4) {
         mx0 = fmaxf(mx0, s[c]); mx1 = fmaxf(mx1, s[c + 1]); mx2 = fmaxf(mx2, s[c + 2]); mx3 = fmaxf(mx3, s[c + 3]);
       }
-      const float m_new = fmaxf(m_used, fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)));
+      const float m_new = (P.debug & 8) ? fmaxf(m_used, mx0) : fmaxf(m_used, fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)));
       // ---- lazy rescale of O (correction merged into the softmax warps; rare after the first tiles)
       if (j == 0) {
         m_used = m_new;
@@ -307,6 +339,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
           tmem_wait_st();
         }
       }
+      if (j < 128) TR(t, j, 3);
       // ---- P = exp2((S - m) * scale*log2e), row sum, bf16 pack, store to TMEM (aliases S)
       const float neg_m = (m_used == -INFINITY) ? 0.f : -m_used * P.scale_log2;
       float sum0 = 0.f, sum1 = 0.f;
@@ -315,17 +348,20 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
         uint32_t pk[16];
 #pragma unroll
         for (int x = 0; x < 16; ++x) {
-          const float p0 = ex2_approx(fmaf(s[32 * c + 2 * x], P.scale_log2, neg_m));
-          const float p1 = ex2_approx(fmaf(s[32 * c + 2 * x + 1], P.scale_log2, neg_m));
+          float p0 = fmaf(s[32 * c + 2 * x], P.scale_log2, neg_m);
+          float p1 = fmaf(s[32 * c + 2 * x + 1], P.scale_log2, neg_m);
+          if (!(P.debug & 1)) { p0 = ex2_approx(p0); p1 = ex2_approx(p1); }
           sum0 += p0; sum1 += p1;
           pk[x] = pack_bf16x2(p0, p1);
         }
-        tmem_st_x16(tm_s + 16 * c, pk);
+        if (!(P.debug & 4) || c == 0) tmem_st_x16(tm_s + 16 * c, pk);
       }
       l += sum0 + sum1;
+      if (j < 128) TR(t, j, 4);
       tmem_wait_st();
       tc_fence_before();
       mbar_arrive(BAR(P_FULL + t));
+      if (j < 128) TR(t, j, 5);
     }
 
     // ---- epilogue: O / l -> bf16 -> global; LSE
@@ -398,6 +434,20 @@ int make_tile_map(CUtensorMap* m, const AkiMmaTensor4& t, int B, int H, int T, i
   return AKI_OK;
 }
 
+// dQ accumulator (B,H,T,96) fp32 contiguous -> [32 x 128 x 1 x 1] fp32 SWIZZLE_128B boxes for TMA reductions
+int make_dq_accum_map(CUtensorMap* m, float* dq_accum, int B, int H, int T) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) { set_last_cuda_error("cuTensorMapEncodeTiled entry point not found"); return AKI_ERR_CUDA; }
+  cuuint64_t dims[4] = {96, (cuuint64_t)T, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t strides[3] = {96 * 4, (cuuint64_t)T * 96 * 4, (cuuint64_t)H * T * 96 * 4};
+  cuuint32_t box[4] = {32, 128, 1, 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, dq_accum, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_last_cuda_error("cuTensorMapEncodeTiled(dq) failed"); return AKI_ERR_CUDA; }
+  return AKI_OK;
+}
+
 }  // namespace aki
 
 using namespace aki;
@@ -419,6 +469,15 @@ extern "C" int aki_mma_attn_fwd(const AkiMmaAttnParams* p, aki_stream_t stream) 
   kp.n_qp = (kp.n_qt + 1) / 2;
   kp.scale = p->scale;
   kp.scale_log2 = p->scale * 1.4426950408889634f;
+  { const char* e = getenv("AKI_MMA_FWD_DEBUG"); kp.debug = e ? atoi(e) : 0; }
+  kp.trace = nullptr; kp.trace_cta = -1;
+  const char* trace_env = getenv("AKI_MMA_FWD_TRACE");
+  const size_t trace_bytes = 4 * 128 * 8 * sizeof(unsigned long long);
+  if (trace_env) {
+    kp.trace_cta = atoi(trace_env);
+    cudaMalloc(&kp.trace, trace_bytes);
+    cudaMemset(kp.trace, 0, trace_bytes);
+  }
   const long long grid = (long long)kp.n_qp * p->H * p->B;
   AKI_REQUIRE(grid > 0 && grid < (1ll << 31), AKI_ERR_BAD_SHAPE);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -435,5 +494,21 @@ extern "C" int aki_mma_attn_fwd(const AkiMmaAttnParams* p, aki_stream_t stream) 
     attn_fwd_sm100_kernel<true><<<(unsigned)grid, fwd::THREADS, fwd::SMEM_ALLOC, st>>>(mq, mk, mv, kp);
   else
     attn_fwd_sm100_kernel<false><<<(unsigned)grid, fwd::THREADS, fwd::SMEM_ALLOC, st>>>(mq, mk, mv, kp);
+  if (trace_env) {   // debug only: dump the stamps of one CTA (synchronises!)
+    cudaDeviceSynchronize();
+    static unsigned long long host[4 * 128 * 8];
+    cudaMemcpy(host, kp.trace, trace_bytes, cudaMemcpyDeviceToHost);
+    cudaFree(kp.trace);
+    unsigned long long t0 = ~0ull;
+    for (size_t i = 0; i < 4 * 128 * 8; ++i) if (host[i] && host[i] < t0) t0 = host[i];
+    const char* names[4] = {"softmax0", "softmax1", "mma_t0", "mma_t1"};
+    for (int slot = 0; slot < 4; ++slot)
+      for (int j = 0; j < 128; ++j) {
+        if (!host[(slot * 128 + j) * 8]) continue;
+        fprintf(stderr, "TRACE %s j=%d:", names[slot], j);
+        for (int k = 0; k < 6; ++k) fprintf(stderr, " %llu", host[(slot * 128 + j) * 8 + k] ? host[(slot * 128 + j) * 8 + k] - t0 : 0ull);
+        fprintf(stderr, "\n");
+      }
+  }
   return check_launch();
 }

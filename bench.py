@@ -1,0 +1,324 @@
+"""bench.py -- headline benchmark of the MMA hot path (BASELINE.json: "MMA attn fwd+bwd TFLOP/s vs BF16 peak").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload attn|prefill]
+
+Workload (config.workload): BASELINE config 3 at the north-star point -- T=8192 context, B=2 per GPU, 32 heads x 96,
+4 interleaved image spans of 128 vision tokens, <|assistant|> 64 tokens before the end, Phi-3 longrope on Q/K,
+bf16, synthetic N(0,1) q/k/v/dO (seeded).  One step = one forward + one backward of the attention core over the
+batch.  value = algorithmic FLOPs / time with FLOPs = 43008 * nnz (fwd 4*H*D*nnz, bwd 10*H*D*nnz; nnz = exact
+number of visible (query,key) pairs) -- masked work that the kernels skip is not counted.
+
+Keys beyond the base contract:
+  roofline      dominant kernel call (backward), tensor-bound, against MEASURED_PEAKS.json bf16_tflops
+  cpu_baseline  the oracle (oracle/mma_oracle.py, fp32 eager with the materialised 4-D mask = the reference's CPU
+                path) on the host cores, bounded sample, rank 0 only
+  e2e           the same metric through the public module API (AkiMMAAttention fwd+bwd incl. qkv/o projections)
+                with pinned HOST inputs copied in and the loss read back inside the timed region
+N>1: one process per GPU (torchrun), batch-sharded, no data-path collective ("weak" scaling: B=2 per GPU).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+H, D, N_VIS = 32, 96, 128
+MEDIA_ID, ASST_ID = 32012, 32001
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="attn", choices=["attn", "prefill"])
+    ap.add_argument("--seq", type=int, default=8192)
+    ap.add_argument("--batch", type=int, default=2)
+    ap.add_argument("--images", type=int, default=4)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    return ap.parse_args()
+
+
+def make_prompt(B, T, n_img, seed=0):
+    """lang_x (B,L) whose spliced length is exactly T: n_img <image> tokens evenly spaced (first at 8),
+    <|assistant|> so that q_end = T - 64."""
+    L = T - n_img * (N_VIS - 1)
+    g = np.random.default_rng(seed)
+    lang = g.integers(3, 31000, size=(B, L)).astype(np.int64)
+    step = (L - 64 - 8) // max(n_img, 1)
+    for k in range(n_img):
+        lang[:, 8 + k * step] = MEDIA_ID
+    lang[:, L - 65] = ASST_ID            # post-splice index T-65 -> q_end = T-64
+    return lang, np.ones_like(lang)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d, "measured (MEASURED_PEAKS.json)"
+    return {"bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.samples, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "50"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.STDOUT, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)
+        self.proc.terminate()
+        try:
+            self.thread.join(timeout=2.0)
+        except Exception:
+            pass
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            f = [x.strip() for x in s.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm_hot = [x for x in sm if x > 0.3 * max(sm)] if sm else []
+        out = {"sm_mhz": statistics.median(sm_hot) if sm_hot else None, "sm_max_mhz": max(mx) if mx else None,
+               "reasons": sorted(reasons), "samples": len(sm)}
+        if not sm and self.samples:
+            out["raw"] = self.samples[:2]
+        return out
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_reference_run(T, B, n_img, steps, warmup, threads=None):
+    """The reference's CPU path for this workload: materialised 4-D 0/1 mask -> additive fp32 mask -> eager
+    softmax(QK^T*scale + mask) V and its autograd backward, fp32, all host threads (oracle/mma_oracle.py)."""
+    from oracle import mma_oracle as O
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    lang, am = make_prompt(B, T, n_img)
+    S = O.segments_ref(lang, am, N_VIS, MEDIA_ID)
+    nnz = O.count_allowed(S)
+    g = torch.Generator().manual_seed(0)
+    q, k, v = (torch.randn(B, H, T, D, generator=g) for _ in range(3))
+    d_o = torch.randn(B, T, H, D, generator=torch.Generator().manual_seed(1))
+    inv = O.longrope_inv_freq(D, 10000.0, np.ones(D // 2, dtype=np.float32))
+    cos, sin = O.rope_cos_sin(torch.arange(T)[None].expand(B, -1), inv, 1.19)
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        mask = torch.from_numpy(O.expand_segments_to_4d(S))                 # the (B,1,T,T) int64 tensor (a1-a3)
+        add = O.invert_4d_mask(mask, torch.float32)                          # a7
+        qq = q.clone().requires_grad_(True); kk = k.clone().requires_grad_(True); vv = v.clone().requires_grad_(True)
+        out = O.eager_attention(O.apply_rope(qq, cos, sin), O.apply_rope(kk, cos, sin), vv, add, D ** -0.5)
+        out.backward(d_o)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    ms = statistics.median(times) * 1e3
+    return 43008.0 * nnz / (ms * 1e-3) / 1e12, ms, threads, nnz
+
+
+# ------------------------------------------------------------------------------------------------ main
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    T, B, n_img = args.seq, args.batch, args.images
+    cfg = {"workload": f"mma_attn_fwd_bwd T={T} B={B}/gpu H={H} D={D} images={n_img}x{N_VIS} q_end=T-64 rope=longrope",
+           "l2": "inputs (q,k,v,o,dO: 5 x %.0f MB per GPU) larger than the 126 MB L2" % (B * T * H * D * 2 / 1e6),
+           "parallelism": f"batch-sharded x{world}, no collective"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        Ts, Bs = min(T, 2048), 1
+        val, ms, threads, nnz = cpu_reference_run(Ts, Bs, min(n_img, 4), max(1, min(args.steps, 3)), min(args.warmup, 1))
+        sample = f"T={Ts} B={Bs} H={H} images={min(n_img, 4)} fwd+bwd fp32 eager with materialised 4-D mask"
+        print(json.dumps({"impl": "reference", "metric": "mma_attn_fwd_bwd_tflops", "value": val, "unit": "TFLOP/s",
+                          "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                          "data": "synthetic", "config": dict(cfg, reference_sample=sample),
+                          "cpu_baseline": {"value": val, "unit": "TFLOP/s", "cores": threads, "kind": "port",
+                                           "sample": sample},
+                          "e2e": {"value": val, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                          "gpu_launches": 0}))
+        return
+
+    import torch.distributed as dist
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    import aki_b200
+    from aki_b200 import ops
+    from oracle import mma_oracle as O
+
+    lang, am = make_prompt(B, T, n_img, seed=rank)
+    segs = ops.build_segments(torch.from_numpy(lang).to(dev), torch.from_numpy(am).to(dev), N_VIS, MEDIA_ID, t_cap=T,
+                              exact_shape=False)
+    nnz = O.count_allowed(O.segments_ref(lang, am, N_VIS, MEDIA_ID))
+    meta = ops.meta_tuple(segs)
+    g = torch.Generator(device=dev).manual_seed(rank)
+    qkv = torch.randn(B, T, 3 * H * D, generator=g, device=dev, dtype=torch.float32).to(torch.bfloat16)
+    d_o = torch.randn(B, T, H, D, generator=g, device=dev, dtype=torch.float32).to(torch.bfloat16)
+    rope = aki_b200.LongRope(device=dev)
+    cos, sin = rope.tables(torch.arange(T, device=dev)[None], max_position=T - 1)
+    scale = D ** -0.5
+    q4 = qkv[..., :H * D].unflatten(-1, (H, D)); v4 = qkv[..., 2 * H * D:].unflatten(-1, (H, D))
+    k_rot = torch.empty(B, H, T, D, dtype=torch.bfloat16, device=dev)
+    d_qkv = torch.empty_like(qkv)
+    dviews = [d_qkv[..., i * H * D:(i + 1) * H * D].unflatten(-1, (H, D)) for i in range(3)]
+
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    per_fwd, per_bwd = [], []
+
+    def step(timed):
+        e0, e1, e2 = ev(), ev(), ev()
+        e0.record()
+        ops.rope_kv_write(qkv, cos, sin, k_rot, None, 0, H)
+        o, lse = ops.attn_fwd_raw(q4, k_rot.transpose(1, 2), v4, cos, sin, meta, scale)
+        e1.record()
+        ops.attn_bwd_raw(d_o, q4, k_rot.transpose(1, 2), v4, o, lse, cos, sin, meta, scale, *dviews)
+        e2.record()
+        if timed:
+            per_fwd.append((e0, e1)); per_bwd.append((e1, e2))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step(False)
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    t_start, t_end = ev(), ev()
+    t_start.record()
+    for _ in range(args.steps):
+        step(True)
+    t_end.record()
+    barrier()
+    clocks = sampler.stop()
+    ms_total = t_start.elapsed_time(t_end)
+    ms_step = ms_total / args.steps
+    fwd_ms = statistics.mean(a.elapsed_time(b) for a, b in per_fwd)
+    bwd_ms = statistics.mean(a.elapsed_time(b) for a, b in per_bwd)
+
+    # ---- e2e: public module API with host inputs --------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        from transformers import Phi3Config
+        pc = Phi3Config(hidden_size=H * D, num_attention_heads=H, num_key_value_heads=H, intermediate_size=8192,
+                        vocab_size=32064)
+        torch.manual_seed(0)
+        mod = aki_b200.AkiMMAAttention(pc, layer_idx=0).to(dev).to(torch.bfloat16)
+        host_x = torch.randn(B, T, H * D).to(torch.bfloat16).pin_memory()
+        host_loss = torch.empty(1, dtype=torch.float32).pin_memory()
+
+        def e2e_step():
+            x = host_x.to(dev, non_blocking=True).requires_grad_(True)
+            out, _ = mod(x, None, None, mma_segments=segs, mma_rope=(cos, sin))
+            loss = out.float().pow(2).mean()
+            loss.backward()
+            host_loss.copy_(loss.detach().reshape(1), non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            mod.zero_grad(set_to_none=True)
+
+        for _ in range(max(3, args.warmup // 2)):
+            e2e_step()
+        barrier()
+        a, b_ = ev(), ev()
+        n_e2e = max(3, args.steps // 2)
+        a.record()
+        for _ in range(n_e2e):
+            e2e_step()
+        b_.record()
+        barrier()
+        e2e_ms = a.elapsed_time(b_) / n_e2e
+    flops = 43008.0 * nnz
+
+    # ---- max over ranks, aggregate ----------------------------------------------------------------
+    stats = torch.tensor([ms_step, fwd_ms, bwd_ms, e2e_ms if not args.no_e2e else 0.0, float(flops)],
+                         dtype=torch.float64, device=dev)
+    if world > 1:
+        mx = stats.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = stats.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        ms_step, fwd_ms, bwd_ms, e2e_ms_r = (float(x) for x in mx[:4])
+        total_flops = float(sm[4])
+    else:
+        e2e_ms_r = float(stats[3]); total_flops = flops
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    pk, pk_src = peaks()
+    value = total_flops / (ms_step * 1e-3) / 1e12
+    bwd_tf = 30720.0 * nnz / (bwd_ms * 1e-3) / 1e12
+    fwd_tf = 12288.0 * nnz / (fwd_ms * 1e-3) / 1e12
+    line = {
+        "metric": "mma_attn_fwd_bwd_tflops", "value": value, "unit": "TFLOP/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": cfg,
+        "frac_of_bf16_peak": value / (pk["bf16_tflops"] * world),
+        "kernels": {"fwd_ms": fwd_ms, "fwd_tflops": fwd_tf, "bwd_ms": bwd_ms, "bwd_tflops": bwd_tf, "nnz_per_gpu": nnz},
+        "roofline": {"bound": "tensor", "kernel": "attn_bwd_sm100_kernel (+preprocess/finalize, whole backward call)",
+                     "achieved": bwd_tf, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                     "frac": bwd_tf / pk["bf16_tflops_sustained"], "frac_of_burst_peak": bwd_tf / pk["bf16_tflops"],
+                     "peak_source": pk_src + ", sustained (kernel timed inside a long step)", "traffic": None},
+        "clocks": clocks, "gpu_launches": 5 * args.steps,
+    }
+    if not args.no_e2e:
+        line["e2e"] = {"value": total_flops / (e2e_ms_r * 1e-3) / 1e12, "unit": "TFLOP/s",
+                       "h2d_bytes_per_step": B * T * H * D * 2, "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms_r,
+                       "api": "AkiMMAAttention.forward + backward (qkv_proj, o_proj included in time, not in FLOPs)"}
+    if not args.no_cpu and world >= 1:
+        Ts = min(T, 2048)
+        val, ms, threads, _ = cpu_reference_run(Ts, 1, min(n_img, 4), 2, 1)
+        line["cpu_baseline"] = {"value": val, "unit": "TFLOP/s", "cores": threads, "kind": "port",
+                                "sample": f"T={Ts} B=1 H={H} images={min(n_img, 4)} fwd+bwd fp32 eager, {ms:.0f} ms/step"}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
