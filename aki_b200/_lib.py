@@ -33,7 +33,7 @@ class AttnParams(C.Structure):
         ("rope_cos", C.c_void_p), ("rope_sin", C.c_void_p), ("rope_stride_b", C.c_int64),
         ("seq_len", C.c_void_p), ("row_lo", C.c_void_p), ("row_hi", C.c_void_p),
         ("kv_valid_bits", C.c_void_p), ("kv_mutual_bits", C.c_void_p),
-        ("q_tile_kv_end", C.c_void_p), ("kv_tile_q_start", C.c_void_p),
+        ("q_tile_kv_end", C.c_void_p), ("kv_tile_q_mask", C.c_void_p),
         ("meta_pitch", C.c_int32), ("bits_pitch", C.c_int32),
     ]
 

@@ -50,6 +50,6 @@ int check_attn_params(const AkiMmaAttnParams& p);
 int make_tile_map(CUtensorMap* m, const AkiMmaTensor4& t, int B, int H, int T, int box_rows);
 int make_dq_accum_map(CUtensorMap* m, float* dq_accum, int B, int H, int T);
 int launch_bwd_preprocess(const AkiMmaAttnBwdParams& p, const BwdWorkspace& w, cudaStream_t st);
-int launch_dq_finalize(const AkiMmaAttnBwdParams& p, const BwdWorkspace& w, cudaStream_t st);
+int launch_dq_finalize(const AkiMmaAttnBwdParams& p, const BwdWorkspace& w, float scale, cudaStream_t st);
 
 }  // namespace aki

@@ -2,23 +2,24 @@
 //
 // Gradient of softmax_fp32(QK^T*scale + mask) V (the eager core of Phi3Attention.forward; installed equivalent
 // transformers/models/phi3/modeling_phi3.py:153-175; the reference obtains it from autograd over five passes
-// on a (B,32,T,T) tensor).  One CTA owns one 128-key tile of one (batch, head) and walks the query tiles that
-// can see it (kv_tile_q_start .. end), with everything transposed so that keys sit on TMEM lanes:
+// on a (B,32,T,T) tensor).  One CTA owns one 128-key tile of one (batch, head) and walks exactly the query tiles
+// that can see it (kv_tile_q_mask: with MMA that set is the image-row tiles before the diagonal plus everything
+// from the diagonal on), with everything transposed so that keys sit on TMEM lanes:
 //     S^T  = K Q_i^T                      (SS)        P^T = exp2(S^T*c - LSE_i)      -> TMEM (bf16, aliases S^T)
-//     dP^T = V dO_i^T                     (SS)        dS^T = P^T o (dP^T - delta_i) * scale -> smem (bf16)
+//     dP^T = V dO_i^T                     (SS)        dS^T = P^T o (dP^T - delta_i)  -> smem (bf16)
 //     dV  += P^T dO_i                     (TS)
-//     dK  += dS^T Q_i                     (SS, A K-major = dS^T, B MN-major = Q_i)
-//     dQ_i = dS K                         (SS, A MN-major = the same dS^T buffer, B MN-major = K)  -> fp32 red.add
-// dK / dV accumulate in TMEM over the whole loop; dQ_i is staged in shared memory (fp32, SWIZZLE_128B) and added
-// to a fp32 accumulator in HBM by TMA tensor reductions (cp.reduce.async.bulk.tensor .add) -- per-lane global
-// atomics cost ~1.3 cycles per lane per SM and were 10x slower.  aki_mma_attn_bwd's finalize kernel applies the
-// inverse RoPE and casts.  The MMA predicate is the
-// same as in the forward, evaluated only on tiles that are not fully visible.
+//     dK  += dS^T Q_i                     (SS, A K-major = dS^T, B MN-major = Q_i)       (x scale in the epilogue)
+//     dQ_i = dS K                         (SS, A MN-major = the same dS^T buffer, B MN-major = K)
+// dK / dV accumulate in TMEM over the whole loop; dQ_i is drained by a dedicated warpgroup: TMEM -> registers ->
+// fp32 SWIZZLE_128B staging in shared memory -> TMA tensor reduction (cp.reduce.async.bulk.tensor .add) into a
+// fp32 accumulator in HBM (per-lane global atomics cost ~1.3 cycles per lane per SM and were 10x slower);
+// aki_mma_attn_bwd's finalize kernel applies scale, the inverse RoPE and the bf16 cast.
 //
-// 12 warps: 0 TMA producer, 1 MMA issuer, 2 TMEM allocator, 3 idle, 4-11 compute (thread <-> key row r = tid%128;
-// the two warpgroups split the 128 query columns of a tile in halves).
+// 16 warps: 0 TMA producer | 1 MMA issuer | 2 TMEM allocator | 3 builds the query-tile list | 4-11 compute
+// (thread <-> key row r; the two warpgroups split the 128 query columns of a tile in halves) | 12-15 dQ drain.
 // TMEM columns: S^T/P^T [0,128)  dP^T/dQ [128,256)  dV [256,352)  dK [352,448).
-// Shared memory: K, V 24 KB each (resident), Q ring 3x24 KB, dO ring 2x24 KB, dS^T 32 KB, per-tile row stats.
+// Shared memory: K, V 24 KB each (resident), Q ring 2x24 KB, dO ring 2x24 KB, dS^T 32 KB, dQ staging 2x16 KB,
+// per-tile row statistics, query-tile list.
 #include <math.h>
 #include "attn_aux.cuh"
 #include "sm100_ptx.cuh"
@@ -27,50 +28,37 @@ namespace aki {
 
 namespace bwd {
 constexpr int BN = 128, BM = 128, HD = 96;
-constexpr int ATOM_BYTES = 128 * 64;
+constexpr int ATOM_BYTES = 128 * 64;          // bf16 operand atom [128 rows][64 B], SWIZZLE_64B
 constexpr int TILE_BYTES = 3 * ATOM_BYTES;
-constexpr int Q_STAGES = 3, DO_STAGES = 2;
-constexpr int THREADS = 384;
+constexpr int DQ_ATOM_BYTES = 128 * 128;      // fp32 staging atom [128 rows][32 floats], SWIZZLE_128B
+constexpr int Q_STAGES = 2, DO_STAGES = 2;
+constexpr int THREADS = 512;
+constexpr int MAX_TILES = 2048;
 constexpr int SMEM_K = 0;
 constexpr int SMEM_V = SMEM_K + TILE_BYTES;
 constexpr int SMEM_Q = SMEM_V + TILE_BYTES;
 constexpr int SMEM_DO = SMEM_Q + Q_STAGES * TILE_BYTES;
 constexpr int SMEM_DS = SMEM_DO + DO_STAGES * TILE_BYTES;   // 4 atoms [128][64 B]
-constexpr int DQ_ATOM_BYTES = 128 * 128;                    // fp32 staging atom: [128 rows][32 floats], SWIZZLE_128B
-constexpr int SMEM_DQ2 = SMEM_DS + 4 * ATOM_BYTES;          // third dQ staging atom (atoms 0,1 alias the dS^T buffer)
-constexpr int SMEM_STATS = SMEM_DQ2 + DQ_ATOM_BYTES;        // 2 stages x {lse2, delta, lo, hi} x 128 x 4 B
-constexpr int SMEM_TOTAL = SMEM_STATS + 2 * 4 * 128 * 4;
+constexpr int SMEM_DQ = SMEM_DS + 4 * ATOM_BYTES;           // 2 staging atoms
+constexpr int SMEM_STATS = SMEM_DQ + 2 * DQ_ATOM_BYTES;     // 2 stages x {lse2, delta, lo, hi} x 128 x 4 B
+constexpr int SMEM_QLIST = SMEM_STATS + 2 * 4 * 128 * 4;    // uint16[MAX_TILES]
+constexpr int SMEM_TOTAL = SMEM_QLIST + MAX_TILES * 2;
 constexpr int SMEM_ALLOC = SMEM_TOTAL + 1024;
 constexpr uint32_t TM_S = 0, TM_DP = 128, TM_DV = 256, TM_DK = 352;
-constexpr int REGS_CTRL = 64, REGS_COMPUTE = 216;
+constexpr int REGS_CTRL = 48, REGS_COMPUTE = 176, REGS_DRAIN = 112;   // 128*48 + 256*176 + 128*112 = 65536
 }  // namespace bwd
 
 struct BwdKernelParams {
   TensorView d_k, d_v;
   const float* lse;
   const float* delta;
-  float* dq_accum;
   const float* rope_cos;
   const float* rope_sin;
   int64_t rope_stride_b;
   MaskMeta mm;
-  int B, H, T, n_t;
+  int B, H, T, n_t, n_words;
   float scale_log2, scale;
 };
-
-__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
-  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-}
-__device__ __forceinline__ float4 lds_v4(uint32_t addr) {
-  float4 r;
-  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(addr));
-  return r;
-}
-__device__ __forceinline__ int4 lds_v4i(uint32_t addr) {
-  int4 r;
-  asm volatile("ld.shared.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
-  return r;
-}
 
 __global__ void __launch_bounds__(bwd::THREADS, 1)
 attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
@@ -79,12 +67,14 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
   using namespace bwd;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* const smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));   // generic pointer to the aligned base
   constexpr int KV_FULL = 0, Q_FULL = 1, Q_EMPTY = Q_FULL + Q_STAGES, DO_FULL = Q_EMPTY + Q_STAGES,
                 DO_EMPTY = DO_FULL + DO_STAGES, S_FULL = DO_EMPTY + DO_STAGES, P_READY = S_FULL + 1,
                 DP_FULL = P_READY + 1, DS_READY = DP_FULL + 1, DQ_FULL = DS_READY + 1, DQ_DRAINED = DQ_FULL + 1,
                 N_BARS = DQ_DRAINED + 1;
   __shared__ __align__(8) uint64_t bars[N_BARS];
   __shared__ uint32_t tmem_base_s;
+  __shared__ int n_q_s;
   const uint32_t bar0 = smem_u32(bars);
   auto BAR = [&](int i) { return bar0 + 8u * i; };
 
@@ -93,17 +83,14 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
   const int b = bh / P.H, h = bh % P.H;
   const int len = meta_len(P.mm, b, P.T);
   const int j0 = kt * BN;
-  const int n_qt_live = (len + BM - 1) / BM;                      // query tiles holding at least one live row
-  int q_start = P.mm.kv_tile_q_start ? P.mm.kv_tile_q_start[(size_t)b * P.n_t + kt] : kt;
-  if (j0 >= len) q_start = n_qt_live;
-  const int n_q = max(0, n_qt_live - q_start);
+  uint16_t* const qlist = reinterpret_cast<uint16_t*>(smem_gen + SMEM_QLIST);
 
   if (tid == 0) {
     mbar_init(BAR(KV_FULL), 1);
     for (int i = 0; i < Q_STAGES; ++i) { mbar_init(BAR(Q_FULL + i), 1); mbar_init(BAR(Q_EMPTY + i), 1); }
     for (int i = 0; i < DO_STAGES; ++i) { mbar_init(BAR(DO_FULL + i), 1); mbar_init(BAR(DO_EMPTY + i), 1); }
     mbar_init(BAR(S_FULL), 1); mbar_init(BAR(P_READY), 256); mbar_init(BAR(DP_FULL), 1);
-    mbar_init(BAR(DS_READY), 256); mbar_init(BAR(DQ_FULL), 1); mbar_init(BAR(DQ_DRAINED), 256);
+    mbar_init(BAR(DS_READY), 256); mbar_init(BAR(DQ_FULL), 1); mbar_init(BAR(DQ_DRAINED), 128);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<512>(smem_u32(&tmem_base_s));
@@ -111,10 +98,46 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
     tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_k); tma_prefetch_desc(&map_v); tma_prefetch_desc(&map_do);
     tma_prefetch_desc(&map_dq);
   }
+  if (warp == 3) {
+    // list of query tiles to visit, ascending
+    const int n_live = (len + BM - 1) / BM;
+    const int lane = tid & 31;
+    int n = 0;
+    if (j0 < len) {
+      if (P.mm.kv_tile_q_mask) {
+        const uint32_t* mrow = P.mm.kv_tile_q_mask + ((size_t)b * P.n_t + kt) * P.n_words;
+        for (int w0 = 0; w0 < P.n_words; w0 += 32) {
+          const int w = w0 + lane;
+          uint32_t word = (w < P.n_words) ? mrow[w] : 0u;
+          if (w * 32 >= n_live) word = 0u;                                        // keep only live tiles
+          else if (w * 32 + 32 > n_live) word &= (1u << (n_live - w * 32)) - 1u;
+          const int cnt = __popc(word);
+          int incl = cnt;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+          }
+          int pos = n + incl - cnt;
+          while (word) {
+            const int bit = __ffs(word) - 1;
+            word &= word - 1;
+            qlist[pos++] = (uint16_t)(w * 32 + bit);
+          }
+          n += __shfl_sync(0xffffffffu, incl, 31);
+        }
+      } else {
+        for (int qt = kt + lane; qt < n_live; qt += 32) qlist[qt - kt] = (uint16_t)qt;
+        n = max(0, n_live - kt);
+      }
+    }
+    if (lane == 0) n_q_s = n;
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
+  const int n_q = n_q_s;
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -126,7 +149,7 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
         tma_load_4d(smem_base + SMEM_V + a * ATOM_BYTES, &map_v, BAR(KV_FULL), a * 32, j0, h, b);
       }
       for (int it = 0; it < n_q; ++it) {
-        const int i0 = (q_start + it) * BM;
+        const int i0 = (int)qlist[it] * BM;
         const int sq = it % Q_STAGES, sd = it % DO_STAGES;
         mbar_wait(BAR(Q_EMPTY + sq), ((it / Q_STAGES) & 1) ^ 1);
         mbar_arrive_expect_tx(BAR(Q_FULL + sq), TILE_BYTES);
@@ -142,15 +165,18 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
     // ------------------------------------------------------------------ MMA issuer
     setmaxnreg_dec<REGS_CTRL>();
     if (elect_one() && n_q > 0) {
-      constexpr uint32_t IDESC_SS_KK = umma_idesc_bf16(128, 128, 0, 0);   // S^T, dP^T
-      constexpr uint32_t IDESC_N96_BMN = umma_idesc_bf16(128, 96, 0, 1);  // dV (TS), dK (SS)
+      constexpr uint32_t IDESC_SS_KK = umma_idesc_bf16(128, 128, 0, 0);       // S^T, dP^T
+      constexpr uint32_t IDESC_N96_BMN = umma_idesc_bf16(128, 96, 0, 1);      // dV (TS), dK (SS)
       constexpr uint32_t IDESC_N96_AMN_BMN = umma_idesc_bf16(128, 96, 1, 1);  // dQ
       const uint32_t sK = smem_base + SMEM_K, sV = smem_base + SMEM_V, sDS = smem_base + SMEM_DS;
-      auto kmajor = [](uint32_t base, int k) {  // 16-element K step k of a [rows][96|128] K-major SW64 tile
-        return umma_smem_desc(base + (k >> 1) * ATOM_BYTES + (k & 1) * 32, 16, 512, UMMA_SW64);
+      // descriptors differ only in the 14-bit start-address field: build the constant parts once
+      const uint64_t DESC_KMAJ = umma_smem_desc(0, 16, 512, UMMA_SW64);
+      const uint64_t DESC_MNMAJ = umma_smem_desc(0, ATOM_BYTES, 512, UMMA_SW64);
+      auto kmajor = [&](uint32_t base, int k) {   // 16-element K step k of a [rows][96|128] K-major SW64 tile
+        return DESC_KMAJ | (uint64_t)(((base + (k >> 1) * ATOM_BYTES + (k & 1) * 32) >> 4) & 0x3FFFu);
       };
-      auto mnmajor = [](uint32_t base, int k) {  // 16-row K step k of a tile read as MN-major
-        return umma_smem_desc(base + k * 1024, ATOM_BYTES, 512, UMMA_SW64);
+      auto mnmajor = [&](uint32_t base, int k) {  // 16-row K step k of a tile read as MN-major
+        return DESC_MNMAJ | (uint64_t)(((base + k * 1024) >> 4) & 0x3FFFu);
       };
       auto issue_s = [&](int it) {
         const uint32_t sQ = smem_base + SMEM_Q + (it % Q_STAGES) * TILE_BYTES;
@@ -201,8 +227,8 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
         umma_commit(BAR(Q_EMPTY + it % Q_STAGES));
         // dP^T of the next query tile overwrites the dQ region: wait until it has been drained
         if (it + 1 < n_q) {
-          mbar_wait(BAR(DQ_DRAINED), it & 1);
           mbar_wait(BAR(DO_FULL + (it + 1) % DO_STAGES), ((it + 1) / DO_STAGES) & 1);
+          mbar_wait(BAR(DQ_DRAINED), it & 1);
           tc_fence_after();
           issue_dp(it + 1);
           umma_commit(BAR(DP_FULL));
@@ -211,42 +237,43 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
     }
   } else if (warp < 4) {
     setmaxnreg_dec<REGS_CTRL>();
-  } else {
-    // ------------------------------------------------------------------ compute warps
+  } else if (warp < 12) {
+    // ------------------------------------------------------------------ compute warps: P^T and dS^T
     setmaxnreg_inc<REGS_COMPUTE>();
     const int ct = tid - 128;                 // 0..255
     const int r = ct & 127;                   // key row within the tile == TMEM lane
-    const int hq = ct >> 7;                   // which half of the query columns / output columns
+    const int hq = ct >> 7;                   // which half of the query columns
     const int j = j0 + r;                     // key index
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-    const uint32_t stats = smem_base + SMEM_STATS;
+    float* const stats_gen = reinterpret_cast<float*>(smem_gen + SMEM_STATS);
     const size_t bhT = ((size_t)b * P.H + h) * P.T;
 
     // key-side predicate bits
     bool k_valid = (j < len), k_mutual = (j < len);
     if (j < len && P.mm.vbits) k_valid = (P.mm.vbits[(size_t)b * P.mm.bits_pitch + (j >> 5)] >> (j & 31)) & 1u;
     if (j < len && P.mm.mbits) k_mutual = (P.mm.mbits[(size_t)b * P.mm.bits_pitch + (j >> 5)] >> (j & 31)) & 1u;
+    const bool warp_keys_valid = __all_sync(0xffffffffu, k_valid);
 
     // per-tile row statistics are fetched one tile ahead into registers, then published to smem
     float pre_a = 0.f, pre_b = 0.f;           // hq==0: (lse*log2e, delta) ; hq==1: (row_lo, row_hi) as int bits
     auto prefetch = [&](int it) {
-      const int i = (q_start + it) * BM + r;
+      const int i = (int)qlist[it] * BM + r;
       if (hq == 0) {
-        pre_a = (i < len) ? P.lse[bhT + i] * 1.4426950408889634f : INFINITY;
-        pre_b = (i < len) ? P.delta[bhT + i] : 0.f;
+        pre_a = (i < len) ? __ldg(P.lse + bhT + i) * 1.4426950408889634f : INFINITY;
+        pre_b = (i < len) ? __ldg(P.delta + bhT + i) : 0.f;
       } else {
         int lo = 0, hi = 0;
         if (i < len && P.mm.row_lo) {
-          lo = P.mm.row_lo[(size_t)b * P.mm.meta_pitch + i];
-          hi = P.mm.row_hi[(size_t)b * P.mm.meta_pitch + i];
+          lo = __ldg(P.mm.row_lo + (size_t)b * P.mm.meta_pitch + i);
+          hi = __ldg(P.mm.row_hi + (size_t)b * P.mm.meta_pitch + i);
         }
         pre_a = __int_as_float(lo); pre_b = __int_as_float(hi);
       }
     };
-    auto publish = [&](int it) {
-      const uint32_t base = stats + (it & 1) * 2048 + hq * 1024 + r * 4;
-      asm volatile("st.shared.f32 [%0], %1;" ::"r"(base), "f"(pre_a) : "memory");
-      asm volatile("st.shared.f32 [%0], %1;" ::"r"(base + 512), "f"(pre_b) : "memory");
+    auto publish = [&](int it) {   // stage layout: [lse2 128][delta 128][lo 128][hi 128]
+      float* st = stats_gen + (it & 1) * 512 + hq * 256;
+      st[r] = pre_a;
+      st[128 + r] = pre_b;
     };
 
     float p[64];   // P^T row half, kept from phase a to phase b
@@ -255,38 +282,43 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
       publish(it);
       if (it + 1 < n_q) prefetch(it + 1);
       named_bar_sync(1, 256);
-      const int qt = q_start + it, i0 = qt * BM;
-      const uint32_t st = stats + (it & 1) * 2048;
+      const int qt = (int)qlist[it], i0 = qt * BM;
+      const float* st = stats_gen + (it & 1) * 512;
       mbar_wait(BAR(S_FULL), it & 1);
       tc_fence_after();
       uint32_t sraw[64];
       tmem_ld_x32(tmem + TM_S + lane_base + 64 * hq, sraw);
       tmem_ld_x32(tmem + TM_S + lane_base + 64 * hq + 32, sraw + 32);
+      // fully visible: every key of this warp precedes every query of the tile, all valid, all queries live
+      const bool full = (qt > kt) && (i0 + BM <= len) && warp_keys_valid;
+      const float4* lse4 = reinterpret_cast<const float4*>(st + 64 * hq);
       tmem_wait_ld();
-      // fully visible tile: every key of the tile precedes every (live) query of the tile and is valid
-      const bool full = (qt > kt) && (i0 + BM <= len) && __all_sync(0xffffffffu, k_valid);
-      // NB `full` must be uniform across the 256 threads only for speed, not for correctness
+      if (full) {
 #pragma unroll
-      for (int c4 = 0; c4 < 16; ++c4) {
-        const float4 l4 = lds_v4(st + (64 * hq + 4 * c4) * 4);
-        const float lse4[4] = {l4.x, l4.y, l4.z, l4.w};
-        int lo4[4] = {0, 0, 0, 0}, hi4[4] = {0, 0, 0, 0};
-        if (!full) {
-          const int4 a4 = lds_v4i(st + 1024 + (64 * hq + 4 * c4) * 4);
-          const int4 e4 = lds_v4i(st + 1536 + (64 * hq + 4 * c4) * 4);
-          lo4[0] = a4.x; lo4[1] = a4.y; lo4[2] = a4.z; lo4[3] = a4.w;
-          hi4[0] = e4.x; hi4[1] = e4.y; hi4[2] = e4.z; hi4[3] = e4.w;
+        for (int c4 = 0; c4 < 16; ++c4) {
+          const float4 v = lse4[c4];
+          p[4 * c4 + 0] = ex2_approx(fmaf(__uint_as_float(sraw[4 * c4 + 0]), P.scale_log2, -v.x));
+          p[4 * c4 + 1] = ex2_approx(fmaf(__uint_as_float(sraw[4 * c4 + 1]), P.scale_log2, -v.y));
+          p[4 * c4 + 2] = ex2_approx(fmaf(__uint_as_float(sraw[4 * c4 + 2]), P.scale_log2, -v.z));
+          p[4 * c4 + 3] = ex2_approx(fmaf(__uint_as_float(sraw[4 * c4 + 3]), P.scale_log2, -v.w));
         }
+      } else {
+        const int4* lo4 = reinterpret_cast<const int4*>(st + 256 + 64 * hq);
+        const int4* hi4 = reinterpret_cast<const int4*>(st + 384 + 64 * hq);
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int c = 4 * c4 + e;
-          float val = ex2_approx(fmaf(__uint_as_float(sraw[c]), P.scale_log2, -lse4[e]));
-          if (!full) {
+        for (int c4 = 0; c4 < 16; ++c4) {
+          const int4 a4 = lo4[c4], e4 = hi4[c4];
+          const float4 l4 = lse4[c4];
+          const float lse2[4] = {l4.x, l4.y, l4.z, l4.w};
+          const int lo[4] = {a4.x, a4.y, a4.z, a4.w}, hi[4] = {e4.x, e4.y, e4.z, e4.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int c = 4 * c4 + e;
             const int i = i0 + 64 * hq + c;
-            const bool ok = (i < len) && ((j <= i && k_valid) || (j >= lo4[e] && j < hi4[e] && k_mutual));
-            val = ok ? val : 0.f;
+            const bool ok = (i < len) && ((j <= i && k_valid) || (j >= lo[e] && j < hi[e] && k_mutual));
+            const float val = ex2_approx(fmaf(__uint_as_float(sraw[c]), P.scale_log2, -lse2[e]));
+            p[c] = ok ? val : 0.f;
           }
-          p[c] = val;
         }
       }
       uint32_t pk[32];
@@ -299,31 +331,25 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
     };
 
     auto phase_b = [&](int it) {
-      const uint32_t st = stats + (it & 1) * 2048;
+      const float* st = stats_gen + (it & 1) * 512 + 128;   // delta
       mbar_wait(BAR(DP_FULL), it & 1);
       tc_fence_after();
       uint32_t draw[64];
       tmem_ld_x32(tmem + TM_DP + lane_base + 64 * hq, draw);
       tmem_ld_x32(tmem + TM_DP + lane_base + 64 * hq + 32, draw + 32);
+      const float4* dl4 = reinterpret_cast<const float4*>(st + 64 * hq);
       tmem_wait_ld();
       const uint32_t ds_base = smem_base + SMEM_DS;
-      // the dS^T buffer doubles as dQ staging: the TMA reduction of the previous tile must have read it
-      if (it > 0) {
-        if (ct == 0) tma_store_wait_read<0>();
-        named_bar_sync(2, 256);
-      }
 #pragma unroll
       for (int c8 = 0; c8 < 8; ++c8) {   // 8 query columns -> one 16-byte chunk of the dS^T row
-        const float4 d0 = lds_v4(st + 512 + (64 * hq + 8 * c8) * 4);
-        const float4 d1 = lds_v4(st + 512 + (64 * hq + 8 * c8 + 4) * 4);
-        const float dl[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
         uint32_t w[4];
+        const float4 da = dl4[2 * c8], db = dl4[2 * c8 + 1];
+        const float dl[8] = {da.x, da.y, da.z, da.w, db.x, db.y, db.z, db.w};
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const int c = 8 * c8 + 2 * e;
-          const float ds0 = p[c] * (__uint_as_float(draw[c]) - dl[2 * e]) * P.scale;
-          const float ds1 = p[c + 1] * (__uint_as_float(draw[c + 1]) - dl[2 * e + 1]) * P.scale;
-          w[e] = pack_bf16x2(ds0, ds1);
+          w[e] = pack_bf16x2(p[c] * (__uint_as_float(draw[c]) - dl[2 * e]),
+                             p[c + 1] * (__uint_as_float(draw[c + 1]) - dl[2 * e + 1]));
         }
         const int col = 64 * hq + 8 * c8;          // query column of this chunk
         const uint32_t addr = ds_base + (col >> 5) * ATOM_BYTES + sw64_offset(r, (col & 31) >> 3);
@@ -334,57 +360,26 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
       mbar_arrive(BAR(DS_READY));
     };
 
-    auto phase_c = [&](int it) {   // drain dQ_it: lane r is now QUERY row r of the tile; this half owns 48 columns
-      const int i0 = (q_start + it) * BM;
-      mbar_wait(BAR(DQ_FULL), it & 1);
-      tc_fence_after();
-      uint32_t dq[48];
-      tmem_ld_x32(tmem + TM_DP + lane_base + 48 * hq, dq);
-      tmem_ld_x16(tmem + TM_DP + lane_base + 48 * hq + 32, dq + 32);
-      tmem_wait_ld();
-      tc_fence_before();
-      mbar_arrive(BAR(DQ_DRAINED));
-      // stage as three [128][32 x fp32] SWIZZLE_128B atoms (atoms 0,1 in the dS^T buffer, which the MMAs have
-      // finished reading once DQ_FULL fired), then one thread issues the TMA reductions
-#pragma unroll
-      for (int x = 0; x < 12; ++x) {
-        const int col = 48 * hq + 4 * x;
-        const int atom = col >> 5, chunk = (col & 31) >> 2;
-        const uint32_t abase = (atom < 2) ? (smem_base + SMEM_DS + atom * DQ_ATOM_BYTES) : (smem_base + SMEM_DQ2);
-        const uint32_t addr = abase + r * 128 + ((chunk ^ (r & 7)) << 4);
-        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(dq[4 * x]), "r"(dq[4 * x + 1]),
-                     "r"(dq[4 * x + 2]), "r"(dq[4 * x + 3]) : "memory");
-      }
-      fence_proxy_async_smem();
-      named_bar_sync(3, 256);
-      if (ct == 0) {
-        tma_reduce_add_4d(&map_dq, smem_base + SMEM_DS, 0, i0, h, b);
-        tma_reduce_add_4d(&map_dq, smem_base + SMEM_DS + DQ_ATOM_BYTES, 32, i0, h, b);
-        tma_reduce_add_4d(&map_dq, smem_base + SMEM_DQ2, 64, i0, h, b);
-        tma_store_commit();
-      }
-    };
-
     if (n_q > 0) {
       prefetch(0);
       phase_a(0);
       for (int it = 0; it < n_q; ++it) {
         phase_b(it);
         if (it + 1 < n_q) phase_a(it + 1);
-        phase_c(it);
       }
-      if (ct == 0) tma_store_wait<0>();   // all dQ reductions have landed before the CTA retires its smem
+      // the last DQ_FULL commit covers every dK / dV MMA
+      mbar_wait(BAR(DQ_FULL), (n_q - 1) & 1);
+      tc_fence_after();
     }
 
-    // ---- epilogue: dV, dK (inverse RoPE) -> bf16 -> global.  tcgen05.ld is warp-collective: the loads are
-    // unconditional, only the global stores are predicated on the row being inside the tensor.
+    // ---- epilogue: dV, dK (x scale, inverse RoPE) -> bf16 -> global.  tcgen05.ld is warp-collective: the loads
+    // are unconditional, only the global stores are predicated on the row being inside the tensor.
     {
       const bool store_row = (j < P.T);
       const int js = store_row ? j : 0;
       __nv_bfloat16* dvrow = P.d_v.row(b, js, h) + 48 * hq;
       __nv_bfloat16* dkrow = P.d_k.row(b, js, h);
       if (n_q > 0) {
-        // DQ_FULL of the last iteration was committed after the last dK MMA (and dV before it): already waited
         uint32_t acc[48];
         tmem_ld_x32(tmem + TM_DV + lane_base + 48 * hq, acc);
         tmem_ld_x16(tmem + TM_DV + lane_base + 48 * hq + 32, acc + 32);
@@ -408,7 +403,7 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
         float flo[24], fhi[24];
 #pragma unroll
         for (int x = 0; x < 24; ++x) {
-          float a = __uint_as_float(lo[x]), e = __uint_as_float(hi[x]);
+          float a = __uint_as_float(lo[x]) * P.scale, e = __uint_as_float(hi[x]) * P.scale;
           if (P.rope_cos) {   // g = R^T g'
             const float c = __ldg(P.rope_cos + (size_t)b * P.rope_stride_b + (size_t)js * 48 + 24 * hq + x);
             const float sn = __ldg(P.rope_sin + (size_t)b * P.rope_stride_b + (size_t)js * 48 + 24 * hq + x);
@@ -440,6 +435,44 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
         }
       }
     }
+  } else {
+    // ------------------------------------------------------------------ dQ drain warps (lane r <-> QUERY row r)
+    setmaxnreg_dec<REGS_DRAIN>();
+    const int r = tid - 384;
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    for (int it = 0; it < n_q; ++it) {
+      const int i0 = (int)qlist[it] * BM;
+      mbar_wait(BAR(DQ_FULL), it & 1);
+      tc_fence_after();
+      uint32_t dq[96];
+      tmem_ld_x32(tmem + TM_DP + lane_base, dq);
+      tmem_ld_x32(tmem + TM_DP + lane_base + 32, dq + 32);
+      tmem_ld_x32(tmem + TM_DP + lane_base + 64, dq + 64);
+      tmem_wait_ld();
+      tc_fence_before();
+      mbar_arrive(BAR(DQ_DRAINED));
+      // three [128][32 x fp32] SWIZZLE_128B atoms through two staging buffers
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        const int buf = (it * 3 + a) & 1;
+        const uint32_t abase = smem_base + SMEM_DQ + buf * DQ_ATOM_BYTES;
+        if (r == 0) tma_store_wait_read<1>();       // the reduction that last read this buffer has finished reading
+        named_bar_sync(2, 128);
+#pragma unroll
+        for (int x = 0; x < 8; ++x) {
+          const uint32_t addr = abase + r * 128 + ((x ^ (r & 7)) << 4);
+          asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(dq[32 * a + 4 * x]),
+                       "r"(dq[32 * a + 4 * x + 1]), "r"(dq[32 * a + 4 * x + 2]), "r"(dq[32 * a + 4 * x + 3]) : "memory");
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(3, 128);
+        if (r == 0) {
+          tma_reduce_add_4d(&map_dq, abase, 32 * a, i0, h, b);
+          tma_store_commit();
+        }
+      }
+    }
+    if (r == 0) tma_store_wait<0>();   // all dQ reductions have landed before the CTA retires its smem
   }
   tc_fence_before();
   __syncthreads();
@@ -477,11 +510,13 @@ extern "C" int aki_mma_attn_bwd(const AkiMmaAttnBwdParams* p, aki_stream_t strea
   if ((rc = make_dq_accum_map(&mdq, w.dq_accum, f.B, f.H, f.T))) return rc;
   BwdKernelParams kp;
   kp.d_k = view_of(p->d_k); kp.d_v = view_of(p->d_v);
-  kp.lse = f.lse; kp.delta = w.delta; kp.dq_accum = w.dq_accum;
+  kp.lse = f.lse; kp.delta = w.delta;
   kp.rope_cos = f.rope_cos; kp.rope_sin = f.rope_sin; kp.rope_stride_b = f.rope_stride_b;
   kp.mm = mask_meta_from(f);
   kp.B = f.B; kp.H = f.H; kp.T = f.T;
   kp.n_t = (f.T + bwd::BN - 1) / bwd::BN;
+  kp.n_words = (kp.n_t + 31) / 32;
+  AKI_REQUIRE(kp.n_t <= bwd::MAX_TILES, AKI_ERR_UNSUPPORTED);
   kp.scale = f.scale;
   kp.scale_log2 = f.scale * 1.4426950408889634f;
   const long long grid = (long long)kp.n_t * f.H * f.B;
@@ -497,5 +532,5 @@ extern "C" int aki_mma_attn_bwd(const AkiMmaAttnBwdParams* p, aki_stream_t strea
   }
   attn_bwd_sm100_kernel<<<(unsigned)grid, bwd::THREADS, bwd::SMEM_ALLOC, st>>>(mq, mk, mv, mdo, mdq, kp);
   if ((rc = check_launch())) return rc;
-  return launch_dq_finalize(*p, w, st);
+  return launch_dq_finalize(*p, w, f.scale, st);   // dS^T is kept unscaled inside the kernel
 }

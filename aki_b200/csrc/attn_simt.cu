@@ -121,12 +121,12 @@ bwd_preprocess_kernel(TensorView q, TensorView o, TensorView d_o, const float* _
 // dq_accum (B,H,T,D) fp32 -> inverse RoPE -> bf16 strided d_q.   g = R^T g' :  lo = lo'*c + hi'*s ; hi = hi'*c - lo'*s
 __global__ void __launch_bounds__(128)
 dq_finalize_kernel(const float* __restrict__ dq_accum, TensorView d_q, const float* __restrict__ rope_cos,
-                   const float* __restrict__ rope_sin, int64_t rope_stride_b, int T, int H) {
+                   const float* __restrict__ rope_sin, int64_t rope_stride_b, int T, int H, float scale) {
   const int t = blockIdx.x, b = blockIdx.y;
   for (int idx = threadIdx.x; idx < H * 48; idx += 128) {
     const int h = idx / 48, d = idx - h * 48;
     const float* src = dq_accum + (((size_t)b * H + h) * T + t) * 96;
-    float lo = src[d], hi = src[d + 48];
+    float lo = src[d] * scale, hi = src[d + 48] * scale;
     if (rope_cos) {
       const float c = rope_cos[(size_t)b * rope_stride_b + (size_t)t * 48 + d];
       const float s = rope_sin[(size_t)b * rope_stride_b + (size_t)t * 48 + d];
@@ -262,10 +262,10 @@ int launch_bwd_preprocess(const AkiMmaAttnBwdParams& p, const BwdWorkspace& w, c
   return check_launch();
 }
 
-int launch_dq_finalize(const AkiMmaAttnBwdParams& p, const BwdWorkspace& w, cudaStream_t st) {
+int launch_dq_finalize(const AkiMmaAttnBwdParams& p, const BwdWorkspace& w, float scale, cudaStream_t st) {
   const AkiMmaAttnParams& f = p.fwd;
   dq_finalize_kernel<<<dim3(f.T, f.B), 128, 0, st>>>(w.dq_accum, view_of(p.d_q), f.rope_cos, f.rope_sin,
-                                                      f.rope_stride_b, f.T, f.H);
+                                                      f.rope_stride_b, f.T, f.H, scale);
   return check_launch();
 }
 
@@ -331,5 +331,5 @@ extern "C" int aki_mma_attn_bwd_simt(const AkiMmaAttnBwdParams* p, aki_stream_t 
                                                                      view_of(p->d_v), f.rope_cos, f.rope_sin,
                                                                      f.rope_stride_b, mm, f.T, f.H, f.scale);
   if ((rc = check_launch())) return rc;
-  return launch_dq_finalize(*p, w, st);
+  return launch_dq_finalize(*p, w, 1.0f, st);   // the SIMT kernels already folded scale into dS
 }

@@ -14,7 +14,7 @@ struct MaskMeta {
   const uint32_t* vbits;
   const uint32_t* mbits;
   const int32_t* q_tile_kv_end;
-  const int32_t* kv_tile_q_start;
+  const uint32_t* kv_tile_q_mask;
   int meta_pitch, bits_pitch;
 };
 
@@ -22,7 +22,7 @@ inline MaskMeta mask_meta_from(const AkiMmaAttnParams& p) {
   MaskMeta m;
   m.seq_len = p.seq_len; m.row_lo = p.row_lo; m.row_hi = p.row_hi;
   m.vbits = p.kv_valid_bits; m.mbits = p.kv_mutual_bits;
-  m.q_tile_kv_end = p.q_tile_kv_end; m.kv_tile_q_start = p.kv_tile_q_start;
+  m.q_tile_kv_end = p.q_tile_kv_end; m.kv_tile_q_mask = p.kv_tile_q_mask;
   m.meta_pitch = p.meta_pitch; m.bits_pitch = p.bits_pitch;
   return m;
 }

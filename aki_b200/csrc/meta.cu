@@ -138,14 +138,16 @@ segments_kernel(const int64_t* __restrict__ lang_x, const int64_t* __restrict__ 
 
 __global__ void __launch_bounds__(128)
 tile_bounds_kernel(const int32_t* __restrict__ seq_len, const int32_t* __restrict__ row_lo,
-                   const int32_t* __restrict__ row_hi, int T, int t_cap, int n_tiles,
-                   int32_t* __restrict__ q_tile_kv_end, int32_t* __restrict__ kv_tile_q_start) {
+                   const int32_t* __restrict__ row_hi, int T, int t_cap, int n_tiles, int n_words,
+                   int32_t* __restrict__ q_tile_kv_end, uint32_t* __restrict__ kv_tile_q_mask) {
   const int tile = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
   const int len = min(seq_len[b], T);
   const int32_t* lo = row_lo + (size_t)b * t_cap;
   const int32_t* hi = row_hi + (size_t)b * t_cap;
-  __shared__ int s_max, s_min;
-  if (tid == 0) { s_max = 0; s_min = n_tiles; }
+  __shared__ int s_max;
+  __shared__ uint32_t s_mask[64];   // up to 2048 tiles (T <= 262144)
+  if (tid == 0) s_max = 0;
+  for (int w = tid; w < n_words; w += 128) s_mask[w] = 0u;
   __syncthreads();
   const int r0 = tile * AKI_MMA_TILE;
   // query tile: how far right do its rows look
@@ -157,22 +159,20 @@ tile_bounds_kernel(const int32_t* __restrict__ seq_len, const int32_t* __restric
     if (e > a) need = max(need, min(e, len));
   }
   atomicMax(&s_max, need);
-  // key tile: first query tile with a row that sees any of its keys
-  int first = n_tiles;
+  // key tile: which query tiles hold a row that sees any of its keys
   if (r0 < len) {
     const int j1 = min(r0 + AKI_MMA_TILE, len);
-    first = tile;  // rows i >= r0 see key r0 causally
-    for (int r = tid; r < r0; r += 128) {
+    const int n_live = (len + AKI_MMA_TILE - 1) / AKI_MMA_TILE;
+    for (int qt = tile + tid; qt < n_live; qt += 128) atomicOr(&s_mask[qt >> 5], 1u << (qt & 31));  // causal part
+    for (int r = tid; r < r0; r += 128) {                                                         // mutual part
       const int a = lo[r], e = hi[r];
-      if (e > a && e > r0 && a < j1) first = min(first, r / AKI_MMA_TILE);
+      if (e > a && e > r0 && a < j1) atomicOr(&s_mask[(r / AKI_MMA_TILE) >> 5], 1u << ((r / AKI_MMA_TILE) & 31));
     }
   }
-  atomicMin(&s_min, first);
   __syncthreads();
-  if (tid == 0) {
-    if (q_tile_kv_end) q_tile_kv_end[(size_t)b * n_tiles + tile] = (s_max + AKI_MMA_TILE - 1) / AKI_MMA_TILE;
-    if (kv_tile_q_start) kv_tile_q_start[(size_t)b * n_tiles + tile] = s_min;
-  }
+  if (tid == 0 && q_tile_kv_end) q_tile_kv_end[(size_t)b * n_tiles + tile] = (s_max + AKI_MMA_TILE - 1) / AKI_MMA_TILE;
+  if (kv_tile_q_mask)
+    for (int w = tid; w < n_words; w += 128) kv_tile_q_mask[((size_t)b * n_tiles + tile) * n_words + w] = s_mask[w];
 }
 
 __global__ void __launch_bounds__(256)
@@ -237,12 +237,14 @@ extern "C" int aki_mma_segments(const int64_t* lang_x, const int64_t* attention_
 }
 
 extern "C" int aki_mma_tile_bounds(const int32_t* seq_len, const int32_t* row_lo, const int32_t* row_hi, int B, int T,
-                                   int t_cap, int32_t* q_tile_kv_end, int32_t* kv_tile_q_start, aki_stream_t stream) {
+                                   int t_cap, int32_t* q_tile_kv_end, uint32_t* kv_tile_q_mask, aki_stream_t stream) {
   AKI_REQUIRE(seq_len && row_lo && row_hi, AKI_ERR_NULL);
   AKI_REQUIRE(B > 0 && T > 0 && t_cap >= T, AKI_ERR_BAD_SHAPE);
   const int n_tiles = (T + AKI_MMA_TILE - 1) / AKI_MMA_TILE;
+  const int n_words = (n_tiles + 31) / 32;
+  AKI_REQUIRE(n_words <= 64, AKI_ERR_UNSUPPORTED);
   tile_bounds_kernel<<<dim3(n_tiles, B), 128, 0, static_cast<cudaStream_t>(stream)>>>(
-      seq_len, row_lo, row_hi, T, t_cap, n_tiles, q_tile_kv_end, kv_tile_q_start);
+      seq_len, row_lo, row_hi, T, t_cap, n_tiles, n_words, q_tile_kv_end, kv_tile_q_mask);
   return check_launch();
 }
 

@@ -52,7 +52,7 @@ class MMASegments:
     kv_valid_bits: torch.Tensor    # (B,ceil(T/32)) int32 (bit pattern of uint32)
     kv_mutual_bits: torch.Tensor   # (B,ceil(T/32)) int32
     q_tile_kv_end: torch.Tensor    # (B,ceil(T/128)) int32
-    kv_tile_q_start: torch.Tensor  # (B,ceil(T/128)) int32
+    kv_tile_q_mask: torch.Tensor   # (B,ceil(T/128),ceil(ceil(T/128)/32)) int32 (bit pattern of uint32)
     T: int
 
     @property
@@ -80,16 +80,16 @@ class MMASegments:
             self.seq_len, self.q_end, self.seg[:, :T].contiguous(), self.row_lo[:, :T].contiguous(),
             self.row_hi[:, :T].contiguous(), self.src[:, :T].contiguous(),
             self.kv_valid_bits[:, :(T + 31) // 32].contiguous(), self.kv_mutual_bits[:, :(T + 31) // 32].contiguous(),
-            self.q_tile_kv_end, self.kv_tile_q_start, T))
+            self.q_tile_kv_end, self.kv_tile_q_mask, T))
 
 
 def rebuild_tile_bounds(s: MMASegments) -> MMASegments:
     nt = (s.T + TILE - 1) // TILE
     dev = s.seq_len.device
     s.q_tile_kv_end = torch.empty(s.B, nt, dtype=torch.int32, device=dev)
-    s.kv_tile_q_start = torch.empty(s.B, nt, dtype=torch.int32, device=dev)
+    s.kv_tile_q_mask = torch.empty(s.B, nt, (nt + 31) // 32, dtype=torch.int32, device=dev)
     check(lib.aki_mma_tile_bounds(_ptr(s.seq_len), _ptr(s.row_lo), _ptr(s.row_hi), s.B, s.T, s.T,
-                                  _ptr(s.q_tile_kv_end), _ptr(s.kv_tile_q_start), _stream()), "aki_mma_tile_bounds")
+                                  _ptr(s.q_tile_kv_end), _ptr(s.kv_tile_q_mask), _stream()), "aki_mma_tile_bounds")
     return s
 
 
@@ -212,7 +212,7 @@ def _fill_params(p: AttnParams, q, k, v, o, lse, cos, sin, meta, scale):
         seq_len, row_lo, row_hi, vbits, mbits, qkv_end, kvq_start = meta
         p.seq_len, p.row_lo, p.row_hi = _ptr(seq_len), _ptr(row_lo), _ptr(row_hi)
         p.kv_valid_bits, p.kv_mutual_bits = _ptr(vbits), _ptr(mbits)
-        p.q_tile_kv_end, p.kv_tile_q_start = _ptr(qkv_end), _ptr(kvq_start)
+        p.q_tile_kv_end, p.kv_tile_q_mask = _ptr(qkv_end), _ptr(kvq_start)
         p.meta_pitch = row_lo.shape[1] if row_lo is not None else 0
         p.bits_pitch = vbits.shape[1] if vbits is not None else 0
         if row_lo is not None:
@@ -225,7 +225,7 @@ def meta_tuple(segs: Optional[MMASegments]):
     if segs is None:
         return None
     return (segs.seq_len, segs.row_lo, segs.row_hi, segs.kv_valid_bits, segs.kv_mutual_bits, segs.q_tile_kv_end,
-            segs.kv_tile_q_start)
+            segs.kv_tile_q_mask)
 
 
 def attn_fwd_raw(q, k, v, cos, sin, meta, scale, need_lse=True, simt=False):
@@ -263,15 +263,15 @@ _OT = Optional[torch.Tensor]
 @torch.library.custom_op("aki_mma::attn", mutates_args=())
 def attn_op(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, scale: float, seq_len: _OT = None, row_lo: _OT = None,
             row_hi: _OT = None, vbits: _OT = None, mbits: _OT = None, q_tile_kv_end: _OT = None,
-            kv_tile_q_start: _OT = None) -> Tuple[torch.Tensor, torch.Tensor]:
+            kv_tile_q_mask: _OT = None) -> Tuple[torch.Tensor, torch.Tensor]:
     """q,k,v (B,T,H,D) logical, already rotated.  Returns o (B,T,H,D), lse (B,H,T)."""
-    meta = None if seq_len is None else (seq_len, row_lo, row_hi, vbits, mbits, q_tile_kv_end, kv_tile_q_start)
+    meta = None if seq_len is None else (seq_len, row_lo, row_hi, vbits, mbits, q_tile_kv_end, kv_tile_q_mask)
     return attn_fwd_raw(q, k, v, None, None, meta, scale)
 
 
 @attn_op.register_fake
 def _(q, k, v, scale, seq_len=None, row_lo=None, row_hi=None, vbits=None, mbits=None, q_tile_kv_end=None,
-      kv_tile_q_start=None):
+      kv_tile_q_mask=None):
     B, T, H, D = q.shape
     return q.new_empty(B, T, H, D), q.new_empty(B, H, T, dtype=torch.float32)
 
@@ -299,7 +299,7 @@ attn_op.register_autograd(_attn_backward, setup_context=_attn_setup)
 @torch.library.custom_op("aki_mma::attn_packed", mutates_args=())
 def attn_packed_op(qkv: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor, num_heads: int, scale: float,
                    seq_len: _OT = None, row_lo: _OT = None, row_hi: _OT = None, vbits: _OT = None, mbits: _OT = None,
-                   q_tile_kv_end: _OT = None, kv_tile_q_start: _OT = None
+                   q_tile_kv_end: _OT = None, kv_tile_q_mask: _OT = None
                    ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
     """qkv (B,T,3*H*D) bf16 straight from qkv_proj; cos/sin (B|1,T,D/2) fp32.
     Returns o (B,T,H*D), lse (B,H,T), k_rot (B,H,T,D) (post-RoPE keys, kept for backward)."""
@@ -309,14 +309,14 @@ def attn_packed_op(qkv: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor, num_
     rope_kv_write(qkv, cos, sin, k_rot, None, 0, H)
     q4 = qkv[..., : H * D].unflatten(-1, (H, D))
     v4 = qkv[..., 2 * H * D:].unflatten(-1, (H, D))
-    meta = None if seq_len is None else (seq_len, row_lo, row_hi, vbits, mbits, q_tile_kv_end, kv_tile_q_start)
+    meta = None if seq_len is None else (seq_len, row_lo, row_hi, vbits, mbits, q_tile_kv_end, kv_tile_q_mask)
     o, lse = attn_fwd_raw(q4, k_rot.transpose(1, 2), v4, cos, sin, meta, scale)
     return o.view(B, T, H * D), lse, k_rot
 
 
 @attn_packed_op.register_fake
 def _(qkv, cos, sin, num_heads, scale, seq_len=None, row_lo=None, row_hi=None, vbits=None, mbits=None,
-      q_tile_kv_end=None, kv_tile_q_start=None):
+      q_tile_kv_end=None, kv_tile_q_mask=None):
     B, T, _ = qkv.shape
     return (qkv.new_empty(B, T, num_heads * HEAD_DIM), qkv.new_empty(B, num_heads, T, dtype=torch.float32),
             qkv.new_empty(B, num_heads, T, HEAD_DIM))

@@ -73,12 +73,15 @@ int aki_mma_segments(const int64_t* lang_x, const int64_t* attention_mask, int B
                      int32_t* src, uint32_t* kv_valid_bits, uint32_t* kv_mutual_bits, int32_t* status,
                      aki_stream_t stream);
 
-/* Per-tile loop bounds for AKI_MMA_TILE-row tiles (derived data the attention kernels consume so that fully
- * masked tiles are never visited):
- *   q_tile_kv_end  (B, ceil(T/128)) : number of key tiles query tile qt must visit (0 = tile is all padding)
- *   kv_tile_q_start(B, ceil(T/128)) : first query tile that sees any key of key tile kt (backward) */
+/* Per-tile visit lists for AKI_MMA_TILE-row tiles (derived data the attention kernels consume so that fully
+ * masked tiles are never visited).  n_t = ceil(T/128), W = ceil(n_t/32):
+ *   q_tile_kv_end  (B, n_t)    : number of key tiles query tile qt must visit (0 = tile is all padding); the
+ *                                visible key tiles of a query tile are always the contiguous range [0, end)
+ *   kv_tile_q_mask (B, n_t, W) : bit qt of row kt is set iff some live row of query tile qt sees some key of
+ *                                key tile kt (backward: with MMA this set is NOT contiguous -- the image-row
+ *                                tiles before the diagonal plus everything from the diagonal on) */
 int aki_mma_tile_bounds(const int32_t* seq_len, const int32_t* row_lo, const int32_t* row_hi, int B, int T,
-                        int t_cap, int32_t* q_tile_kv_end, int32_t* kv_tile_q_start, aki_stream_t stream);
+                        int t_cap, int32_t* q_tile_kv_end, uint32_t* kv_tile_q_mask, aki_stream_t stream);
 
 /* Debug / parity helper: expand the compact description to the reference's (B,1,T,T) int64 0/1 tensor
  * (what _prepare_inputs_for_forward returns under "attention_mask", vlm.py:589-603). */
@@ -145,7 +148,7 @@ typedef struct AkiMmaAttnParams {
   const uint32_t* kv_valid_bits;   /* (B, bits_pitch) */
   const uint32_t* kv_mutual_bits;  /* (B, bits_pitch) */
   const int32_t* q_tile_kv_end;    /* (B, ceil(T/128)) */
-  const int32_t* kv_tile_q_start;  /* (B, ceil(T/128)); backward only */
+  const uint32_t* kv_tile_q_mask;  /* (B, ceil(T/128), ceil(ceil(T/128)/32)); backward only */
   int32_t meta_pitch, bits_pitch;
 } AkiMmaAttnParams;
 
