@@ -5,22 +5,22 @@
 // equivalent transformers/models/phi3/modeling_phi3.py:153-175) fed by the reference's materialised
 // (B,1,T,T) mask (codes/open_flamingo/src/vlm.py:410-443).  No mask is read from HBM: the predicate
 //   allowed(i,j) = (j<=i & valid[j]) | (row_lo[i]<=j<row_hi[i] & mutual_ok[j])
-// is evaluated in registers on the few tiles that are not fully visible, and tiles beyond
+// is evaluated in registers on the few tiles that are not fully visible, and key tiles beyond
 // q_tile_kv_end[b][qt] are never visited.  RoPE is applied to Q in shared memory right after the TMA load.
 //
-// CTA = 2 query tiles x 128 rows of one (batch, head); 20 warps:
-//   warp 0        TMA producer (Q once, then K_j / V_j through two 3-deep rings)
-//   warp 1        MMA issuer (one elected lane): S_t = Q_t K_j^T (SS), O_t += P_t V_j (TS, P read from TMEM)
-//   warp 2        TMEM allocator;   warp 3 idle
-//   warps 4-11    softmax of tile 0: thread <-> row r <-> TMEM lane r; warps 4-7 own key columns [0,64) of the
-//                 128-key tile, warps 8-11 columns [64,128) (row max / row sum exchanged through shared memory)
-//   warps 12-19   softmax of tile 1, same split
-// Four softmax warps per SM sub-partition (instead of two) keep the MUFU (exp2) pipe -- the real bound of this
-// head_dim (128 exp vs 768 tensor cycles per row tile) -- busy while other warps wait on TMEM / barriers.
-// TMEM columns: S0 [0,128) S1 [128,256) O0 [256,352) O1 [352,448); P_t (bf16 pairs) aliases S_t[0,64).
-// Shared memory: Q 2x24 KB, K ring 3x24 KB, V ring 3x24 KB; every tile is 3 SWIZZLE_64B atoms [128][64 B]
-// (head_dim 96 = 3 x 32), the layout both the TMA boxes and the UMMA descriptors use (validated by
-// tools/umma_probe.cu).
+// CTA = 2 query tiles x 128 rows of one (batch, head), key tiles of 64; 12 warps:
+//   warp 0      TMA producer (Q once, then K_j / V_j through two 4-deep rings of 12 KB tiles)
+//   warp 1      MMA issuer: S_t[j&1] = Q_t K_j^T (SS, N=64), O_t += P_t V_j (TS, P read from TMEM)
+//   warp 2      TMEM allocator;   warp 3 idle
+//   warps 4-7   softmax of tile 0 (thread r <-> row r <-> TMEM lane r), warps 8-11 softmax of tile 1
+// S is DOUBLE-BUFFERED per query tile (that is why the key tile is 64 wide: 4 x 64 S columns + 2 x 96 O + 2 x 32 P
+// = 512 TMEM columns exactly): QK^T of key tile j+2 is issued as soon as the softmax has read S(j), so a softmax
+// warp goes straight from tile j to tile j+1 and the chain softmax -> PV -> QK -> softmax of the single-buffered
+// design (measured: 1200 idle cycles per tile) disappears.  P has its own columns, so PV(j) never blocks QK(j+2).
+// The exp2 (MUFU) pipe is the real bound of this head_dim: 64 exp vs 384 tensor cycles per row per key tile.
+// TMEM columns: S0a S0b S1a S1b [0,256) | O0 [256,352) O1 [352,448) | P0 [448,480) P1 [480,512).
+// Shared memory: Q 2x24 KB; K ring 4x12 KB; V ring 4x12 KB.  Every tile is 3 SWIZZLE_64B atoms [rows][64 B]
+// (head_dim 96 = 3 x 32), the layout both the TMA boxes and the UMMA descriptors use (tools/umma_probe.cu).
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -30,19 +30,18 @@
 namespace aki {
 
 namespace fwd {
-constexpr int BM = 128, BN = 128, HD = 96;
-constexpr int ATOM_BYTES = 128 * 64;
-constexpr int TILE_BYTES = 3 * ATOM_BYTES;  // 24576
-constexpr int STAGES = 3;
-constexpr int THREADS = 640;
+constexpr int BM = 128, BN = 64, HD = 96;
+constexpr int Q_ATOM = 128 * 64, Q_TILE = 3 * Q_ATOM;     // 24576
+constexpr int KV_ATOM = BN * 64, KV_TILE = 3 * KV_ATOM;   // 12288
+constexpr int STAGES = 4;
+constexpr int THREADS = 384;
 constexpr int SMEM_Q = 0;
-constexpr int SMEM_K = SMEM_Q + 2 * TILE_BYTES;
-constexpr int SMEM_V = SMEM_K + STAGES * TILE_BYTES;
-constexpr int SMEM_X = SMEM_V + STAGES * TILE_BYTES;      // exchange: [tile 2][parity 2][half 2][128] floats
-constexpr int SMEM_TOTAL = SMEM_X + 2 * 2 * 2 * 128 * 4;  // 196608 + 4096
+constexpr int SMEM_K = SMEM_Q + 2 * Q_TILE;
+constexpr int SMEM_V = SMEM_K + STAGES * KV_TILE;
+constexpr int SMEM_TOTAL = SMEM_V + STAGES * KV_TILE;     // 147456
 constexpr int SMEM_ALLOC = SMEM_TOTAL + 1024;             // slack for 1024-byte alignment
-constexpr uint32_t TM_S0 = 0, TM_S1 = 128, TM_O0 = 256, TM_O1 = 352;
-constexpr int REGS_CTRL = 40, REGS_SOFTMAX = 104;  // setmaxnreg draws from the CTA pool: 128*40 + 512*104 = 58368 <= 640*96 = 61440
+constexpr uint32_t TM_S = 0, TM_O = 256, TM_P = 448;      // S: tile t buffer u at 128 t + 64 u; O: 96 t; P: 32 t
+constexpr int REGS_CTRL = 64, REGS_SOFTMAX = 216;         // CTA pool: 128*64 + 256*216 = 63488 <= 384*168
 constexpr float RESCALE_THRESHOLD = 8.0f;  // log2 units: P may grow to 2^8 before O is rescaled
 }  // namespace fwd
 
@@ -72,21 +71,21 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
   using namespace fwd;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  uint8_t* const smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-  __shared__ __align__(8) uint64_t bars[2 + 2 + 4 * STAGES + 6];
+  // barrier indices
+  constexpr int Q_FULL = 0, Q_READY = 2, K_FULL = 4, K_EMPTY = K_FULL + STAGES, V_FULL = K_EMPTY + STAGES,
+                V_EMPTY = V_FULL + STAGES, S_FULL = V_EMPTY + STAGES /* [t][buf] */, P_FULL = S_FULL + 4,
+                O_FULL = P_FULL + 2, N_BARS = O_FULL + 2;
+  __shared__ __align__(8) uint64_t bars[N_BARS];
   __shared__ uint32_t tmem_base_s;
   const uint32_t bar0 = smem_u32(bars);
   auto BAR = [&](int i) { return bar0 + 8u * i; };
-  // barrier indices
-  constexpr int Q_FULL = 0, Q_READY = 2, K_FULL = 4, K_EMPTY = K_FULL + STAGES, V_FULL = K_EMPTY + STAGES,
-                V_EMPTY = V_FULL + STAGES, S_FULL = V_EMPTY + STAGES, P_FULL = S_FULL + 2, O_FULL = P_FULL + 2;
 
   const int tid = threadIdx.x, warp = tid >> 5;
   // work decomposition: consecutive CTAs share (b,h) so K/V stay in L2; heaviest query tiles first
   const int bh = blockIdx.x / P.n_qp;
   const int qp = P.n_qp - 1 - (blockIdx.x % P.n_qp);
   const int b = bh / P.H, h = bh % P.H;
-  const int n_kt = (P.T + BN - 1) / BN;
+  const int n_kt = (P.T + BN - 1) / BN;            // 64-key tiles
   int n_kv0, n_kv1;
   {
     int n[2];
@@ -94,20 +93,21 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
     for (int t = 0; t < 2; ++t) {
       const int qt = 2 * qp + t;
       if (qt >= P.n_qt) n[t] = 0;
-      else if (P.mm.q_tile_kv_end) n[t] = min(P.mm.q_tile_kv_end[(size_t)b * P.n_qt + qt], n_kt);
-      else n[t] = min(qt + 1, n_kt);
+      else if (P.mm.q_tile_kv_end) n[t] = min(2 * P.mm.q_tile_kv_end[(size_t)b * P.n_qt + qt], n_kt);  // 128 -> 64 units
+      else n[t] = min(2 * (qt + 1), n_kt);
     }
     n_kv0 = n[0]; n_kv1 = n[1];
   }
   const int n_max = max(n_kv0, n_kv1);
 
   if (tid == 0) {
-    for (int i = 0; i < 2; ++i) { mbar_init(BAR(Q_FULL + i), 1); mbar_init(BAR(Q_READY + i), 256); }
+    for (int i = 0; i < 2; ++i) { mbar_init(BAR(Q_FULL + i), 1); mbar_init(BAR(Q_READY + i), 128); }
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(BAR(K_FULL + i), 1); mbar_init(BAR(K_EMPTY + i), 1);
       mbar_init(BAR(V_FULL + i), 1); mbar_init(BAR(V_EMPTY + i), 1);
     }
-    for (int i = 0; i < 2; ++i) { mbar_init(BAR(S_FULL + i), 1); mbar_init(BAR(P_FULL + i), 256); mbar_init(BAR(O_FULL + i), 1); }
+    for (int i = 0; i < 4; ++i) mbar_init(BAR(S_FULL + i), 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(BAR(P_FULL + i), 128); mbar_init(BAR(O_FULL + i), 1); }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<512>(smem_u32(&tmem_base_s));
@@ -123,86 +123,99 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
     if (elect_one()) {
       for (int t = 0; t < 2; ++t) {
         if ((t ? n_kv1 : n_kv0) == 0) continue;
-        mbar_arrive_expect_tx(BAR(Q_FULL + t), TILE_BYTES);
+        mbar_arrive_expect_tx(BAR(Q_FULL + t), Q_TILE);
         for (int a = 0; a < 3; ++a)
-          tma_load_4d(smem_base + SMEM_Q + t * TILE_BYTES + a * ATOM_BYTES, &map_q, BAR(Q_FULL + t), a * 32,
-                      (2 * qp + t) * BM, h, b);
+          tma_load_4d(smem_base + SMEM_Q + t * Q_TILE + a * Q_ATOM, &map_q, BAR(Q_FULL + t), a * 32, (2 * qp + t) * BM, h, b);
       }
-      for (int j = 0; j < n_max; ++j) {
+      auto load_k = [&](int j) {
         const int s = j % STAGES;
-        const uint32_t ph = (j / STAGES) & 1;
-        mbar_wait(BAR(K_EMPTY + s), ph ^ 1);
-        mbar_arrive_expect_tx(BAR(K_FULL + s), TILE_BYTES);
+        mbar_wait(BAR(K_EMPTY + s), ((j / STAGES) & 1) ^ 1);
+        mbar_arrive_expect_tx(BAR(K_FULL + s), KV_TILE);
         for (int a = 0; a < 3; ++a)
-          tma_load_4d(smem_base + SMEM_K + s * TILE_BYTES + a * ATOM_BYTES, &map_k, BAR(K_FULL + s), a * 32, j * BN, h, b);
-        mbar_wait(BAR(V_EMPTY + s), ph ^ 1);
-        mbar_arrive_expect_tx(BAR(V_FULL + s), TILE_BYTES);
+          tma_load_4d(smem_base + SMEM_K + s * KV_TILE + a * KV_ATOM, &map_k, BAR(K_FULL + s), a * 32, j * BN, h, b);
+      };
+      auto load_v = [&](int j) {
+        const int s = j % STAGES;
+        mbar_wait(BAR(V_EMPTY + s), ((j / STAGES) & 1) ^ 1);
+        mbar_arrive_expect_tx(BAR(V_FULL + s), KV_TILE);
         for (int a = 0; a < 3; ++a)
-          tma_load_4d(smem_base + SMEM_V + s * TILE_BYTES + a * ATOM_BYTES, &map_v, BAR(V_FULL + s), a * 32, j * BN, h, b);
+          tma_load_4d(smem_base + SMEM_V + s * KV_TILE + a * KV_ATOM, &map_v, BAR(V_FULL + s), a * 32, j * BN, h, b);
+      };
+      // consumption order of the MMA warp: K0 K1 | V0 K2 | V1 K3 | ...
+      if (n_max > 0) load_k(0);
+      if (n_max > 1) load_k(1);
+      for (int j = 0; j < n_max; ++j) {
+        load_v(j);
+        if (j + 2 < n_max) load_k(j + 2);
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
+    // The whole warp runs the loop so that addresses / descriptors stay in uniform registers; one elected lane
+    // issues the tcgen05 instructions.
     setmaxnreg_dec<REGS_CTRL>();
-    if (elect_one()) {
-      const bool tracing = P.trace && (int)blockIdx.x == P.trace_cta;
-      constexpr uint32_t IDESC_QK = umma_idesc_bf16(BM, BN, 0, 0);
-      constexpr uint32_t IDESC_PV = umma_idesc_bf16(BM, HD, 0, 1);
-      // descriptors differ only in the 14-bit start-address field (units of 16 B)
-      const uint64_t DESC_KMAJ = umma_smem_desc(0, 16, 512, UMMA_SW64);
-      const uint64_t DESC_MNMAJ = umma_smem_desc(0, ATOM_BYTES, 512, UMMA_SW64);
-      const uint32_t q_lo = (smem_base + SMEM_Q) >> 4, k_lo = (smem_base + SMEM_K) >> 4, v_lo = (smem_base + SMEM_V) >> 4;
-      auto issue_qk = [&](int t, int j) {
-        const uint32_t qa = q_lo + t * (TILE_BYTES >> 4), ka = k_lo + (j % STAGES) * (TILE_BYTES >> 4);
-        const uint32_t d = tmem + (t ? TM_S1 : TM_S0);
+    const bool leader = elect_one();
+    const bool tracing = P.trace && (int)blockIdx.x == P.trace_cta && leader;
+    constexpr uint32_t IDESC_QK = umma_idesc_bf16(BM, BN, 0, 0);
+    constexpr uint32_t IDESC_PV = umma_idesc_bf16(BM, HD, 0, 1);
+    // descriptors differ only in the 14-bit start-address field (units of 16 B)
+    const uint64_t DESC_KMAJ = umma_smem_desc(0, 16, 512, UMMA_SW64);
+    const uint64_t DESC_V = umma_smem_desc(0, KV_ATOM, 512, UMMA_SW64);     // MN-major: LBO = atom stride
+    const uint32_t q_lo = (smem_base + SMEM_Q) >> 4, k_lo = (smem_base + SMEM_K) >> 4, v_lo = (smem_base + SMEM_V) >> 4;
+    auto issue_qk = [&](int t, int j) {      // S_t[j&1] = Q_t K_j^T
+      const uint32_t qa = q_lo + t * (Q_TILE >> 4), ka = k_lo + (j % STAGES) * (KV_TILE >> 4);
+      const uint32_t d = tmem + TM_S + 128 * t + 64 * (j & 1);
+      if (leader) {
 #pragma unroll
-        for (int k = 0; k < 6; ++k) {
-          const uint32_t off = ((k >> 1) * ATOM_BYTES + (k & 1) * 32) >> 4;
-          umma_ss(d, DESC_KMAJ | (uint64_t)(qa + off), DESC_KMAJ | (uint64_t)(ka + off), IDESC_QK, k > 0);
-        }
-      };
-      auto issue_pv = [&](int t, int j) {
-        const uint32_t va = v_lo + (j % STAGES) * (TILE_BYTES >> 4);
-        const uint32_t d = tmem + (t ? TM_O1 : TM_O0), a = tmem + (t ? TM_S1 : TM_S0);
-#pragma unroll
-        for (int k = 0; k < 8; ++k)
-          umma_ts(d, a + 8 * k, DESC_MNMAJ | (uint64_t)(va + k * 64), IDESC_PV, (j > 0 || k > 0));
-      };
-      if (n_kv0 > 0) mbar_wait(BAR((ROPE ? Q_READY : Q_FULL) + 0), 0);
-      if (n_kv1 > 0) mbar_wait(BAR((ROPE ? Q_READY : Q_FULL) + 1), 0);
-      if (n_max > 0) {
-        mbar_wait(BAR(K_FULL + 0), 0);
-        tc_fence_after();
-        if (n_kv0 > 0) { issue_qk(0, 0); umma_commit(BAR(S_FULL + 0)); }
-        if (n_kv1 > 0) { issue_qk(1, 0); umma_commit(BAR(S_FULL + 1)); }
-        umma_commit(BAR(K_EMPTY + 0));
+        for (int k = 0; k < 6; ++k)
+          umma_ss(d, DESC_KMAJ | (uint64_t)(qa + (((k >> 1) * Q_ATOM + (k & 1) * 32) >> 4)),
+                  DESC_KMAJ | (uint64_t)(ka + (((k >> 1) * KV_ATOM + (k & 1) * 32) >> 4)), IDESC_QK, k > 0);
+        umma_commit(BAR(S_FULL + 2 * t + (j & 1)));
       }
-      for (int j = 0; j < n_max; ++j) {
-        const int sv = j % STAGES, jn = j + 1, sk = jn % STAGES;
-        // operand-ready waits first: they are long complete in steady state and must not sit between the
-        // softmax's P_FULL arrival and the MMA issue (the critical chain of each tile)
-        mbar_wait(BAR(V_FULL + sv), (j / STAGES) & 1);
-        if (jn < n_max) mbar_wait(BAR(K_FULL + sk), (jn / STAGES) & 1);
+    };
+    auto issue_pv = [&](int t, int j) {      // O_t += P_t V_j
+      const uint32_t va = v_lo + (j % STAGES) * (KV_TILE >> 4);
+      const uint32_t d = tmem + TM_O + 96 * t, a = tmem + TM_P + 32 * t;
+      if (leader) {
 #pragma unroll
-        for (int t = 0; t < 2; ++t) {
-          const int nk = t ? n_kv1 : n_kv0, nk_other = t ? n_kv0 : n_kv1;
-          if (j >= nk) continue;
-          TR(2 + t, j, 0);
-          mbar_wait(BAR(P_FULL + t), j & 1);
-          tc_fence_after();
-          TR(2 + t, j, 1);
-          issue_pv(t, j);
-          umma_commit(BAR(O_FULL + t));
-          // V_j is released by its last user: tile 1 if it uses j, else tile 0
-          if (t == 1 || j >= nk_other) umma_commit(BAR(V_EMPTY + sv));
-          TR(2 + t, j, 2);
-          if (jn < nk) {
-            issue_qk(t, jn);
-            umma_commit(BAR(S_FULL + t));
-            if (t == 1 || jn >= nk_other) umma_commit(BAR(K_EMPTY + sk));
-          }
-          TR(2 + t, j, 3);
+        for (int k = 0; k < 4; ++k)
+          umma_ts(d, a + 8 * k, DESC_V | (uint64_t)(va + k * 64), IDESC_PV, (j > 0 || k > 0));
+        umma_commit(BAR(O_FULL + t));
+      }
+    };
+    if (n_kv0 > 0) mbar_wait(BAR((ROPE ? Q_READY : Q_FULL) + 0), 0);
+    if (n_kv1 > 0) mbar_wait(BAR((ROPE ? Q_READY : Q_FULL) + 1), 0);
+    for (int jj = 0; jj < 2 && jj < n_max; ++jj) {
+      mbar_wait(BAR(K_FULL + jj), 0);
+      tc_fence_after();
+      if (jj < n_kv0) issue_qk(0, jj);
+      if (jj < n_kv1) issue_qk(1, jj);
+      if (leader) umma_commit(BAR(K_EMPTY + jj));
+      __syncwarp();
+    }
+    for (int j = 0; j < n_max; ++j) {
+      const int sv = j % STAGES, jn = j + 2, sk = jn % STAGES;
+      // operand-ready waits first: long complete in steady state, keep them off the P_FULL -> issue path
+      mbar_wait(BAR(V_FULL + sv), (j / STAGES) & 1);
+      if (jn < n_max) mbar_wait(BAR(K_FULL + sk), (jn / STAGES) & 1);
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        const int nk = t ? n_kv1 : n_kv0, nk_other = t ? n_kv0 : n_kv1;
+        if (j >= nk) continue;
+        TR(2 + t, j, 0);
+        mbar_wait(BAR(P_FULL + t), j & 1);
+        tc_fence_after();
+        TR(2 + t, j, 1);
+        issue_pv(t, j);
+        // V_j is released by its last user: tile 1 if it uses j, else tile 0
+        if (leader && (t == 1 || j >= nk_other)) umma_commit(BAR(V_EMPTY + sv));
+        TR(2 + t, j, 2);
+        if (jn < nk) {                 // the softmax has read S_t(j): its buffer can take key tile j+2
+          issue_qk(t, jn);
+          if (leader && (t == 1 || jn >= nk_other)) umma_commit(BAR(K_EMPTY + sk));
         }
+        __syncwarp();
+        TR(2 + t, j, 3);
       }
     }
   } else if (warp < 4) {
@@ -210,32 +223,28 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
   } else {
     // ------------------------------------------------------------------ softmax / correction / epilogue
     setmaxnreg_inc<REGS_SOFTMAX>();
-    const int st_ = tid - 128;                    // 0..511
-    const int t = st_ >> 8;                       // query tile of the pair
-    const int hf = (st_ >> 7) & 1;                // half of the key columns (and of the output columns)
-    const int r = st_ & 127;                      // row within the tile == TMEM lane
+    const int t = (warp - 4) >> 2;
+    const int r = tid - 128 - t * 128;           // row within the tile == TMEM lane
     const int qt = 2 * qp + t;
     const int i = qt * BM + r;                    // query index in mask coordinates
     const int len = meta_len(P.mm, b, P.T);
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-    const uint32_t tm_s = tmem + (t ? TM_S1 : TM_S0) + lane_base;
-    const uint32_t tm_o = tmem + (t ? TM_O1 : TM_O0) + lane_base;
+    const uint32_t tm_s = tmem + TM_S + 128 * t + lane_base;
+    const uint32_t tm_o = tmem + TM_O + 96 * t + lane_base;
+    const uint32_t tm_p = tmem + TM_P + 32 * t + lane_base;
     const int nk = t ? n_kv1 : n_kv0;
-    const int bar_id = 1 + t;                     // named barrier of the 256 threads of this tile
-    float* const xch = reinterpret_cast<float*>(smem_gen + SMEM_X) + t * 512;   // [parity][half][128]
-    const bool tracing = P.trace && (int)blockIdx.x == P.trace_cta && r == 0 && hf == 0;
+    const bool tracing = P.trace && (int)blockIdx.x == P.trace_cta && r == 0;
 
     if (ROPE && nk > 0) {
       mbar_wait(BAR(Q_FULL + t), 0);
       if (i < P.T) {
-        const uint32_t qa = smem_base + SMEM_Q + t * TILE_BYTES;
+        const uint32_t qa = smem_base + SMEM_Q + t * Q_TILE;
         const float* cr = P.rope_cos + (size_t)b * P.rope_stride_b + (size_t)i * 48;
         const float* sr = P.rope_sin + (size_t)b * P.rope_stride_b + (size_t)i * 48;
 #pragma unroll
-        for (int cc = 0; cc < 3; ++cc) {
-          const int c = 3 * hf + cc;              // 16-byte chunk c pairs with chunk c+6 (d <-> d+48)
-          const uint32_t a_lo = qa + (c >> 2) * ATOM_BYTES + sw64_offset(r, c & 3);
-          const uint32_t a_hi = qa + ((c + 6) >> 2) * ATOM_BYTES + sw64_offset(r, (c + 6) & 3);
+        for (int c = 0; c < 6; ++c) {             // 16-byte chunk c pairs with chunk c+6 (d <-> d+48)
+          const uint32_t a_lo = qa + (c >> 2) * Q_ATOM + sw64_offset(r, c & 3);
+          const uint32_t a_hi = qa + ((c + 6) >> 2) * Q_ATOM + sw64_offset(r, (c + 6) & 3);
           uint4 lo, hi;
           asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w) : "r"(a_lo));
           asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w) : "r"(a_hi));
@@ -268,21 +277,29 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
       row_hi = P.mm.row_hi[(size_t)b * P.mm.meta_pitch + i];
     }
     float m_used = -INFINITY;  // running max (raw score units) the accumulators are expressed against
-    float l = 0.f;             // partial row sum over this thread's key columns
+    float l = 0.f;
+    int o_waited = 0;          // number of O_FULL phases this thread has already observed
 
-    for (int j = 0; j < nk; ++j) {
-      TR(t, j, 0);
-      mbar_wait(BAR(S_FULL + t), j & 1);
+    // Both tiles share the 4 MUFU lanes of each SM sub-partition.  Start tile 1 half an iteration late so that
+    // one warp's exp2 phase overlaps the other's TMEM traffic / max / bookkeeping instead of colliding with it.
+    if (n_kv0 > 0 && n_kv1 > 0) {
+      if (t == 1) named_bar_sync(3, 256);
+    }
+
+    auto load_s = [&](float (&dst)[64], int j) {     // S_t(j): wait for the MMA, start the TMEM load (no wait)
+      mbar_wait(BAR(S_FULL + 2 * t + (j & 1)), (j >> 1) & 1);
       tc_fence_after();
-      TR(t, j, 1);
-      float s[64];
-      tmem_ld_x32(tm_s + 64 * hf, reinterpret_cast<uint32_t*>(s));
-      tmem_ld_x32(tm_s + 64 * hf + 32, reinterpret_cast<uint32_t*>(s) + 32);
+      tmem_ld_x32(tm_s + 64 * (j & 1), reinterpret_cast<uint32_t*>(dst));
+      tmem_ld_x32(tm_s + 64 * (j & 1) + 32, reinterpret_cast<uint32_t*>(dst) + 32);
+    };
 
+    // one key tile: s holds S_t(j) (already in registers); nxt receives S_t(j+1) while the exponentials run
+    auto body = [&](float (&s)[64], float (&nxt)[64], int j) {
+      TR(t, j, 0);
       // ---- tile classification (warp-uniform): fully visible tiles skip the predicate
-      const int j0 = j * BN + 64 * hf;              // first key column of this thread
+      const int j0 = j * BN;
       uint32_t vw[2], mw[2];
-      bool full = (j < qt) && (j * BN + BN <= len);
+      bool full = (j0 + BN <= qt * BM) && (j0 + BN <= len);
 #pragma unroll
       for (int w = 0; w < 2; ++w) {
         const int jw = j0 + 32 * w;
@@ -291,8 +308,6 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
         mw[w] = P.mm.mbits ? (__ldg(P.mm.mbits + (size_t)b * P.mm.bits_pitch + (jw >> 5)) & in_len) : in_len;
         full = full && (vw[w] == 0xffffffffu);
       }
-      tmem_wait_ld();
-      TR(t, j, 2);
       if (!full) {
         const int d = row_live ? (i - j0) : -1;             // causal: column c visible iff c <= d
         const int a = row_lo - j0, e = row_hi - j0;         // mutual: a <= c < e
@@ -311,37 +326,36 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
       for (int c = 4; c < 64; c += 4) {
         mx0 = fmaxf(mx0, s[c]); mx1 = fmaxf(mx1, s[c + 1]); mx2 = fmaxf(mx2, s[c + 2]); mx3 = fmaxf(mx3, s[c + 3]);
       }
-      const float mx_half = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
-      // ---- exchange the half-row maxima with the partner warpgroup
-      float* xp = xch + (j & 1) * 256;
-      xp[hf * 128 + r] = mx_half;
-      named_bar_sync(bar_id, 256);
-      const float m_new = fmaxf(m_used, fmaxf(mx_half, xp[(hf ^ 1) * 128 + r]));
-      TR(t, j, 3);
-      // ---- lazy rescale of O (correction merged into the softmax warps; rare after the first tiles).
-      // Both halves take the same decision (same m_used / m_new); each rescales its 48 output columns.
+      const float m_new = fmaxf(m_used, fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)));
+      TR(t, j, 1);
+      // ---- lazy rescale of O (correction merged into the softmax warps; rare after the first tiles)
       if (j == 0) {
         m_used = m_new;
+        if (t == 0 && n_kv1 > 0) asm volatile("bar.arrive 3, 256;" ::: "memory");   // release tile 1 (stagger)
       } else {
         const bool need = (m_new - m_used) * P.scale_log2 > RESCALE_THRESHOLD || (m_used == -INFINITY && m_new > -INFINITY);
         if (__any_sync(0xffffffffu, need)) {
           const float alpha = (m_used == -INFINITY) ? 0.f : ex2_approx((m_used - m_new) * P.scale_log2);
           m_used = m_new;
           l *= alpha;
-          mbar_wait(BAR(O_FULL + t), (j - 1) & 1);
+          if (o_waited < j) { mbar_wait(BAR(O_FULL + t), (j - 1) & 1); o_waited = j; }   // PV(j-1) has landed
           tc_fence_after();
-          uint32_t o[48];
-          tmem_ld_x32(tm_o + 48 * hf, o);
-          tmem_ld_x16(tm_o + 48 * hf + 32, o + 32);
-          tmem_wait_ld();
+          uint32_t o[32];
 #pragma unroll
-          for (int x = 0; x < 48; ++x) o[x] = __float_as_uint(__uint_as_float(o[x]) * alpha);
-          tmem_st_x32(tm_o + 48 * hf, o);
-          tmem_st_x16(tm_o + 48 * hf + 32, o + 32);
+          for (int c = 0; c < 3; ++c) {
+            tmem_ld_x32(tm_o + 32 * c, o);
+            tmem_wait_ld();
+#pragma unroll
+            for (int x = 0; x < 32; ++x) o[x] = __float_as_uint(__uint_as_float(o[x]) * alpha);
+            tmem_st_x32(tm_o + 32 * c, o);
+          }
           tmem_wait_st();
         }
       }
-      // ---- P = exp2((S - m) * scale*log2e), row sum, bf16 pack, store to TMEM (aliases S)
+      // ---- prefetch S_t(j+1) from the other TMEM buffer; its latency hides behind the exponentials
+      if (j + 1 < nk) load_s(nxt, j + 1);
+      TR(t, j, 2);
+      // ---- P = exp2((S - m) * scale*log2e), row sum, bf16 pack
       const float neg_m = (m_used == -INFINITY) ? 0.f : -m_used * P.scale_log2;
       float sum0 = 0.f, sum1 = 0.f;
       uint32_t pk[32];
@@ -352,50 +366,61 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
         sum0 += p0; sum1 += p1;
         pk[x] = pack_bf16x2(p0, p1);
       }
-      // every thread of the tile has read its S (barrier above) -> the aliased columns may be overwritten
-      tmem_st_x32(tm_s + 32 * hf, pk);
       l += sum0 + sum1;
-      TR(t, j, 4);
-      tmem_wait_st();
+      TR(t, j, 3);
+      // ---- P_t has its own TMEM columns, single-buffered: PV(j-1) must have consumed P(j-1)
+      if (j > 0 && o_waited < j) { mbar_wait(BAR(O_FULL + t), (j - 1) & 1); o_waited = j; }
+      tmem_st_x32(tm_p, pk);
+      tmem_wait_st();            // (tcgen05.wait::st; the S prefetch is covered by wait::ld below)
       tc_fence_before();
       mbar_arrive(BAR(P_FULL + t));
+      TR(t, j, 4);
+      if (j + 1 < nk) tmem_wait_ld();
       TR(t, j, 5);
+    };
+
+    if (nk > 0) {
+      float sA[64], sB[64];
+      load_s(sA, 0);
+      tmem_wait_ld();
+      for (int j = 0; j < nk; j += 2) {
+        body(sA, sB, j);
+        if (j + 1 < nk) body(sB, sA, j + 1);
+      }
     }
 
-    // ---- epilogue: O / l -> bf16 -> global; LSE.  Each half stores 48 of the 96 output columns.
+    // ---- epilogue: O / l -> bf16 -> global; LSE
     if (qt < P.n_qt) {
-      float inv_l = 0.f, l_tot = 0.f;
+      float inv_l = 0.f;
       if (nk > 0) {
-        float* xp = xch + (nk & 1) * 256;          // parity not used by the last main-loop iteration
-        xp[hf * 128 + r] = l;
-        named_bar_sync(bar_id, 256);
-        l_tot = l + xp[(hf ^ 1) * 128 + r];
         mbar_wait(BAR(O_FULL + t), (nk - 1) & 1);
         tc_fence_after();
-        inv_l = (row_live && l_tot > 0.f) ? 1.f / l_tot : 0.f;  // batch-padding rows: zeros
+        inv_l = (row_live && l > 0.f) ? 1.f / l : 0.f;  // batch-padding rows: zeros
       }
       // tcgen05.ld is warp-collective (.sync.aligned): load unconditionally, predicate only the global stores
       const bool store_row = (i < P.T);
-      __nv_bfloat16* orow = P.o.row(b, store_row ? i : 0, h) + 48 * hf;
-      uint32_t o[48];
-      if (nk > 0) {
-        tmem_ld_x32(tm_o + 48 * hf, o);
-        tmem_ld_x16(tm_o + 48 * hf + 32, o + 32);
-        tmem_wait_ld();
-      }
+      __nv_bfloat16* orow = P.o.row(b, store_row ? i : 0, h);
 #pragma unroll
-      for (int x = 0; x < 6; ++x) {
-        uint4 u;
-        uint32_t* w = reinterpret_cast<uint32_t*>(&u);
+      for (int c = 0; c < 3; ++c) {
+        uint32_t o[32];
+        if (nk > 0) {
+          tmem_ld_x32(tm_o + 32 * c, o);
+          tmem_wait_ld();
+        }
 #pragma unroll
-        for (int e = 0; e < 4; ++e)
-          w[e] = (inv_l > 0.f) ? pack_bf16x2(__uint_as_float(o[8 * x + 2 * e]) * inv_l,
-                                               __uint_as_float(o[8 * x + 2 * e + 1]) * inv_l)
-                               : 0u;
-        if (store_row) *reinterpret_cast<uint4*>(orow + 8 * x) = u;
+        for (int x = 0; x < 4; ++x) {
+          uint4 u;
+          uint32_t* w = reinterpret_cast<uint32_t*>(&u);
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            w[e] = (inv_l > 0.f) ? pack_bf16x2(__uint_as_float(o[8 * x + 2 * e]) * inv_l,
+                                                 __uint_as_float(o[8 * x + 2 * e + 1]) * inv_l)
+                                 : 0u;
+          if (store_row) *reinterpret_cast<uint4*>(orow + 32 * c + 8 * x) = u;
+        }
       }
-      if (P.lse && store_row && hf == 0)
-        P.lse[((size_t)b * P.H + h) * P.T + i] = (inv_l > 0.f) ? (m_used * P.scale + __logf(l_tot)) : INFINITY;
+      if (P.lse && store_row)
+        P.lse[((size_t)b * P.H + h) * P.T + i] = (inv_l > 0.f) ? (m_used * P.scale + __logf(l)) : INFINITY;
     }
   }
   tc_fence_before();

@@ -1,0 +1,217 @@
+"""-m gpu: the tcgen05 forward / backward and the decode kernel through the C ABI against the fp32 oracle, with
+the tolerance rule of SURVEY 8(d): error <= 2 x (reference-style bf16 eager error) + 1e-3 * RMS floor; plus
+size-independent properties at the BASELINE sizes where the CPU oracle is too slow."""
+import numpy as np
+import pytest
+import torch
+
+import helpers as Hp
+from oracle import mma_oracle as O
+
+pytestmark = pytest.mark.gpu
+dev = "cuda"
+H, D = 32, 96
+SCALE = D ** -0.5
+
+
+def _ops():
+    from aki_b200 import ops
+    return ops
+
+
+def _rope(T, B=1):
+    inv = O.longrope_inv_freq(96, 10000.0, 1.0 + np.arange(48, dtype=np.float32) / 48)
+    cos, sin = O.rope_cos_sin(torch.arange(T)[None], inv, 1.1902)
+    return cos[..., :48].contiguous(), sin[..., :48].contiguous()
+
+
+def _gpu_inputs(q, k, v, cos, sin):
+    ops = _ops()
+    B, T = q.shape[:2]
+    qd, kd, vd = q.to(dev), k.to(dev), v.to(dev)
+    cd = sd = None
+    k_in = kd
+    if cos is not None:
+        cd, sd = cos.to(dev), sin.to(dev)
+        kr = torch.empty(B, H, T, D, dtype=torch.bfloat16, device=dev)
+        packed = torch.cat([qd.reshape(B, T, -1), kd.reshape(B, T, -1), vd.reshape(B, T, -1)], -1).contiguous()
+        ops.rope_kv_write(packed, cd, sd, kr, None, 0, H)
+        k_in = kr.transpose(1, 2)
+    return qd, k_in, vd, cd, sd
+
+
+CASES = [  # name, B, L, N, n_img, rope, pad_right
+    ("cfg1", 1, 257, 128, 1, True, 0),            # BASELINE config 1 geometry: 128 image + 256 text tokens
+    ("cfg1-norope", 1, 257, 128, 1, False, 0),
+    ("sft-pad", 2, 300, 144, 1, True, 37),         # SFT collate: right padding, N=144
+    ("two-images", 1, 600, 128, 2, True, 0),
+    ("ragged-causal", 1, 200, 4, 0, False, 0),
+    ("tiny", 1, 9, 3, 1, True, 0),
+]
+
+
+@pytest.mark.parametrize("name,B,L,N,n_img,rope,pad", CASES)
+def test_forward_matches_oracle(name, B, L, N, n_img, rope, pad):
+    ops = _ops()
+    lang, am = Hp.make_prompt(B, L, N, n_img, pad_right=pad, first_img=min(8, L // 3))
+    S = O.segments_ref(lang, am, N, Hp.MEDIA_ID)
+    segs = ops.build_segments(torch.from_numpy(lang).to(dev), torch.from_numpy(am).to(dev), N, Hp.MEDIA_ID)
+    T = segs.T
+    q, k, v = Hp.qkv_inputs(B, T, H, D, seed=11)
+    cos, sin = _rope(T) if rope else (None, None)
+    ref32 = Hp.oracle_attention(q, k, v, S, SCALE, cos, sin, torch.float32)
+    ref16 = Hp.oracle_attention(q, k, v, S, SCALE, cos, sin, torch.bfloat16)
+    rows = Hp.live_rows(S, B, T)
+    qd, k_in, vd, cd, sd = _gpu_inputs(q, k, v, cos, sin)
+    o, lse = ops.attn_fwd_raw(qd, k_in, vd, cd, sd, ops.meta_tuple(segs), SCALE)
+    ok, ek, eb, rms = Hp.within_tolerance(o, ref16, ref32, rows)
+    assert ok, f"{name}: kernel err {ek:.3e} vs bf16-eager err {eb:.3e} (rms {rms:.3f})"
+    assert not torch.isnan(o.float()).any()
+    # fully masked rows (batch padding): zeros by design (the reference gives a uniform average)
+    if (~rows).any():
+        assert float(o.float().cpu()[~rows].abs().max()) == 0.0
+    # LSE of live rows against the oracle's log-sum-exp
+    s = torch.einsum("bthd,bshd->bhts", ref_q(q, cos, sin), ref_q(k, cos, sin)) * SCALE
+    m4 = torch.from_numpy(O.expand_segments_to_4d(S, t_out=T)).bool()
+    lse_ref = torch.logsumexp(s.masked_fill(~m4, float("-inf")), dim=-1)
+    live = rows[:, None, :].expand(-1, H, -1)
+    assert float((lse.cpu() - lse_ref)[live].abs().max()) < 2e-2
+
+
+def ref_q(x, cos, sin):
+    xf = x.float()
+    if cos is None:
+        return xf
+    c = torch.cat([cos, cos], -1); s = torch.cat([sin, sin], -1)
+    return O.apply_rope(xf.transpose(1, 2), c, s).transpose(1, 2)
+
+
+@pytest.mark.parametrize("name,B,L,N,n_img,rope,pad", CASES[:5])
+def test_backward_matches_autograd_oracle(name, B, L, N, n_img, rope, pad):
+    ops = _ops()
+    lang, am = Hp.make_prompt(B, L, N, n_img, pad_right=pad)
+    S = O.segments_ref(lang, am, N, Hp.MEDIA_ID)
+    segs = ops.build_segments(torch.from_numpy(lang).to(dev), torch.from_numpy(am).to(dev), N, Hp.MEDIA_ID)
+    T = segs.T
+    q, k, v = Hp.qkv_inputs(B, T, H, D, seed=12)
+    d_o = torch.randn(B, T, H, D, generator=torch.Generator().manual_seed(13)).to(torch.bfloat16)
+    cos, sin = _rope(T) if rope else (None, None)
+    rows = Hp.live_rows(S, B, T)
+    m4 = torch.from_numpy(O.expand_segments_to_4d(S, t_out=T))
+
+    def oracle(dtype):
+        qf = q.to(dtype).requires_grad_(True); kf = k.to(dtype).requires_grad_(True); vf = v.to(dtype).requires_grad_(True)
+        qh, kh, vh = qf.transpose(1, 2), kf.transpose(1, 2), vf.transpose(1, 2)
+        if rope:
+            c = torch.cat([cos, cos], -1).to(dtype).expand(B, -1, -1); s_ = torch.cat([sin, sin], -1).to(dtype).expand(B, -1, -1)
+            qh = O.apply_rope(qh, c, s_); kh = O.apply_rope(kh, c, s_)
+        out = O.eager_attention(qh, kh, vh, O.invert_4d_mask(m4, dtype).to(dtype), SCALE)
+        out.backward((d_o.float() * rows[:, :, None, None]).to(dtype))     # no gradient through don't-care rows
+        return qf.grad, kf.grad, vf.grad
+
+    g32 = oracle(torch.float32)
+    g16 = oracle(torch.bfloat16)
+    qd, k_in, vd, cd, sd = _gpu_inputs(q, k, v, cos, sin)
+    meta = ops.meta_tuple(segs)
+    o, lse = ops.attn_fwd_raw(qd, k_in, vd, cd, sd, meta, SCALE)
+    dq = torch.full((B, T, H, D), float("nan"), dtype=torch.bfloat16, device=dev); dk = dq.clone(); dv = dq.clone()
+    ops.attn_bwd_raw(d_o.to(dev), qd, k_in, vd, o, lse, cd, sd, meta, SCALE, dq, dk, dv)
+    for nm, got, r32, r16 in zip(("dq", "dk", "dv"), (dq, dk, dv), g32, g16):
+        assert not torch.isnan(got.float()).any(), (name, nm)
+        ok, ek, eb, rms = Hp.within_tolerance(got, r16, r32, None, floor=2e-3)
+        assert ok, f"{name} {nm}: kernel err {ek:.3e} vs bf16-eager err {eb:.3e} (rms {rms:.3f})"
+
+
+def test_custom_op_autograd_packed_matches_raw():
+    """aki_mma::attn_packed (what the module calls): gradient of the packed projection = [dq | dk | dv]."""
+    ops = _ops()
+    B, T = 1, 300
+    lang, am = Hp.make_prompt(B, 200, 101, 1)
+    segs = ops.build_segments(torch.from_numpy(lang).to(dev), torch.from_numpy(am).to(dev), 101, Hp.MEDIA_ID)
+    assert segs.T == T
+    torch.manual_seed(3)
+    qkv = torch.randn(B, T, 3 * H * D, device=dev).to(torch.bfloat16).requires_grad_(True)
+    cos, sin = (x.to(dev) for x in _rope(T))
+    o, lse, k_rot = ops.attn_packed_op(qkv, cos, sin, H, SCALE, *ops.meta_tuple(segs))
+    d_o = torch.randn_like(o)
+    o.backward(d_o)
+    q4 = qkv.detach()[..., :H * D].unflatten(-1, (H, D)); v4 = qkv.detach()[..., 2 * H * D:].unflatten(-1, (H, D))
+    o2, lse2 = ops.attn_fwd_raw(q4, k_rot.transpose(1, 2), v4, cos, sin, ops.meta_tuple(segs), SCALE)
+    assert torch.equal(o2.view(B, T, -1), o.detach())
+    dq = torch.empty(B, T, H, D, dtype=torch.bfloat16, device=dev); dk = torch.empty_like(dq); dv = torch.empty_like(dq)
+    ops.attn_bwd_raw(d_o.view(B, T, H, D), q4, k_rot.transpose(1, 2), v4, o2, lse2, cos, sin, ops.meta_tuple(segs),
+                     SCALE, dq, dk, dv)
+    # dQ is accumulated with fp32 atomics (TMA reductions): summation order may differ between runs
+    ref = torch.cat([dq.view(B, T, -1), dk.view(B, T, -1), dv.view(B, T, -1)], -1).float()
+    assert float((qkv.grad.float() - ref).abs().max()) <= 1e-2 * float(ref.abs().max())
+
+
+def test_full_size_properties_and_simt_cross_check():
+    """BASELINE config 3 size (T=8192, 4 image spans): properties that need no oracle, plus the SIMT verification
+    kernel on the same device."""
+    ops = _ops()
+    import bench
+    B, T = 1, 8192
+    lang, am = bench.make_prompt(B, T, 4)
+    segs = ops.build_segments(torch.from_numpy(lang).to(dev), torch.from_numpy(am).to(dev), 128, Hp.MEDIA_ID, t_cap=T,
+                              exact_shape=False)
+    meta = ops.meta_tuple(segs)
+    g = torch.Generator(device=dev).manual_seed(0)
+    q = torch.randn(B, T, H, D, device=dev, generator=g).to(torch.bfloat16)
+    k = torch.randn(B, T, H, D, device=dev, generator=g).to(torch.bfloat16)
+    v = torch.randn(B, T, H, D, device=dev, generator=g).to(torch.bfloat16)
+    o, lse = ops.attn_fwd_raw(q, k, v, None, None, meta, SCALE)
+    # (1) rows of P sum to one: V = 1 -> O = 1 exactly up to bf16 rounding of P
+    o1, _ = ops.attn_fwd_raw(q, k, torch.ones_like(v), None, None, meta, SCALE)
+    assert float((o1.float() - 1).abs().max()) < 2e-2
+    # (2) linearity in V
+    o2, _ = ops.attn_fwd_raw(q, k, (2 * v.float()).to(torch.bfloat16), None, None, meta, SCALE)
+    assert float((o2.float() - 2 * o.float()).abs().max()) < 3e-2
+    # (3) visibility: changing keys/values at positions >= q_end changes no image row and no row before them
+    q_end = int(segs.q_end[0])
+    k2, v2 = k.clone(), v.clone()
+    k2[:, q_end:] = torch.randn_like(k2[:, q_end:]); v2[:, q_end:] = torch.randn_like(v2[:, q_end:])
+    o3, _ = ops.attn_fwd_raw(q, k2, v2, None, None, meta, SCALE)
+    assert torch.equal(o3[:, :q_end], o[:, :q_end]) and not torch.equal(o3[:, q_end:], o[:, q_end:])
+    # ... while changing TEXT keys right after the first image span does change that span's rows (the MMA block)
+    first_img = int((segs.seg[0] == 1).nonzero()[0]); span_end = first_img + 128
+    k4 = k.clone(); k4[:, span_end:span_end + 64] = torch.randn_like(k4[:, span_end:span_end + 64])
+    o4, _ = ops.attn_fwd_raw(q, k4, v, None, None, meta, SCALE)
+    assert not torch.equal(o4[:, first_img:span_end], o[:, first_img:span_end])
+    assert torch.equal(o4[:, :first_img], o[:, :first_img])
+    # (4) tcgen05 kernel vs the SIMT verification kernel (fp32 arithmetic) on the device
+    os_, lse_s = ops.attn_fwd_raw(q, k, v, None, None, meta, SCALE, simt=True)
+    assert float((o.float() - os_.float()).abs().max()) < 3e-2
+    assert float((lse - lse_s).abs().max()) < 1e-2
+    # (5) backward cross-check on the same problem
+    d_o = torch.randn(B, T, H, D, device=dev, generator=g).to(torch.bfloat16)
+    grads = []
+    for simt in (False, True):
+        dq = torch.empty_like(q); dk = torch.empty_like(q); dv = torch.empty_like(q)
+        oo, ll = (os_, lse_s) if simt else (o, lse)
+        ops.attn_bwd_raw(d_o, q, k, v, oo, ll, None, None, meta, SCALE, dq, dk, dv, simt=simt)
+        grads.append((dq.float(), dk.float(), dv.float()))
+    for a, b_, nm in zip(grads[0], grads[1], ("dq", "dk", "dv")):
+        scale = float(b_.abs().max())
+        assert float((a - b_).abs().max()) < 2e-2 * max(scale, 1.0), nm
+
+
+def test_decode_matches_oracle_and_prefill_consistency():
+    ops = _ops()
+    # oracle: one query against the cache, per-sample lengths (batched decode is an extension of the reference's B=1)
+    B, tcap = 3, 700
+    lens = [700, 1, 513]
+    g = torch.Generator().manual_seed(3)
+    q = torch.randn(B, H, D, generator=g).to(torch.bfloat16)
+    kc = torch.randn(B, H, tcap, D, generator=g).to(torch.bfloat16)
+    vc = torch.randn(B, H, tcap, D, generator=g).to(torch.bfloat16)
+    ref = O.decode_attention(q.float()[:, :, None], kc.float(), vc.float(), lens, SCALE)[:, 0]
+    out = ops.decode_op(q.to(dev), kc.to(dev), vc.to(dev), torch.tensor(lens, dtype=torch.int32, device=dev), max(lens), SCALE)
+    assert float((out.float().cpu() - ref).abs().max()) < 4e-3
+    # decode of token T == last row of a causal prefill over T+1 tokens (same keys, the query sees everything)
+    T = 300
+    qq, kk, vv = Hp.qkv_inputs(1, T + 1, H, D, seed=4, device=dev)
+    o_full, _ = ops.attn_fwd_raw(qq, kk, vv, None, None, None, SCALE)
+    kcache = kk.transpose(1, 2).contiguous(); vcache = vv.transpose(1, 2).contiguous()
+    o_dec = ops.decode_op(qq[:, T].contiguous(), kcache, vcache, torch.tensor([T + 1], dtype=torch.int32, device=dev), T + 1, SCALE)
+    assert float((o_dec.float() - o_full[:, T].float()).abs().max()) < 1e-2

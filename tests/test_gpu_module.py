@@ -1,0 +1,212 @@
+"""-m gpu: the drop-in boundary -- AkiMMAAttention (Phi3Attention signature / state-dict keys), the KV-cache
+contract, the AttentionInterface plugin and a Phi-3 model with its attention swapped, against the fixture produced
+by the installed transformers' eager Phi3Attention and against the oracle."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+import helpers as Hp
+from oracle import mma_oracle as O
+
+pytestmark = pytest.mark.gpu
+dev = "cuda"
+
+
+def _config(short=None, long=None, layers=2, intermediate=1024, vocab=1000):
+    from transformers import Phi3Config
+    rp = {"rope_type": "longrope", "rope_theta": 10000.0, "short_factor": [float(x) for x in short], "long_factor": [float(x) for x in long],
+          "original_max_position_embeddings": 4096} if short is not None else None
+    kw = dict(hidden_size=3072, num_attention_heads=32, num_key_value_heads=32, intermediate_size=intermediate,
+              vocab_size=vocab, num_hidden_layers=layers, max_position_embeddings=131072,
+              original_max_position_embeddings=4096, rms_norm_eps=1e-5, attention_dropout=0.0, pad_token_id=0,
+              attn_implementation="eager")
+    if rp is not None:
+        kw["rope_parameters"] = rp
+    return Phi3Config(**kw)
+
+
+def _module_like_fixture(g):
+    """Same construction + init order as oracle/gen_golden.py (o_proj is registered before qkv_proj)."""
+    import aki_b200
+    cfg = _config(g["short_factor"], g["long_factor"])
+    torch.manual_seed(0)
+    mod = aki_b200.AkiMMAAttention(cfg, layer_idx=0).float().eval()
+    for p in mod.parameters():
+        torch.nn.init.normal_(p, std=0.02)
+    assert list(mod.state_dict().keys()) == ["o_proj.weight", "qkv_proj.weight"]
+    assert mod.qkv_proj.weight.shape == (9216, 3072) and mod.o_proj.weight.shape == (3072, 3072)
+    assert np.allclose(mod.qkv_proj.weight.detach()[::257, ::31].numpy(), g["w_qkv_sample"])
+    assert np.allclose(mod.o_proj.weight.detach()[::129, ::29].numpy(), g["w_o_sample"])
+    return cfg, mod
+
+
+def test_module_matches_installed_phi3_eager_fixture():
+    import aki_b200
+    from aki_b200 import ops
+    g = np.load(os.path.join(GOLDEN, "attn_cfg1_small.npz"))
+    cfg, mod = _module_like_fixture(g)
+    w_qkv, w_o = mod.qkv_proj.weight.detach().clone(), mod.o_proj.weight.detach().clone()
+    mod = mod.to(dev).to(torch.bfloat16)
+    T, N = int(g["T"]), int(g["N"])
+    lang = torch.from_numpy(g["lang"]).to(dev)
+    segs = ops.build_segments(lang, torch.ones_like(lang), N, Hp.MEDIA_ID)
+    m4 = np.unpackbits(g["mask_bits"], axis=-1)[..., :T].reshape(g["mask_shape"]).astype(np.int64)
+    assert np.array_equal(segs.expand_to_4d().cpu().numpy(), m4)
+    rope = aki_b200.LongRope(short_factor=g["short_factor"], long_factor=g["long_factor"], device=dev)
+    add = O.invert_4d_mask(torch.from_numpy(m4), torch.float32)
+    for tag in ("short", "long"):
+        pos0 = int(g[f"{tag}_pos0"])
+        pos = torch.arange(pos0, pos0 + T, device=dev)[None]
+        cos, sin = rope.tables(pos)
+        torch.manual_seed(1)
+        hidden = torch.randn(1, T, 3072)
+        with torch.no_grad():
+            out, w = mod(hidden.to(dev).to(torch.bfloat16), None, None, mma_segments=segs, mma_rope=(cos, sin))
+        assert w is None and out.shape == (1, T, 3072)
+        ref = torch.from_numpy(g[f"{tag}_out"])                                # fp32 HF eager, every 16th column
+        # reference-style bf16 eager error of the same module (CPU oracle in bf16)
+        c96 = torch.cat([cos, cos], -1).cpu(); s96 = torch.cat([sin, sin], -1).cpu()
+        o16, _ = O.attention_module_forward(hidden.bfloat16(), w_qkv.bfloat16(), w_o.bfloat16(), c96, s96, add.bfloat16())
+        ok, ek, eb, rms = Hp.within_tolerance(out[:, :, ::16], o16[:, :, ::16], ref, None, floor=2e-3)
+        assert ok, f"{tag}: module err {ek:.3e} vs bf16-eager err {eb:.3e} (rms {rms:.3f})"
+        # the HF-style call with position_embeddings=(cos, sin) of shape (B,T,96) gives the same result
+        with torch.no_grad():
+            out2, _ = mod(hidden.to(dev).to(torch.bfloat16), (c96.to(dev).bfloat16().float(), s96.to(dev).bfloat16().float()), None,
+                          mma_segments=segs)
+        assert float((out2.float() - out.float()).abs().max()) < 2e-2 * max(1.0, float(out.float().abs().max()))
+
+
+def test_module_rejects_4d_mask_without_segments_and_wrong_head_dim():
+    import aki_b200
+    g = np.load(os.path.join(GOLDEN, "attn_cfg1_small.npz"))
+    cfg = _config(g["short_factor"], g["long_factor"])
+    mod = aki_b200.AkiMMAAttention(cfg, 0).to(dev).to(torch.bfloat16)
+    x = torch.zeros(1, 8, 3072, device=dev, dtype=torch.bfloat16)
+    cs = torch.ones(1, 8, 48, device=dev)
+    with pytest.raises(ValueError):
+        mod(x, None, torch.ones(1, 1, 8, 8, device=dev), mma_rope=(cs, cs))
+    from transformers import Phi3Config
+    with pytest.raises(ValueError):
+        aki_b200.AkiMMAAttention(Phi3Config(hidden_size=4096, num_attention_heads=32, num_key_value_heads=32), 0)
+
+
+def test_kv_cache_prefill_then_decode_equals_full_recompute():
+    """Generate contract (aki_generation.py:36-86): prefill with the MMA mask writes post-RoPE K and V into the
+    cache; each decode step sees every cached key (2-D all-ones mask), position id = past length."""
+    import aki_b200
+    from aki_b200 import ops
+    g = np.load(os.path.join(GOLDEN, "attn_cfg1_small.npz"))
+    cfg, mod = _module_like_fixture(g)
+    mod = mod.to(dev).to(torch.bfloat16)
+    T, N = int(g["T"]), int(g["N"])
+    lang = torch.from_numpy(g["lang"]).to(dev)
+    segs = ops.build_segments(lang, torch.ones_like(lang), N, Hp.MEDIA_ID)
+    rope = aki_b200.LongRope(short_factor=g["short_factor"], long_factor=g["long_factor"], device=dev)
+    n_new = 3
+    torch.manual_seed(2)
+    hidden = torch.randn(1, T + n_new, 3072, device=dev).to(torch.bfloat16)
+    cos_all, sin_all = rope.tables(torch.arange(T + n_new, device=dev)[None])
+    cache = aki_b200.AkiKVCache(1, 1, 32, 96, t_cap=T + 8, device=dev)
+    with torch.no_grad():
+        out_p, _ = mod(hidden[:, :T], None, None, past_key_values=cache, mma_segments=segs,
+                       mma_rope=(cos_all[:, :T].contiguous(), sin_all[:, :T].contiguous()))
+        ref_p, _ = mod(hidden[:, :T], None, None, mma_segments=segs,
+                       mma_rope=(cos_all[:, :T].contiguous(), sin_all[:, :T].contiguous()))
+    assert torch.equal(out_p, ref_p)                              # cache write does not change the prefill result
+    assert cache[0][0].shape == (1, 32, T, 96) and cache.get_seq_length() == T
+    for step in range(n_new):
+        t = T + step
+        with torch.no_grad():
+            out_d, _ = mod(hidden[:, t:t + 1], None, None, past_key_values=cache,
+                           mma_rope=(cos_all[:, t:t + 1].contiguous(), sin_all[:, t:t + 1].contiguous()))
+        assert cache[0][0].shape[2] == t + 1
+        # oracle for the step: row t of full attention where rows >= T are plain causal over all keys
+        S = O.segments_ref(g["lang"], np.ones_like(g["lang"]), N, Hp.MEDIA_ID)
+        m = np.zeros((1, 1, t + 1, t + 1), dtype=np.int64)
+        m[:, :, :T, :T] = O.expand_segments_to_4d(S)
+        for rr in range(T, t + 1):
+            m[0, 0, rr, :rr + 1] = 1
+        c96 = torch.cat([cos_all, cos_all], -1)[:, :t + 1].cpu(); s96 = torch.cat([sin_all, sin_all], -1)[:, :t + 1].cpu()
+        ref, _ = O.attention_module_forward(hidden[:, :t + 1].float().cpu(), mod.qkv_proj.weight.float().cpu(),
+                                            mod.o_proj.weight.float().cpu(), c96, s96,
+                                            O.invert_4d_mask(torch.from_numpy(m), torch.float32))
+        err = float((out_d[0, 0].float().cpu() - ref[0, t]).abs().max())
+        assert err < 3e-2 * max(1.0, float(ref.abs().max())), (step, err)
+
+
+def test_dynamic_cache_and_plugin_paths():
+    """Foreign HF DynamicCache honoured through update(); AttentionInterface function on rotated q/k/v."""
+    import aki_b200
+    from aki_b200 import ops
+    from transformers import DynamicCache
+    g = np.load(os.path.join(GOLDEN, "attn_cfg1_small.npz"))
+    cfg, mod = _module_like_fixture(g)
+    mod = mod.to(dev).to(torch.bfloat16)
+    T, N = int(g["T"]), int(g["N"])
+    lang = torch.from_numpy(g["lang"]).to(dev)
+    segs = ops.build_segments(lang, torch.ones_like(lang), N, Hp.MEDIA_ID)
+    rope = aki_b200.LongRope(short_factor=g["short_factor"], long_factor=g["long_factor"], device=dev)
+    cos, sin = rope.tables(torch.arange(T + 1, device=dev)[None])
+    torch.manual_seed(4)
+    hidden = torch.randn(1, T + 1, 3072, device=dev).to(torch.bfloat16)
+    rp = lambda a, b_: (cos[:, a:b_].contiguous(), sin[:, a:b_].contiguous())
+    with torch.no_grad():
+        ref_p, _ = mod(hidden[:, :T], None, None, mma_segments=segs, mma_rope=rp(0, T))
+        try:
+            dc = DynamicCache(config=cfg)
+        except TypeError:
+            dc = DynamicCache()
+        out_p, _ = mod(hidden[:, :T], None, None, past_key_values=dc, mma_segments=segs, mma_rope=rp(0, T))
+        assert float((out_p.float() - ref_p.float()).abs().max()) < 2e-2 * max(1.0, float(ref_p.float().abs().max()))
+        assert dc.get_seq_length() == T
+        ak = aki_b200.AkiKVCache(1, 1, 32, 96, t_cap=T + 4, device=dev)
+        mod(hidden[:, :T], None, None, past_key_values=ak, mma_segments=segs, mma_rope=rp(0, T))
+        d1, _ = mod(hidden[:, T:], None, None, past_key_values=dc, mma_rope=rp(T, T + 1))
+        d2, _ = mod(hidden[:, T:], None, None, past_key_values=ak, mma_rope=rp(T, T + 1))
+        assert float((d1.float() - d2.float()).abs().max()) < 2e-2 * max(1.0, float(d2.float().abs().max()))
+    # plugin function: same contract as eager_attention_forward
+    q, k, v = Hp.qkv_inputs(1, T, 32, 96, seed=6, device=dev)
+    o, w = aki_b200.aki_mma_attention(None, q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2), None,
+                                      scaling=96 ** -0.5, mma_segments=segs)
+    assert w is None and o.shape == (1, T, 32, 96) and o.is_contiguous()
+    S = O.segments_ref(g["lang"], np.ones_like(g["lang"]), N, Hp.MEDIA_ID)
+    ref32 = Hp.oracle_attention(q.cpu(), k.cpu(), v.cpu(), S, 96 ** -0.5)
+    ref16 = Hp.oracle_attention(q.cpu(), k.cpu(), v.cpu(), S, 96 ** -0.5, dtype=torch.bfloat16)
+    ok, ek, eb, _ = Hp.within_tolerance(o, ref16, ref32)
+    assert ok, (ek, eb)
+
+
+def test_phi3_model_with_swapped_attention_matches_hf_eager_on_reference_mask():
+    """2-layer random-init Phi-3 (hidden 3072, 32x96): HF eager fed the reference's inverted 4-D mask vs the same
+    weights with every self_attn replaced by AkiMMAAttention fed mma_segments.  Logits within bf16 tolerance."""
+    import aki_b200
+    from aki_b200 import ops
+    from transformers import Phi3ForCausalLM
+    g = np.load(os.path.join(GOLDEN, "attn_cfg1_small.npz"))
+    cfg = _config(g["short_factor"], g["long_factor"])
+    torch.manual_seed(0)
+    model = Phi3ForCausalLM(cfg).to(dev).to(torch.bfloat16).eval()
+    B, L, N = 2, 80, 32
+    lang, am = Hp.make_prompt(B, L, N, 1, pad_right=9)
+    segs = ops.build_segments(torch.from_numpy(lang).to(dev), torch.from_numpy(am).to(dev), N, Hp.MEDIA_ID)
+    T = segs.T
+    S = O.segments_ref(lang, am, N, Hp.MEDIA_ID)
+    m4 = torch.from_numpy(O.expand_segments_to_4d(S)).to(dev)
+    torch.manual_seed(5)
+    embeds = (torch.randn(B, T, 3072, device=dev) * 0.5).to(torch.bfloat16)
+    pos = torch.arange(T, device=dev)[None].expand(B, -1)
+    add = O.invert_4d_mask(m4, torch.bfloat16).to(torch.bfloat16)          # a7: {0, finfo(bf16).min}
+    with torch.no_grad():
+        ref = model(inputs_embeds=embeds, attention_mask=add, position_ids=pos, use_cache=False).logits
+        n = aki_b200.replace_phi3_attention(model)
+        assert n == 2
+        got = model(inputs_embeds=embeds, attention_mask=segs.spliced_mask_2d(), position_ids=pos, use_cache=False,
+                    mma_segments=segs).logits
+    rows = Hp.live_rows(S, B, T).to(dev)
+    d = (got.float() - ref.float())[rows]
+    scale = float(ref.float()[rows].abs().max())
+    assert float(d.abs().max()) < 0.06 * max(scale, 1.0), (float(d.abs().max()), scale)
+    assert float(d.pow(2).mean().sqrt()) < 0.01 * max(scale, 1.0)
