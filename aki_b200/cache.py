@@ -63,5 +63,10 @@ class AkiKVCache:
         if need > self.t_cap:
             raise ValueError(f"KV cache capacity {self.t_cap} exceeded (need {need})")
 
+    def reset(self) -> None:
+        """Forget the contents (buffers are reused; nothing is freed)."""
+        self._len = [0] * len(self.k)
+        self.kv_len.zero_()
+
     def to_legacy_cache(self):
         return tuple(self[i] for i in range(len(self.k)))

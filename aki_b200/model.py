@@ -1,0 +1,89 @@
+"""Minimal Phi-3.5-mini runner around the drop-in attention: prefill that writes the KV cache in place and a greedy
+decode loop ("next" rows f-1 / f-4 of SURVEY section 8 in their simplest form).  The decoder layers are the installed
+transformers' Phi3DecoderLayer objects with `self_attn` swapped for AkiMMAAttention (same parameters / state-dict
+keys); everything except the attention stays cuBLAS / ATen.  Calling the layers directly avoids HF's (B,1,T,T) mask
+construction -- the MMA description travels as `mma_segments`."""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+from torch import nn
+
+from . import ops
+from .attention import replace_phi3_attention
+from .cache import AkiKVCache
+from .rope import LongRope
+
+
+def phi35_mini_config(num_layers: int = 32, short_factor=None, long_factor=None, vocab_size: int = 32064):
+    """microsoft/Phi-3.5-mini-instruct geometry (hidden 3072, 32 heads x 96, MLP 8192, longrope 4096 -> 131072).
+    The hub config.json is not available offline: the 48 longrope factors default to 1.0 unless given."""
+    from transformers import Phi3Config
+    half = 48
+    sf = [1.0] * half if short_factor is None else [float(x) for x in short_factor]
+    lf = [1.0] * half if long_factor is None else [float(x) for x in long_factor]
+    return Phi3Config(hidden_size=3072, num_attention_heads=32, num_key_value_heads=32, intermediate_size=8192,
+                      vocab_size=vocab_size, num_hidden_layers=num_layers, max_position_embeddings=131072,
+                      original_max_position_embeddings=4096, rms_norm_eps=1e-5, attention_dropout=0.0, pad_token_id=0,
+                      rope_parameters={"rope_type": "longrope", "rope_theta": 10000.0, "short_factor": sf,
+                                       "long_factor": lf, "original_max_position_embeddings": 4096},
+                      attn_implementation="eager")
+
+
+class AkiPhi3Runner(nn.Module):
+    def __init__(self, config, device="cuda", dtype=torch.bfloat16, seed: int = 0):
+        super().__init__()
+        from transformers import Phi3ForCausalLM
+        torch.manual_seed(seed)
+        with torch.device(device):
+            self.lm = Phi3ForCausalLM(config).to(dtype)
+        replace_phi3_attention(self.lm)
+        self.config = config
+        rp = config.rope_parameters
+        self.rope = LongRope(96, rp["rope_theta"], rp["short_factor"], rp["long_factor"], config.max_position_embeddings,
+                             rp["original_max_position_embeddings"], device=device)
+
+    def new_cache(self, batch: int, t_cap: int) -> AkiKVCache:
+        p = next(self.lm.parameters())
+        return AkiKVCache(self.config.num_hidden_layers, batch, 32, 96, t_cap, p.device, p.dtype)
+
+    def _run_layers(self, h, cos, sin, segs, cache):
+        for layer in self.lm.model.layers:
+            h = layer(h, attention_mask=None, position_ids=None, past_key_values=cache, use_cache=cache is not None,
+                      position_embeddings=None, mma_segments=segs, mma_rope=(cos, sin))
+            if isinstance(h, tuple):
+                h = h[0]
+        return self.lm.model.norm(h)
+
+    @torch.no_grad()
+    def prefill(self, inputs_embeds: torch.Tensor, segs: Optional[ops.MMASegments], cache: Optional[AkiKVCache],
+                last_only: bool = True):
+        """inputs_embeds (B,T,3072); positions arange(T) as AKI.generate passes them (aki.py:184-191)."""
+        B, T, _ = inputs_embeds.shape
+        cos, sin = self.rope.tables(torch.arange(T, device=inputs_embeds.device)[None], max_position=T - 1)
+        h = self._run_layers(inputs_embeds, cos, sin, segs, cache)
+        return self.lm.lm_head(h[:, -1:] if last_only else h)
+
+    @torch.no_grad()
+    def decode_step(self, token_ids: torch.Tensor, cache: AkiKVCache):
+        """One greedy step for every sequence: position id = past length (aki_generation.py:72-84)."""
+        past = cache.get_seq_length()
+        h = self.lm.model.embed_tokens(token_ids)            # (B,1,3072)
+        pos = torch.full((1, 1), past, device=h.device, dtype=torch.long)
+        cos, sin = self.rope.tables(pos, max_position=past)
+        h = self._run_layers(h, cos, sin, None, cache)
+        return self.lm.lm_head(h)
+
+    @torch.no_grad()
+    def generate(self, inputs_embeds, segs, max_new_tokens: int, t_cap: Optional[int] = None):
+        B, T, _ = inputs_embeds.shape
+        cache = self.new_cache(B, t_cap or (T + max_new_tokens))
+        logits = self.prefill(inputs_embeds, segs, cache)
+        out = []
+        tok = logits[:, -1].argmax(-1, keepdim=True)
+        for _ in range(max_new_tokens):
+            out.append(tok)
+            logits = self.decode_step(tok, cache)
+            tok = logits[:, -1].argmax(-1, keepdim=True)
+        return torch.cat(out, dim=1), cache

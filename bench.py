@@ -50,6 +50,8 @@ def parse():
     ap.add_argument("--images", type=int, default=4)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-prefill", action="store_true", help="skip the AKI-4B prefill/decode section")
+    ap.add_argument("--prefill-batch", type=int, default=8)
     return ap.parse_args()
 
 
@@ -153,6 +155,97 @@ def cpu_reference_run(T, B, n_img, steps, warmup, threads=None):
             times.append(dt)
     ms = statistics.median(times) * 1e3
     return 43008.0 * nnz / (ms * 1e-3) / 1e12, ms, threads, nnz
+
+
+# ------------------------------------------------------------------------------------------------ AKI-4B prefill
+def prefill_section(dev, rank, world, steps, warmup):
+    """BASELINE config 2: random-init AKI-4B language model (Phi-3.5-mini geometry, 32 layers, bf16), batch 8 per
+    GPU, 1 image (144 vision tokens, AKI default) + 511 text tokens -> T = 655; prefill writes the KV cache in place,
+    then 32 greedy decode steps.  LM only: the vision tower is replaced by N(0,0.02) vision tokens.
+    e2e: host token ids + host vision tokens -> device -> segments + splice kernels -> prefill -> argmax -> host."""
+    import aki_b200
+    from aki_b200 import ops
+    from aki_b200.model import AkiPhi3Runner, phi35_mini_config
+    import torch.distributed as dist
+    B, L, N = parse().prefill_batch, 512, 144
+    g = np.random.default_rng(100 + rank)
+    lang = g.integers(3, 31000, size=(B, L)).astype(np.int64)
+    lang[:, 8] = MEDIA_ID; lang[:, L - 40] = ASST_ID
+    am = np.ones_like(lang)
+    T = L - 1 + N
+    runner = AkiPhi3Runner(phi35_mini_config(), device=dev, seed=0)
+    host_ids = torch.from_numpy(lang).pin_memory(); host_am = torch.from_numpy(am).pin_memory()
+    host_vis = (torch.randn(B, 1, N, 3072) * 0.02).to(torch.bfloat16).pin_memory()
+    host_out = torch.empty(B, dtype=torch.int64).pin_memory()
+    me = type("M", (), {})()
+    me.lang_model = runner.lm; me.media_token_id = MEDIA_ID; me.num_tokens_per_vis = N; me.pad_token_id = 32000
+    n_dec = 32
+    cache = runner.new_cache(B, T + n_dec + 1)
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    ids_d, am_d, vis_d = host_ids.to(dev), host_am.to(dev), host_vis.to(dev)
+    prep = aki_b200.prepare_inputs_for_forward(me, vis_d, ids_d, am_d, padding_side="left", exact_shape=False)
+    embeds, segs = prep["inputs_embeds"], prep["mma_segments"]
+
+    def prefill_resident():
+        cache.reset()
+        return runner.prefill(embeds, segs, cache)
+
+    def prefill_e2e():
+        cache.reset()
+        i_d = host_ids.to(dev, non_blocking=True); a_d = host_am.to(dev, non_blocking=True)
+        v_d = host_vis.to(dev, non_blocking=True)
+        pr = aki_b200.prepare_inputs_for_forward(me, v_d, i_d, a_d, padding_side="left", exact_shape=False)
+        logits = runner.prefill(pr["inputs_embeds"], pr["mma_segments"], cache)
+        host_out.copy_(logits[:, -1].argmax(-1), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    res = {}
+    for name, fn in (("resident", prefill_resident), ("e2e", prefill_e2e)):
+        for _ in range(max(3, warmup // 3)):
+            fn()
+        barrier()
+        a, b_ = ev(), ev()
+        n = max(5, steps // 5)
+        a.record()
+        for _ in range(n):
+            fn()
+        b_.record()
+        barrier()
+        res[name] = a.elapsed_time(b_) / n
+    # decode: 32 steps on top of the last prefill
+    logits = prefill_resident()
+    tok = logits[:, -1].argmax(-1, keepdim=True)
+    for _ in range(3):
+        runner.decode_step(tok, cache)
+    cache.reset(); prefill_resident()
+    barrier()
+    a, b_ = ev(), ev()
+    a.record()
+    for _ in range(n_dec):
+        tok = runner.decode_step(tok, cache)[:, -1].argmax(-1, keepdim=True)
+    b_.record()
+    barrier()
+    dec_ms = a.elapsed_time(b_) / n_dec
+    kv_bytes = 2 * B * 32 * (T + n_dec / 2) * 96 * 2 * 32          # K+V read per step, all layers
+    stats = torch.tensor([res["resident"], res["e2e"], dec_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(stats, op=dist.ReduceOp.MAX)
+    r_ms, e_ms, d_ms = (float(x) for x in stats)
+    del runner, cache
+    torch.cuda.empty_cache()
+    return {"workload": f"AKI-4B LM (Phi-3.5-mini geometry, 32 layers, random init, bf16) prefill B={B}/gpu T={T} "
+                        f"(1 image x {N} + {L - 1} text), KV cache written in place, last-token logits",
+            "prefill_tokens_per_s": world * B * T / (r_ms * 1e-3), "prefill_ms": r_ms,
+            "prefill_e2e_tokens_per_s": world * B * T / (e_ms * 1e-3), "prefill_e2e_ms": e_ms,
+            "e2e_h2d_bytes": int(host_ids.numel() * 8 * 2 + host_vis.numel() * 2), "e2e_d2h_bytes": B * 8,
+            "decode_tokens_per_s": world * B / (d_ms * 1e-3), "decode_ms_per_step": d_ms,
+            "decode_attn_kv_bytes_per_step": kv_bytes}
 
 
 # ------------------------------------------------------------------------------------------------ main
@@ -285,6 +378,11 @@ def main():
         total_flops = float(sm[4])
     else:
         e2e_ms_r = float(stats[3]); total_flops = flops
+    prefill = None
+    if not args.no_prefill:
+        del qkv, d_o, d_qkv, k_rot
+        torch.cuda.empty_cache()
+        prefill = prefill_section(dev, rank, world, args.steps, args.warmup)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -310,6 +408,8 @@ def main():
         line["e2e"] = {"value": total_flops / (e2e_ms_r * 1e-3) / 1e12, "unit": "TFLOP/s",
                        "h2d_bytes_per_step": B * T * H * D * 2, "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms_r,
                        "api": "AkiMMAAttention.forward + backward (qkv_proj, o_proj included in time, not in FLOPs)"}
+    if prefill is not None:
+        line["prefill"] = prefill
     if not args.no_cpu and world >= 1:
         Ts = min(T, 2048)
         val, ms, threads, _ = cpu_reference_run(Ts, 1, min(n_img, 4), 2, 1)
