@@ -5,7 +5,7 @@
 // on a (B,32,T,T) tensor).  One CTA owns one 128-key tile of one (batch, head) and walks exactly the query tiles
 // that can see it (kv_tile_q_mask: with MMA that set is the image-row tiles before the diagonal plus everything
 // from the diagonal on), with everything transposed so that keys sit on TMEM lanes:
-//     S^T  = K Q_i^T                      (SS)        P^T = exp2(S^T*c - LSE_i)      -> TMEM (bf16, aliases S^T)
+//     S^T  = K Q_i^T                      (SS)        P^T = exp2(S^T*c - LSE_i)      -> TMEM (bf16, own columns)
 //     dP^T = V dO_i^T                     (SS)        dS^T = P^T o (dP^T - delta_i)  -> smem (bf16)
 //     dV  += P^T dO_i                     (TS)
 //     dK  += dS^T Q_i                     (SS, A K-major = dS^T, B MN-major = Q_i)       (x scale in the epilogue)
@@ -17,7 +17,7 @@
 //
 // 16 warps: 0 TMA producer | 1 MMA issuer | 2 TMEM allocator | 3 builds the query-tile list | 4-11 compute
 // (thread <-> key row r; the two warpgroups split the 128 query columns of a tile in halves) | 12-15 dQ drain.
-// TMEM columns: S^T/P^T [0,128)  dP^T/dQ [128,256)  dV [256,352)  dK [352,448).
+// TMEM columns: S^T [0,128)  dP^T/dQ [128,256)  dV [256,352)  dK [352,448)  P^T (bf16 pairs) [448,512).
 // Shared memory: K, V 24 KB each (resident), Q ring 2x24 KB, dO ring 2x24 KB, dS^T 32 KB, dQ staging 2x16 KB,
 // per-tile row statistics, query-tile list.
 #include <math.h>
@@ -44,7 +44,7 @@ constexpr int SMEM_STATS = SMEM_DQ + 2 * DQ_ATOM_BYTES;     // 2 stages x {lse2,
 constexpr int SMEM_QLIST = SMEM_STATS + 2 * 4 * 128 * 4;    // uint16[MAX_TILES]
 constexpr int SMEM_TOTAL = SMEM_QLIST + MAX_TILES * 2;
 constexpr int SMEM_ALLOC = SMEM_TOTAL + 1024;
-constexpr uint32_t TM_S = 0, TM_DP = 128, TM_DV = 256, TM_DK = 352;
+constexpr uint32_t TM_S = 0, TM_DP = 128, TM_DV = 256, TM_DK = 352, TM_P = 448;
 constexpr int REGS_CTRL = 48, REGS_COMPUTE = 176, REGS_DRAIN = 112;   // 128*48 + 256*176 + 128*112 = 65536
 }  // namespace bwd
 
@@ -205,7 +205,7 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
         tc_fence_after();
 #pragma unroll
         for (int k = 0; k < 8; ++k)
-          umma_ts(tmem + TM_DV, tmem + TM_S + 8 * k, mnmajor(sDO, k), IDESC_N96_BMN, (it > 0 || k > 0));
+          umma_ts(tmem + TM_DV, tmem + TM_P + 8 * k, mnmajor(sDO, k), IDESC_N96_BMN, (it > 0 || k > 0));
         umma_commit(BAR(DO_EMPTY + it % DO_STAGES));
         // S^T of the next query tile (the S region is free once dV has consumed P^T: in-order pipe)
         if (it + 1 < n_q) {
@@ -324,7 +324,7 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
       uint32_t pk[32];
 #pragma unroll
       for (int x = 0; x < 32; ++x) pk[x] = pack_bf16x2(p[2 * x], p[2 * x + 1]);
-      tmem_st_x32(tmem + TM_S + lane_base + 32 * hq, pk);
+      tmem_st_x32(tmem + TM_P + lane_base + 32 * hq, pk);   // own columns: the other half may still be reading S^T
       tmem_wait_st();
       tc_fence_before();
       mbar_arrive(BAR(P_READY));
