@@ -4,6 +4,12 @@
 //   mode 2: TS  A in TMEM  (bf16 pairs)      x B MN-major (TMA tile)   -> O  = P V        (128x96,  K=128)
 //   mode 3: SS  A MN-major (thread-written)  x B MN-major (TMA tile)   -> dQ = dS K       (128x96,  K=128)
 //   mode 4: SS  A K-major  (thread-written)  x B MN-major (TMA tile)   -> dK = dS^T Q     (128x96,  K=128)
+//   mode 5: mode 1 plus a 7th k-step in the SWIZZLE_NONE K-major form: A = thread-written "ones" rows [1,1,1,0..],
+//           B = TMA-loaded [128][8] bf16 row statistics (box 8x128, no swizzle), second 16-byte K chunk of both
+//           operands = one shared zero region reached through LBO  -> S'[m][n] = S[m][n] + sum_k aug[n][k]
+//           (this is how the backward folds -LSE / -delta into the S^T and dP^T MMAs).
+//           mode 6: same with SBO = 0 for the ones operand (all row groups alias one core matrix);
+//           mode 7: same with LBO = 0 for the statistics operand (second K chunk aliases the first).
 // Descriptor strides (LBO/SBO) and the per-k-step start-address advance are arguments so that one GPU
 // call can sweep candidates:   umma_probe <mode> <a_lbo> <a_sbo> <a_kadv> <b_lbo> <b_sbo> <b_kadv>
 #include <cstdio>
@@ -23,12 +29,18 @@ struct ProbeArgs {
 
 __global__ void __launch_bounds__(128, 1)
 probe_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
-             const __nv_bfloat16* __restrict__ X,   // [128][128] bf16 (modes 2,3,4)
+             const __grid_constant__ CUtensorMap mapAug, const __nv_bfloat16* __restrict__ X,   // [128][128] bf16 (modes 2,3,4)
              float* __restrict__ D, uint8_t* __restrict__ dump, ProbeArgs pa) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;                 // 32 KB region
   uint8_t* sB = smem + 32768;         // 24 KB
+  uint8_t* sAug = smem + 57344;       // 2 KB  [16 groups][8 rows][16 B]
+  uint8_t* sOnes = smem + 59392;      // 2 KB
+  uint8_t* sZero = smem + 61440;      // 2 KB
+  const bool aug = pa.mode >= 5;
+  const int mode_in = pa.mode;
+  if (aug) pa.mode = 1;
   __shared__ __align__(8) uint64_t bar_load, bar_mma;
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -44,9 +56,18 @@ probe_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
 
+  if (aug) {
+    for (int r = tid; r < 128; r += 128) {
+      const uint4 one = make_uint4(0x3f803f80u, 0x00003f80u, 0u, 0u);   // bf16 [1,1,1,0,0,0,0,0]
+      *reinterpret_cast<uint4*>(sOnes + (r >> 3) * 128 + (r & 7) * 16) = one;
+      *reinterpret_cast<uint4*>(sZero + r * 16) = make_uint4(0, 0, 0, 0);
+    }
+    fence_proxy_async_smem();
+  }
   if (tid == 0) {
-    uint32_t bytes = 24576 * ((pa.mode <= 1) ? 2 : 1);
+    uint32_t bytes = 24576 * ((pa.mode <= 1) ? 2 : 1) + (aug ? 2048 : 0);
     mbar_arrive_expect_tx(smem_u32(&bar_load), bytes);
+    if (aug) tma_load_4d(smem_u32(sAug), &mapAug, smem_u32(&bar_load), 0, 0, 0, 0);
     if (pa.mode <= 1)
       for (int a = 0; a < 3; ++a) tma_load_4d(smem_u32(sA + a * 8192), &mapA, smem_u32(&bar_load), a * 32, 0, 0, 0);
     for (int a = 0; a < 3; ++a) tma_load_4d(smem_u32(sB + a * 8192), &mapB, smem_u32(&bar_load), a * 32, 0, 0, 0);
@@ -90,6 +111,12 @@ probe_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
           uint32_t boff = (k >> 1) * 8192 + (k & 1) * pa.b_kadv;
           umma_ss(tmem, umma_smem_desc(smem_u32(sA) + aoff, pa.a_lbo, pa.a_sbo, UMMA_SW64),
                   umma_smem_desc(smem_u32(sB) + boff, pa.b_lbo, pa.b_sbo, UMMA_SW64), idesc, k > 0);
+        }
+        if (aug) {
+          const uint32_t ones_sbo = (mode_in == 6) ? 0u : 128u;
+          const uint32_t aug_lbo = (mode_in == 7) ? 0u : (uint32_t)(sZero - sAug);
+          umma_ss(tmem, umma_smem_desc(smem_u32(sOnes), (uint32_t)(sZero - sOnes), ones_sbo, UMMA_SW_NONE),
+                  umma_smem_desc(smem_u32(sAug), aug_lbo, 128, UMMA_SW_NONE), idesc, 1);
         }
       } else if (pa.mode == 2) {
         const uint32_t idesc = umma_idesc_bf16(128, 96, 0, 1);
@@ -182,9 +209,29 @@ int main(int argc, char** argv) {
     return m;
   };
   CUtensorMap mA = make_map(dA), mB = make_map(dB);
-  const int smem_bytes = 32768 + 24576 + 1024;
+  std::vector<float> AUG(128 * 8, 0.f);
+  std::vector<__nv_bfloat16> hAug(128 * 8);
+  for (int n = 0; n < 128; ++n) {
+    AUG[n * 8 + 0] = bf(100.f * rnd()); AUG[n * 8 + 1] = bf(rnd()); AUG[n * 8 + 2] = bf(0.01f * rnd());
+    for (int k = 0; k < 8; ++k) hAug[n * 8 + k] = __float2bfloat16(AUG[n * 8 + k]);
+  }
+  __nv_bfloat16* dAug;
+  CK(cudaMalloc(&dAug, hAug.size() * 2));
+  CK(cudaMemcpy(dAug, hAug.data(), hAug.size() * 2, cudaMemcpyHostToDevice));
+  CUtensorMap mAug;
+  {
+    cuuint64_t dims[4] = {8, 128, 1, 1};
+    cuuint64_t strides[3] = {16, 16 * 128, 16 * 128};
+    cuuint32_t box[4] = {8, 128, 1, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = encode(&mAug, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, dAug, dims, strides, box, es,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { printf("encode(aug) failed %d\n", (int)r); exit(3); }
+  }
+  const int smem_bytes = 32768 + 24576 + 6144 + 1024;
   CK(cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-  probe_kernel<<<1, 128, smem_bytes>>>(mA, mB, dX, dD, ddump, pa);
+  probe_kernel<<<1, 128, smem_bytes>>>(mA, mB, mAug, dX, dD, ddump, pa);
   CK(cudaGetLastError());
   CK(cudaDeviceSynchronize());
 
@@ -202,13 +249,14 @@ int main(int argc, char** argv) {
     printf("mode 0: TMA SW64 layout mismatches = %d / %d\n", bad, 128 * 96);
     return 0;
   }
-  const int ncol = (pa.mode == 1) ? 128 : 96;
+  const int ncol = (pa.mode == 1 || pa.mode >= 5) ? 128 : 96;
   std::vector<float> D(128 * ncol), R(128 * ncol, 0.f);
   CK(cudaMemcpy(D.data(), dD, D.size() * 4, cudaMemcpyDeviceToHost));
   for (int m = 0; m < 128; ++m)
     for (int n = 0; n < ncol; ++n) {
       double acc = 0;
-      if (pa.mode == 1) for (int k = 0; k < 96; ++k) acc += (double)A[m * 96 + k] * Bm[n * 96 + k];
+      if (pa.mode == 1 || pa.mode >= 5) for (int k = 0; k < 96; ++k) acc += (double)A[m * 96 + k] * Bm[n * 96 + k];
+      if (pa.mode >= 5) acc += (double)AUG[n * 8] + AUG[n * 8 + 1] + AUG[n * 8 + 2];
       if (pa.mode == 2) for (int k = 0; k < 128; ++k) acc += (double)X[m * 128 + k] * Bm[k * 96 + n];
       if (pa.mode == 3) for (int k = 0; k < 128; ++k) acc += (double)X[k * 128 + m] * Bm[k * 96 + n];
       if (pa.mode == 4) for (int k = 0; k < 128; ++k) acc += (double)X[m * 128 + k] * Bm[k * 96 + n];
