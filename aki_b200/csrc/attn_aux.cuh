@@ -8,9 +8,12 @@
 namespace aki {
 
 struct BwdWorkspace {
-  __nv_bfloat16* q_rot;  // (B,H,T,D) bf16, post-RoPE queries
-  float* delta;          // (B,H,T)
-  float* dq_accum;       // (B,H,T,D) fp32
+  __nv_bfloat16* q_rot;   // (B,H,T,D) bf16, post-RoPE queries
+  float* delta;           // (B,H,T)
+  float* dq_accum;        // (B,H,T,D) fp32
+  __nv_bfloat16* q_aug;   // (B,H,t_pad,8) bf16: -LSE/scale as hi+mid+lo, 0 x5   (statistics k-step of S^T)
+  __nv_bfloat16* do_aug;  // (B,H,t_pad,8) bf16: -delta as hi+mid+lo, 0 x5       (statistics k-step of dP^T)
+  int t_pad;              // T rounded up to the 128-row tile: the statistics tiles are never out of bounds
   size_t bytes;
 };
 
@@ -24,6 +27,10 @@ inline BwdWorkspace carve_bwd_workspace(void* base, int B, int H, int T, int D) 
   w.q_rot = reinterpret_cast<__nv_bfloat16*>(p + off); off += align256(n * D * 2);
   w.delta = reinterpret_cast<float*>(p + off);         off += align256(n * 4);
   w.dq_accum = reinterpret_cast<float*>(p + off);      off += align256(n * D * 4);
+  w.t_pad = (T + 127) / 128 * 128;
+  const size_t na = (size_t)B * H * w.t_pad;
+  w.q_aug = reinterpret_cast<__nv_bfloat16*>(p + off);  off += align256(na * 16);
+  w.do_aug = reinterpret_cast<__nv_bfloat16*>(p + off); off += align256(na * 16);
   w.bytes = off;
   return w;
 }
@@ -49,6 +56,7 @@ int check_attn_params(const AkiMmaAttnParams& p);
 
 int make_tile_map(CUtensorMap* m, const AkiMmaTensor4& t, int B, int H, int T, int box_rows);
 int make_dq_accum_map(CUtensorMap* m, float* dq_accum, int B, int H, int T);
+int make_row_stats_map(CUtensorMap* m, void* base, int B, int H, int t_pad);
 int launch_bwd_preprocess(const AkiMmaAttnBwdParams& p, const BwdWorkspace& w, cudaStream_t st);
 int launch_dq_finalize(const AkiMmaAttnBwdParams& p, const BwdWorkspace& w, float scale, cudaStream_t st);
 

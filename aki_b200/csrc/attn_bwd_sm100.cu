@@ -5,21 +5,30 @@
 // on a (B,32,T,T) tensor).  One CTA owns one 128-key tile of one (batch, head) and walks exactly the query tiles
 // that can see it (kv_tile_q_mask: with MMA that set is the image-row tiles before the diagonal plus everything
 // from the diagonal on), with everything transposed so that keys sit on TMEM lanes:
-//     S^T  = K Q_i^T                      (SS)        P^T = exp2(S^T*c - LSE_i)      -> TMEM (bf16, own columns)
-//     dP^T = V dO_i^T                     (SS)        dS^T = P^T o (dP^T - delta_i)  -> smem (bf16)
+//     S^T  = K Q_i^T  - LSE_i/scale       (SS)        P^T = exp2(S^T * scale*log2e)   -> TMEM (bf16, own columns)
+//     dP^T = V dO_i^T - delta_i           (SS)        dS^T = P^T o dP^T               -> smem (bf16)
 //     dV  += P^T dO_i                     (TS)
+//     dQ_i = dS K                         (SS, A MN-major = the dS^T buffer, B MN-major = K)
 //     dK  += dS^T Q_i                     (SS, A K-major = dS^T, B MN-major = Q_i)       (x scale in the epilogue)
-//     dQ_i = dS K                         (SS, A MN-major = the same dS^T buffer, B MN-major = K)
+// The per-query statistics are folded INTO the two score MMAs: a 7th k-step multiplies a constant "ones" operand
+// [1,1,1,0..] on the key side with a [128][8] bf16 row-statistics operand on the query side that holds -LSE/scale
+// (resp. -delta) split into three bf16 terms (hi + mid + lo: 2^-24 relative).  In this transposed layout LSE and
+// delta vary along the TMEM COLUMNS, so without the fold every element would need a shared-memory broadcast read
+// and an FFMA/FADD; with it the element-wise work per score is one multiply (packed f32x2), one ex2 and one
+// bf16 pack for P, and one multiply and one pack for dS (ncu before the fold: the compute warps, not the tensor
+// pipe, bounded the kernel at 35% tensor-active).  Rows beyond the sequence get -1e30 there, so P is exactly 0.
 // dK / dV accumulate in TMEM over the whole loop; dQ_i is drained by a dedicated warpgroup: TMEM -> registers ->
 // fp32 SWIZZLE_128B staging in shared memory -> TMA tensor reduction (cp.reduce.async.bulk.tensor .add) into a
-// fp32 accumulator in HBM (per-lane global atomics cost ~1.3 cycles per lane per SM and were 10x slower);
-// aki_mma_attn_bwd's finalize kernel applies scale, the inverse RoPE and the bf16 cast.
+// fp32 accumulator in HBM; aki_mma_attn_bwd's finalize kernel applies scale, the inverse RoPE and the bf16 cast.
 //
-// 16 warps: 0 TMA producer | 1 MMA issuer | 2 TMEM allocator | 3 builds the query-tile list | 4-11 compute
-// (thread <-> key row r; the two warpgroups split the 128 query columns of a tile in halves) | 12-15 dQ drain.
+// 16 warps: 0 TMA producer | 1 MMA issuer | 2 TMEM allocator | 3 query-tile list, then per-tile mask statistics
+// (row_lo / width of the mutual interval, published through a 2-stage mbarrier ring; only tiles that are not fully
+// visible read them) | 4-11 compute (thread <-> key row r; the two warpgroups split the 128 query columns of a
+// tile in halves) | 12-15 dQ drain.  Tensor-pipe order per query tile: dV(i) S(i+1) dQ(i) dK(i) dP(i+1) -- the dQ
+// drain overlaps dK, the exponentials of tile i+1 overlap dQ/dK/dP.
 // TMEM columns: S^T [0,128)  dP^T/dQ [128,256)  dV [256,352)  dK [352,448)  P^T (bf16 pairs) [448,512).
 // Shared memory: K, V 24 KB each (resident), Q ring 2x24 KB, dO ring 2x24 KB, dS^T 32 KB, dQ staging 2x16 KB,
-// per-tile row statistics, query-tile list.
+// row-statistics operands 2x2 KB + 2x2 KB, ones/zero core matrices, mask statistics, query-tile list.
 #include <math.h>
 #include "attn_aux.cuh"
 #include "sm100_ptx.cuh"
@@ -27,31 +36,36 @@
 namespace aki {
 
 namespace bwd {
-constexpr int BN = 128, BM = 128, HD = 96;
+constexpr int BN = 128, BM = 128;
 constexpr int ATOM_BYTES = 128 * 64;          // bf16 operand atom [128 rows][64 B], SWIZZLE_64B
 constexpr int TILE_BYTES = 3 * ATOM_BYTES;
+constexpr int AUG_BYTES = 128 * 16;           // row-statistics operand [16 groups][8 rows][16 B], no swizzle
 constexpr int DQ_ATOM_BYTES = 128 * 128;      // fp32 staging atom [128 rows][32 floats], SWIZZLE_128B
 constexpr int Q_STAGES = 2, DO_STAGES = 2;
 constexpr int THREADS = 512;
-constexpr int MAX_TILES = 2048;
+constexpr int MAX_TILES = 1024;
 constexpr int SMEM_K = 0;
 constexpr int SMEM_V = SMEM_K + TILE_BYTES;
 constexpr int SMEM_Q = SMEM_V + TILE_BYTES;
 constexpr int SMEM_DO = SMEM_Q + Q_STAGES * TILE_BYTES;
 constexpr int SMEM_DS = SMEM_DO + DO_STAGES * TILE_BYTES;   // 4 atoms [128][64 B]
 constexpr int SMEM_DQ = SMEM_DS + 4 * ATOM_BYTES;           // 2 staging atoms
-constexpr int SMEM_STATS = SMEM_DQ + 2 * DQ_ATOM_BYTES;     // 2 stages x {lse2, delta, lo, hi} x 128 x 4 B
-constexpr int SMEM_QLIST = SMEM_STATS + 2 * 4 * 128 * 4;    // uint16[MAX_TILES]
+constexpr int SMEM_QAUG = SMEM_DQ + 2 * DQ_ATOM_BYTES;      // Q_STAGES x AUG_BYTES
+constexpr int SMEM_DOAUG = SMEM_QAUG + Q_STAGES * AUG_BYTES;
+constexpr int SMEM_ONES = SMEM_DOAUG + DO_STAGES * AUG_BYTES;   // one core matrix [8][16 B] = [1,1,1,0,0,0,0,0] x 8
+constexpr int SMEM_ZERO = SMEM_ONES + 128;                      // one all-zero core matrix
+constexpr int SMEM_STATS = SMEM_ZERO + 128;                 // 2 stages x {lo[128], width[128], flags[4]} int32
+constexpr int STATS_STAGE_INTS = 260;
+constexpr int SMEM_QLIST = SMEM_STATS + 2 * STATS_STAGE_INTS * 4 + 32;   // uint16[MAX_TILES]
 constexpr int SMEM_TOTAL = SMEM_QLIST + MAX_TILES * 2;
 constexpr int SMEM_ALLOC = SMEM_TOTAL + 1024;
+static_assert(SMEM_ALLOC + 256 <= 232448, "shared memory budget");
 constexpr uint32_t TM_S = 0, TM_DP = 128, TM_DV = 256, TM_DK = 352, TM_P = 448;
-constexpr int REGS_CTRL = 48, REGS_COMPUTE = 176, REGS_DRAIN = 112;   // 128*48 + 256*176 + 128*112 = 65536
+constexpr int REGS_CTRL = 64, REGS_COMPUTE = 168, REGS_DRAIN = 112;   // 128*64 + 256*168 + 128*112 = 65536
 }  // namespace bwd
 
 struct BwdKernelParams {
   TensorView d_k, d_v;
-  const float* lse;
-  const float* delta;
   const float* rope_cos;
   const float* rope_sin;
   int64_t rope_stride_b;
@@ -60,10 +74,22 @@ struct BwdKernelParams {
   float scale_log2, scale;
 };
 
+__device__ __forceinline__ uint64_t f32x2_pack(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void f32x2_mul(float& lo, float& hi, float a_lo, float a_hi, float b_lo, float b_hi) {
+  uint64_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(f32x2_pack(a_lo, a_hi)), "l"(f32x2_pack(b_lo, b_hi)));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(r));
+}
+
 __global__ void __launch_bounds__(bwd::THREADS, 1)
 attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                       const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_do,
-                      const __grid_constant__ CUtensorMap map_dq, const BwdKernelParams P) {
+                      const __grid_constant__ CUtensorMap map_dq, const __grid_constant__ CUtensorMap map_qaug,
+                      const __grid_constant__ CUtensorMap map_doaug, const BwdKernelParams P) {
   using namespace bwd;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -71,10 +97,10 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
   constexpr int KV_FULL = 0, Q_FULL = 1, Q_EMPTY = Q_FULL + Q_STAGES, DO_FULL = Q_EMPTY + Q_STAGES,
                 DO_EMPTY = DO_FULL + DO_STAGES, S_FULL = DO_EMPTY + DO_STAGES, P_READY = S_FULL + 1,
                 DP_FULL = P_READY + 1, DS_READY = DP_FULL + 1, DQ_FULL = DS_READY + 1, DQ_DRAINED = DQ_FULL + 1,
-                N_BARS = DQ_DRAINED + 1;
+                ALL_DONE = DQ_DRAINED + 1, ST_FULL = ALL_DONE + 1, ST_EMPTY = ST_FULL + 2, N_BARS = ST_EMPTY + 2;
   __shared__ __align__(8) uint64_t bars[N_BARS];
   __shared__ uint32_t tmem_base_s;
-  __shared__ int n_q_s;
+  __shared__ int n_q_s, keys_all_valid_s;
   const uint32_t bar0 = smem_u32(bars);
   auto BAR = [&](int i) { return bar0 + 8u * i; };
 
@@ -84,6 +110,7 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
   const int len = meta_len(P.mm, b, P.T);
   const int j0 = kt * BN;
   uint16_t* const qlist = reinterpret_cast<uint16_t*>(smem_gen + SMEM_QLIST);
+  int* const stats_gen = reinterpret_cast<int*>(smem_gen + SMEM_STATS);
 
   if (tid == 0) {
     mbar_init(BAR(KV_FULL), 1);
@@ -91,12 +118,21 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
     for (int i = 0; i < DO_STAGES; ++i) { mbar_init(BAR(DO_FULL + i), 1); mbar_init(BAR(DO_EMPTY + i), 1); }
     mbar_init(BAR(S_FULL), 1); mbar_init(BAR(P_READY), 256); mbar_init(BAR(DP_FULL), 1);
     mbar_init(BAR(DS_READY), 256); mbar_init(BAR(DQ_FULL), 1); mbar_init(BAR(DQ_DRAINED), 128);
+    mbar_init(BAR(ALL_DONE), 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(BAR(ST_FULL + i), 1); mbar_init(BAR(ST_EMPTY + i), 256); }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc<512>(smem_u32(&tmem_base_s));
+  if (warp == 2) {
+    tmem_alloc<512>(smem_u32(&tmem_base_s));
+    // constant operands of the statistics k-step: one core matrix of [1,1,1,0,0,0,0,0] rows, one of zeros
+    const int lane = tid & 31;
+    if (lane < 8) *reinterpret_cast<uint4*>(smem_gen + SMEM_ONES + lane * 16) = make_uint4(0x3f803f80u, 0x00003f80u, 0u, 0u);
+    else if (lane < 16) *reinterpret_cast<uint4*>(smem_gen + SMEM_ZERO + (lane - 8) * 16) = make_uint4(0u, 0u, 0u, 0u);
+    fence_proxy_async_smem();
+  }
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_k); tma_prefetch_desc(&map_v); tma_prefetch_desc(&map_do);
-    tma_prefetch_desc(&map_dq);
+    tma_prefetch_desc(&map_dq); tma_prefetch_desc(&map_qaug); tma_prefetch_desc(&map_doaug);
   }
   if (warp == 3) {
     // list of query tiles to visit, ascending
@@ -131,13 +167,22 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
         n = max(0, n_live - kt);
       }
     }
-    if (lane == 0) n_q_s = n;
+    // are all 128 keys of this tile inside the sequence and causally visible (no padding)?
+    bool ok = true;
+    if (lane < 4) {
+      const int jw = j0 + 32 * lane;
+      ok = (jw + 32 <= len);
+      if (ok && P.mm.vbits) ok = (P.mm.vbits[(size_t)b * P.mm.bits_pitch + (jw >> 5)] == 0xffffffffu);
+    }
+    ok = __all_sync(0xffffffffu, ok);
+    if (lane == 0) { n_q_s = n; keys_all_valid_s = ok ? 1 : 0; }
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
   const int n_q = n_q_s;
+  const bool keys_all_valid = keys_all_valid_s != 0;
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -152,13 +197,15 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
         const int i0 = (int)qlist[it] * BM;
         const int sq = it % Q_STAGES, sd = it % DO_STAGES;
         mbar_wait(BAR(Q_EMPTY + sq), ((it / Q_STAGES) & 1) ^ 1);
-        mbar_arrive_expect_tx(BAR(Q_FULL + sq), TILE_BYTES);
+        mbar_arrive_expect_tx(BAR(Q_FULL + sq), TILE_BYTES + AUG_BYTES);
         for (int a = 0; a < 3; ++a)
           tma_load_4d(smem_base + SMEM_Q + sq * TILE_BYTES + a * ATOM_BYTES, &map_q, BAR(Q_FULL + sq), a * 32, i0, h, b);
+        tma_load_4d(smem_base + SMEM_QAUG + sq * AUG_BYTES, &map_qaug, BAR(Q_FULL + sq), 0, i0, h, b);
         mbar_wait(BAR(DO_EMPTY + sd), ((it / DO_STAGES) & 1) ^ 1);
-        mbar_arrive_expect_tx(BAR(DO_FULL + sd), TILE_BYTES);
+        mbar_arrive_expect_tx(BAR(DO_FULL + sd), TILE_BYTES + AUG_BYTES);
         for (int a = 0; a < 3; ++a)
           tma_load_4d(smem_base + SMEM_DO + sd * TILE_BYTES + a * ATOM_BYTES, &map_do, BAR(DO_FULL + sd), a * 32, i0, h, b);
+        tma_load_4d(smem_base + SMEM_DOAUG + sd * AUG_BYTES, &map_doaug, BAR(DO_FULL + sd), 0, i0, h, b);
       }
     }
   } else if (warp == 1) {
@@ -172,6 +219,11 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
       // descriptors differ only in the 14-bit start-address field: build the constant parts once
       const uint64_t DESC_KMAJ = umma_smem_desc(0, 16, 512, UMMA_SW64);
       const uint64_t DESC_MNMAJ = umma_smem_desc(0, ATOM_BYTES, 512, UMMA_SW64);
+      // statistics k-step (no swizzle, K-major): ones = one core matrix shared by every row group (SBO 0), its
+      // second K chunk = the zero core matrix (LBO); row statistics = [16 groups][128 B], second K chunk aliases
+      // the first (LBO 0) and meets the zero chunk of the ones operand.  Validated in tools/umma_probe.cu (5-7).
+      const uint64_t DESC_ONES = umma_smem_desc(smem_base + SMEM_ONES, SMEM_ZERO - SMEM_ONES, 0, UMMA_SW_NONE);
+      const uint64_t DESC_AUG = umma_smem_desc(0, 0, 128, UMMA_SW_NONE);
       auto kmajor = [&](uint32_t base, int k) {   // 16-element K step k of a [rows][96|128] K-major SW64 tile
         return DESC_KMAJ | (uint64_t)(((base + (k >> 1) * ATOM_BYTES + (k & 1) * 32) >> 4) & 0x3FFFu);
       };
@@ -180,13 +232,17 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
       };
       auto issue_s = [&](int it) {
         const uint32_t sQ = smem_base + SMEM_Q + (it % Q_STAGES) * TILE_BYTES;
+        const uint32_t sA = smem_base + SMEM_QAUG + (it % Q_STAGES) * AUG_BYTES;
 #pragma unroll
         for (int k = 0; k < 6; ++k) umma_ss(tmem + TM_S, kmajor(sK, k), kmajor(sQ, k), IDESC_SS_KK, k > 0);
+        umma_ss(tmem + TM_S, DESC_ONES, DESC_AUG | (uint64_t)((sA >> 4) & 0x3FFFu), IDESC_SS_KK, 1);
       };
       auto issue_dp = [&](int it) {
         const uint32_t sDO = smem_base + SMEM_DO + (it % DO_STAGES) * TILE_BYTES;
+        const uint32_t sA = smem_base + SMEM_DOAUG + (it % DO_STAGES) * AUG_BYTES;
 #pragma unroll
         for (int k = 0; k < 6; ++k) umma_ss(tmem + TM_DP, kmajor(sV, k), kmajor(sDO, k), IDESC_SS_KK, k > 0);
+        umma_ss(tmem + TM_DP, DESC_ONES, DESC_AUG | (uint64_t)((sA >> 4) & 0x3FFFu), IDESC_SS_KK, 1);
       };
       mbar_wait(BAR(KV_FULL), 0);
       mbar_wait(BAR(Q_FULL + 0), 0);
@@ -207,23 +263,23 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
         for (int k = 0; k < 8; ++k)
           umma_ts(tmem + TM_DV, tmem + TM_P + 8 * k, mnmajor(sDO, k), IDESC_N96_BMN, (it > 0 || k > 0));
         umma_commit(BAR(DO_EMPTY + it % DO_STAGES));
-        // S^T of the next query tile (the S region is free once dV has consumed P^T: in-order pipe)
+        // S^T of the next query tile (the S region is free once P^T(it) has been written)
         if (it + 1 < n_q) {
           mbar_wait(BAR(Q_FULL + (it + 1) % Q_STAGES), ((it + 1) / Q_STAGES) & 1);
           tc_fence_after();
           issue_s(it + 1);
           umma_commit(BAR(S_FULL));
         }
-        // dK += dS^T Q_it ;  dQ_it = dS K
+        // dQ_it = dS K first (its drain then overlaps dK), dK += dS^T Q_it
         mbar_wait(BAR(DS_READY), it & 1);
         tc_fence_after();
 #pragma unroll
         for (int k = 0; k < 8; ++k)
-          umma_ss(tmem + TM_DK, kmajor(sDS, k), mnmajor(sQ, k), IDESC_N96_BMN, (it > 0 || k > 0));
-#pragma unroll
-        for (int k = 0; k < 8; ++k)
           umma_ss(tmem + TM_DP, mnmajor(sDS, k), mnmajor(sK, k), IDESC_N96_AMN_BMN, k > 0);
         umma_commit(BAR(DQ_FULL));
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          umma_ss(tmem + TM_DK, kmajor(sDS, k), mnmajor(sQ, k), IDESC_N96_BMN, (it > 0 || k > 0));
         umma_commit(BAR(Q_EMPTY + it % Q_STAGES));
         // dP^T of the next query tile overwrites the dQ region: wait until it has been drained
         if (it + 1 < n_q) {
@@ -234,9 +290,37 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
           umma_commit(BAR(DP_FULL));
         }
       }
+      umma_commit(BAR(ALL_DONE));
     }
-  } else if (warp < 4) {
+  } else if (warp == 2) {
     setmaxnreg_dec<REGS_CTRL>();
+  } else if (warp == 3) {
+    // ------------------------------------------------------------------ mask statistics of each query tile
+    setmaxnreg_dec<REGS_CTRL>();
+    const int lane = tid & 31;
+    for (int it = 0; it < n_q; ++it) {
+      const int st = it & 1;
+      mbar_wait(BAR(ST_EMPTY + st), ((it >> 1) & 1) ^ 1);
+      const int i0 = (int)qlist[it] * BM;
+      int* dst = stats_gen + st * STATS_STAGE_INTS;
+      bool rel = false;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int row = 32 * k + lane, i = i0 + row;
+        int lo = 0, w = 0;
+        if (i < len && P.mm.row_lo) {
+          lo = __ldg(P.mm.row_lo + (size_t)b * P.mm.meta_pitch + i);
+          w = max(__ldg(P.mm.row_hi + (size_t)b * P.mm.meta_pitch + i) - lo, 0);
+        }
+        rel = rel || (w > 0 && lo < j0 + BN && lo + w > j0);
+        dst[row] = lo;
+        dst[128 + row] = w;
+      }
+      rel = __any_sync(0xffffffffu, rel);
+      if (lane == 0) dst[256] = rel ? 1 : 0;
+      __syncwarp();
+      if (lane == 0) mbar_arrive(BAR(ST_FULL + st));
+    }
   } else if (warp < 12) {
     // ------------------------------------------------------------------ compute warps: P^T and dS^T
     setmaxnreg_inc<REGS_COMPUTE>();
@@ -245,80 +329,53 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
     const int hq = ct >> 7;                   // which half of the query columns
     const int j = j0 + r;                     // key index
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-    float* const stats_gen = reinterpret_cast<float*>(smem_gen + SMEM_STATS);
-    const size_t bhT = ((size_t)b * P.H + h) * P.T;
 
     // key-side predicate bits
     bool k_valid = (j < len), k_mutual = (j < len);
     if (j < len && P.mm.vbits) k_valid = (P.mm.vbits[(size_t)b * P.mm.bits_pitch + (j >> 5)] >> (j & 31)) & 1u;
     if (j < len && P.mm.mbits) k_mutual = (P.mm.mbits[(size_t)b * P.mm.bits_pitch + (j >> 5)] >> (j & 31)) & 1u;
-    const bool warp_keys_valid = __all_sync(0xffffffffu, k_valid);
-
-    // per-tile row statistics are fetched one tile ahead into registers, then published to smem
-    float pre_a = 0.f, pre_b = 0.f;           // hq==0: (lse*log2e, delta) ; hq==1: (row_lo, row_hi) as int bits
-    auto prefetch = [&](int it) {
-      const int i = (int)qlist[it] * BM + r;
-      if (hq == 0) {
-        pre_a = (i < len) ? __ldg(P.lse + bhT + i) * 1.4426950408889634f : INFINITY;
-        pre_b = (i < len) ? __ldg(P.delta + bhT + i) : 0.f;
-      } else {
-        int lo = 0, hi = 0;
-        if (i < len && P.mm.row_lo) {
-          lo = __ldg(P.mm.row_lo + (size_t)b * P.mm.meta_pitch + i);
-          hi = __ldg(P.mm.row_hi + (size_t)b * P.mm.meta_pitch + i);
-        }
-        pre_a = __int_as_float(lo); pre_b = __int_as_float(hi);
-      }
-    };
-    auto publish = [&](int it) {   // stage layout: [lse2 128][delta 128][lo 128][hi 128]
-      float* st = stats_gen + (it & 1) * 512 + hq * 256;
-      st[r] = pre_a;
-      st[128 + r] = pre_b;
-    };
 
     float p[64];   // P^T row half, kept from phase a to phase b
 
     auto phase_a = [&](int it) {
-      publish(it);
-      if (it + 1 < n_q) prefetch(it + 1);
-      named_bar_sync(1, 256);
-      const int qt = (int)qlist[it], i0 = qt * BM;
-      const float* st = stats_gen + (it & 1) * 512;
+      const int qt = (int)qlist[it];
+      const bool full = (qt > kt) && keys_all_valid;     // CTA-uniform
       mbar_wait(BAR(S_FULL), it & 1);
       tc_fence_after();
       uint32_t sraw[64];
       tmem_ld_x32(tmem + TM_S + lane_base + 64 * hq, sraw);
       tmem_ld_x32(tmem + TM_S + lane_base + 64 * hq + 32, sraw + 32);
-      // fully visible: every key of this warp precedes every query of the tile, all valid, all queries live
-      const bool full = (qt > kt) && (i0 + BM <= len) && warp_keys_valid;
-      const float4* lse4 = reinterpret_cast<const float4*>(st + 64 * hq);
       tmem_wait_ld();
-      if (full) {
 #pragma unroll
-        for (int c4 = 0; c4 < 16; ++c4) {
-          const float4 v = lse4[c4];
-          p[4 * c4 + 0] = ex2_approx(fmaf(__uint_as_float(sraw[4 * c4 + 0]), P.scale_log2, -v.x));
-          p[4 * c4 + 1] = ex2_approx(fmaf(__uint_as_float(sraw[4 * c4 + 1]), P.scale_log2, -v.y));
-          p[4 * c4 + 2] = ex2_approx(fmaf(__uint_as_float(sraw[4 * c4 + 2]), P.scale_log2, -v.z));
-          p[4 * c4 + 3] = ex2_approx(fmaf(__uint_as_float(sraw[4 * c4 + 3]), P.scale_log2, -v.w));
-        }
-      } else {
-        const int4* lo4 = reinterpret_cast<const int4*>(st + 256 + 64 * hq);
-        const int4* hi4 = reinterpret_cast<const int4*>(st + 384 + 64 * hq);
+      for (int c = 0; c < 64; c += 2) {
+        float x0, x1;
+        f32x2_mul(x0, x1, __uint_as_float(sraw[c]), __uint_as_float(sraw[c + 1]), P.scale_log2, P.scale_log2);
+        p[c] = ex2_approx(x0);
+        p[c + 1] = ex2_approx(x1);
+      }
+      if (!full) {
+        // c visible iff (c >= cmin, causal) or (row c of the tile is an image row whose interval holds key j)
+        const int st = it & 1;
+        mbar_wait(BAR(ST_FULL + st), (it >> 1) & 1);
+        const int* sp = stats_gen + st * STATS_STAGE_INTS;
+        const int cmin = k_valid ? (j - qt * BM - 64 * hq) : (1 << 30);
+        if (sp[256] && k_mutual) {
+          const int4* lo4 = reinterpret_cast<const int4*>(sp + 64 * hq);
+          const int4* w4 = reinterpret_cast<const int4*>(sp + 128 + 64 * hq);
 #pragma unroll
-        for (int c4 = 0; c4 < 16; ++c4) {
-          const int4 a4 = lo4[c4], e4 = hi4[c4];
-          const float4 l4 = lse4[c4];
-          const float lse2[4] = {l4.x, l4.y, l4.z, l4.w};
-          const int lo[4] = {a4.x, a4.y, a4.z, a4.w}, hi[4] = {e4.x, e4.y, e4.z, e4.w};
+          for (int c4 = 0; c4 < 16; ++c4) {
+            const int4 a = lo4[c4], w = w4[c4];
+            const int lo[4] = {a.x, a.y, a.z, a.w}, wd[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int c = 4 * c4 + e;
-            const int i = i0 + 64 * hq + c;
-            const bool ok = (i < len) && ((j <= i && k_valid) || (j >= lo[e] && j < hi[e] && k_mutual));
-            const float val = ex2_approx(fmaf(__uint_as_float(sraw[c]), P.scale_log2, -lse2[e]));
-            p[c] = ok ? val : 0.f;
+            for (int e = 0; e < 4; ++e) {
+              const int c = 4 * c4 + e;
+              const bool ok = (c >= cmin) || ((unsigned)(j - lo[e]) < (unsigned)wd[e]);
+              p[c] = ok ? p[c] : 0.f;
+            }
           }
+        } else {
+#pragma unroll
+          for (int c = 0; c < 64; ++c) p[c] = (c >= cmin) ? p[c] : 0.f;
         }
       }
       uint32_t pk[32];
@@ -328,48 +385,40 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
       tmem_wait_st();
       tc_fence_before();
       mbar_arrive(BAR(P_READY));
+      mbar_arrive(BAR(ST_EMPTY + (it & 1)));
     };
 
     auto phase_b = [&](int it) {
-      const float* st = stats_gen + (it & 1) * 512 + 128;   // delta
       mbar_wait(BAR(DP_FULL), it & 1);
       tc_fence_after();
       uint32_t draw[64];
       tmem_ld_x32(tmem + TM_DP + lane_base + 64 * hq, draw);
       tmem_ld_x32(tmem + TM_DP + lane_base + 64 * hq + 32, draw + 32);
-      const float4* dl4 = reinterpret_cast<const float4*>(st + 64 * hq);
       tmem_wait_ld();
       const uint32_t ds_base = smem_base + SMEM_DS;
 #pragma unroll
       for (int c8 = 0; c8 < 8; ++c8) {   // 8 query columns -> one 16-byte chunk of the dS^T row
         uint32_t w[4];
-        const float4 da = dl4[2 * c8], db = dl4[2 * c8 + 1];
-        const float dl[8] = {da.x, da.y, da.z, da.w, db.x, db.y, db.z, db.w};
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const int c = 8 * c8 + 2 * e;
-          w[e] = pack_bf16x2(p[c] * (__uint_as_float(draw[c]) - dl[2 * e]),
-                             p[c + 1] * (__uint_as_float(draw[c + 1]) - dl[2 * e + 1]));
+          float d0, d1;
+          f32x2_mul(d0, d1, p[c], p[c + 1], __uint_as_float(draw[c]), __uint_as_float(draw[c + 1]));
+          w[e] = pack_bf16x2(d0, d1);
         }
         const int col = 64 * hq + 8 * c8;          // query column of this chunk
         const uint32_t addr = ds_base + (col >> 5) * ATOM_BYTES + sw64_offset(r, (col & 31) >> 3);
-        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]));
       }
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(BAR(DS_READY));
     };
 
-    if (n_q > 0) {
-      prefetch(0);
-      phase_a(0);
-      for (int it = 0; it < n_q; ++it) {
-        phase_b(it);
-        if (it + 1 < n_q) phase_a(it + 1);
-      }
-      // the last DQ_FULL commit covers every dK / dV MMA
-      mbar_wait(BAR(DQ_FULL), (n_q - 1) & 1);
-      tc_fence_after();
+    // a(0) | b(0) a(1) | b(1) a(2) | ... | b(n_q-1)   (one instance of each phase in the instruction stream)
+    for (int step = 0; step <= n_q && n_q > 0; ++step) {
+      if (step > 0) phase_b(step - 1);
+      if (step < n_q) phase_a(step);
     }
 
     // ---- epilogue: dV, dK (x scale, inverse RoPE) -> bf16 -> global.  tcgen05.ld is warp-collective: the loads
@@ -380,6 +429,19 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
       __nv_bfloat16* dvrow = P.d_v.row(b, js, h) + 48 * hq;
       __nv_bfloat16* dkrow = P.d_k.row(b, js, h);
       if (n_q > 0) {
+        // RoPE tables of this key row: fetched before the wait so that their latency hides behind the last MMAs
+        float cs[24], sn[24];
+        if (P.rope_cos) {
+          const float4* c4 = reinterpret_cast<const float4*>(P.rope_cos + (size_t)b * P.rope_stride_b + (size_t)js * 48 + 24 * hq);
+          const float4* s4 = reinterpret_cast<const float4*>(P.rope_sin + (size_t)b * P.rope_stride_b + (size_t)js * 48 + 24 * hq);
+#pragma unroll
+          for (int x = 0; x < 6; ++x) {
+            *reinterpret_cast<float4*>(cs + 4 * x) = __ldg(c4 + x);
+            *reinterpret_cast<float4*>(sn + 4 * x) = __ldg(s4 + x);
+          }
+        }
+        mbar_wait(BAR(ALL_DONE), 0);
+        tc_fence_after();
         uint32_t acc[48];
         tmem_ld_x32(tmem + TM_DV + lane_base + 48 * hq, acc);
         tmem_ld_x16(tmem + TM_DV + lane_base + 48 * hq + 32, acc + 32);
@@ -405,9 +467,7 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
         for (int x = 0; x < 24; ++x) {
           float a = __uint_as_float(lo[x]) * P.scale, e = __uint_as_float(hi[x]) * P.scale;
           if (P.rope_cos) {   // g = R^T g'
-            const float c = __ldg(P.rope_cos + (size_t)b * P.rope_stride_b + (size_t)js * 48 + 24 * hq + x);
-            const float sn = __ldg(P.rope_sin + (size_t)b * P.rope_stride_b + (size_t)js * 48 + 24 * hq + x);
-            const float a2 = a * c + e * sn, e2 = e * c - a * sn;
+            const float a2 = a * cs[x] + e * sn[x], e2 = e * cs[x] - a * sn[x];
             a = a2; e = e2;
           }
           flo[x] = a; fhi[x] = e;
@@ -502,15 +562,16 @@ extern "C" int aki_mma_attn_bwd(const AkiMmaAttnBwdParams* p, aki_stream_t strea
     return AKI_ERR_CUDA;
   }
   AkiMmaTensor4 qrot{w.q_rot, (int64_t)f.H * f.T * f.D, (int64_t)f.D, (int64_t)f.T * f.D};
-  CUtensorMap mq, mk, mv, mdo, mdq;
+  CUtensorMap mq, mk, mv, mdo, mdq, mqa, mda;
   if ((rc = make_tile_map(&mq, qrot, f.B, f.H, f.T, bwd::BM))) return rc;
   if ((rc = make_tile_map(&mk, f.k, f.B, f.H, f.T, bwd::BN))) return rc;
   if ((rc = make_tile_map(&mv, f.v, f.B, f.H, f.T, bwd::BN))) return rc;
   if ((rc = make_tile_map(&mdo, p->d_o, f.B, f.H, f.T, bwd::BM))) return rc;
   if ((rc = make_dq_accum_map(&mdq, w.dq_accum, f.B, f.H, f.T))) return rc;
+  if ((rc = make_row_stats_map(&mqa, w.q_aug, f.B, f.H, w.t_pad))) return rc;
+  if ((rc = make_row_stats_map(&mda, w.do_aug, f.B, f.H, w.t_pad))) return rc;
   BwdKernelParams kp;
   kp.d_k = view_of(p->d_k); kp.d_v = view_of(p->d_v);
-  kp.lse = f.lse; kp.delta = w.delta;
   kp.rope_cos = f.rope_cos; kp.rope_sin = f.rope_sin; kp.rope_stride_b = f.rope_stride_b;
   kp.mm = mask_meta_from(f);
   kp.B = f.B; kp.H = f.H; kp.T = f.T;
@@ -530,7 +591,7 @@ extern "C" int aki_mma_attn_bwd(const AkiMmaAttnBwdParams* p, aki_stream_t strea
     }
     attr_done = true;
   }
-  attn_bwd_sm100_kernel<<<(unsigned)grid, bwd::THREADS, bwd::SMEM_ALLOC, st>>>(mq, mk, mv, mdo, mdq, kp);
+  attn_bwd_sm100_kernel<<<(unsigned)grid, bwd::THREADS, bwd::SMEM_ALLOC, st>>>(mq, mk, mv, mdo, mdq, mqa, mda, kp);
   if ((rc = check_launch())) return rc;
   return launch_dq_finalize(*p, w, f.scale, st);   // dS^T is kept unscaled inside the kernel
 }

@@ -471,6 +471,21 @@ int make_dq_accum_map(CUtensorMap* m, float* dq_accum, int B, int H, int T) {
   return AKI_OK;
 }
 
+// row statistics (B,H,t_pad,8) bf16 contiguous -> [8 x 128 x 1 x 1] boxes, no swizzle: one box is the K-major
+// SWIZZLE_NONE operand [16 row groups][8 rows][16 B] of the backward's statistics k-step
+int make_row_stats_map(CUtensorMap* m, void* base, int B, int H, int t_pad) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) { set_last_cuda_error("cuTensorMapEncodeTiled entry point not found"); return AKI_ERR_CUDA; }
+  cuuint64_t dims[4] = {8, (cuuint64_t)t_pad, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t strides[3] = {16, (cuuint64_t)t_pad * 16, (cuuint64_t)H * t_pad * 16};
+  cuuint32_t box[4] = {8, 128, 1, 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_last_cuda_error("cuTensorMapEncodeTiled(row stats) failed"); return AKI_ERR_CUDA; }
+  return AKI_OK;
+}
+
 }  // namespace aki
 
 using namespace aki;

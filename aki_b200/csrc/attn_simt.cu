@@ -87,34 +87,105 @@ attn_fwd_simt_kernel(TensorView q, TensorView k, TensorView v, TensorView o, flo
 }
 
 // ------------------------------------------------------------------------------------------------ preprocess
-// delta[b,h,t] = sum_d O*dO ; q_rot[b,h,t,:] = RoPE(q)  (or a plain copy when no tables are given)
+// Per (b,t,h) row: delta = sum_d O*dO ; q_rot = RoPE(q) (plain copy without tables) ; and the two [8] bf16
+// row-statistics operands of the tcgen05 backward: q_aug = -LSE/scale, do_aug = -delta, each split into
+// hi + mid + lo bf16 terms (rows that see nothing, and the padding rows t in [T, t_pad), get -1e30 / 0 so that
+// their P^T is exactly 0).  HBM-bound: 6 lanes per row (lane l owns the 16-byte chunks l and l+6, i.e. the RoPE
+// pair d <-> d+48), 5 rows per warp, every access a 16-byte vector.
+__device__ __forceinline__ void split3_bf16(float v, __nv_bfloat16& a0, __nv_bfloat16& a1, __nv_bfloat16& a2) {
+  a0 = __float2bfloat16(v);
+  const float r1 = v - __bfloat162float(a0);
+  a1 = __float2bfloat16(r1);
+  a2 = __float2bfloat16(r1 - __bfloat162float(a1));
+}
+
 __global__ void __launch_bounds__(128)
-bwd_preprocess_kernel(TensorView q, TensorView o, TensorView d_o, const float* __restrict__ rope_cos,
-                      const float* __restrict__ rope_sin, int64_t rope_stride_b, int T, int H,
-                      __nv_bfloat16* __restrict__ q_rot, float* __restrict__ delta) {
-  const int t = blockIdx.x, b = blockIdx.y;
+bwd_preprocess_kernel(TensorView q, TensorView o, TensorView d_o, const float* __restrict__ lse,
+                      const float* __restrict__ rope_cos, const float* __restrict__ rope_sin, int64_t rope_stride_b,
+                      int B, int T, int t_pad, int H, float inv_scale, __nv_bfloat16* __restrict__ q_rot,
+                      float* __restrict__ delta, __nv_bfloat16* __restrict__ q_aug, __nv_bfloat16* __restrict__ do_aug) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int h = warp; h < H; h += 4) {
-    const __nv_bfloat16* orow = o.row(b, t, h);
-    const __nv_bfloat16* drow = d_o.row(b, t, h);
-    float acc = 0.f;
-    for (int d = lane; d < 96; d += 32) acc = fmaf(bf(orow[d]), bf(drow[d]), acc);
+  const int g = lane / 6, l = lane - 6 * g;
+  const long long n_rows = (long long)B * t_pad * H;
+  const long long row = ((long long)blockIdx.x * 4 + warp) * 5 + g;
+  const bool active = (lane < 30) && (row < n_rows);
+  int h = 0, t = 0, b = 0;
+  if (active) {
+    h = (int)(row % H);
+    const long long bt = row / H;
+    t = (int)(bt % t_pad);
+    b = (int)(bt / t_pad);
+  }
+  const bool live = active && (t < T);
+  float part = 0.f;
+  if (live) {
+    const uint4 q_lo = *reinterpret_cast<const uint4*>(q.row(b, t, h) + 8 * l);
+    const uint4 q_hi = *reinterpret_cast<const uint4*>(q.row(b, t, h) + 48 + 8 * l);
+    const uint4 o_lo = *reinterpret_cast<const uint4*>(o.row(b, t, h) + 8 * l);
+    const uint4 o_hi = *reinterpret_cast<const uint4*>(o.row(b, t, h) + 48 + 8 * l);
+    const uint4 g_lo = *reinterpret_cast<const uint4*>(d_o.row(b, t, h) + 8 * l);
+    const uint4 g_hi = *reinterpret_cast<const uint4*>(d_o.row(b, t, h) + 48 + 8 * l);
+    const __nv_bfloat162* ol = reinterpret_cast<const __nv_bfloat162*>(&o_lo);
+    const __nv_bfloat162* oh = reinterpret_cast<const __nv_bfloat162*>(&o_hi);
+    const __nv_bfloat162* gl = reinterpret_cast<const __nv_bfloat162*>(&g_lo);
+    const __nv_bfloat162* gh = reinterpret_cast<const __nv_bfloat162*>(&g_hi);
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-    if (lane == 0) delta[((size_t)b * H + h) * T + t] = acc;
-    const __nv_bfloat16* qrow = q.row(b, t, h);
-    __nv_bfloat16* dst = q_rot + (((size_t)b * H + h) * T + t) * 96;
-    for (int d = lane; d < 48; d += 32) {
-      float lo = bf(qrow[d]), hi = bf(qrow[d + 48]);
-      if (rope_cos) {
-        const float c = rope_cos[(size_t)b * rope_stride_b + (size_t)t * 48 + d];
-        const float s = rope_sin[(size_t)b * rope_stride_b + (size_t)t * 48 + d];
-        const float lo2 = lo * c - hi * s, hi2 = hi * c + lo * s;
-        lo = lo2; hi = hi2;
-      }
-      dst[d] = __float2bfloat16(lo);
-      dst[d + 48] = __float2bfloat16(hi);
+    for (int e = 0; e < 4; ++e) {
+      const float2 a = __bfloat1622float2(ol[e]), c = __bfloat1622float2(gl[e]);
+      const float2 d = __bfloat1622float2(oh[e]), f = __bfloat1622float2(gh[e]);
+      part = fmaf(a.x, c.x, part); part = fmaf(a.y, c.y, part);
+      part = fmaf(d.x, f.x, part); part = fmaf(d.y, f.y, part);
     }
+    uint4 r_lo = q_lo, r_hi = q_hi;
+    if (rope_cos) {
+      float cs[8], sn[8];
+      const float* cr = rope_cos + (size_t)b * rope_stride_b + (size_t)t * 48 + 8 * l;
+      const float* sr = rope_sin + (size_t)b * rope_stride_b + (size_t)t * 48 + 8 * l;
+      *reinterpret_cast<float4*>(cs) = __ldg(reinterpret_cast<const float4*>(cr));
+      *reinterpret_cast<float4*>(cs + 4) = __ldg(reinterpret_cast<const float4*>(cr + 4));
+      *reinterpret_cast<float4*>(sn) = __ldg(reinterpret_cast<const float4*>(sr));
+      *reinterpret_cast<float4*>(sn + 4) = __ldg(reinterpret_cast<const float4*>(sr + 4));
+      const __nv_bfloat162* ql = reinterpret_cast<const __nv_bfloat162*>(&q_lo);
+      const __nv_bfloat162* qh = reinterpret_cast<const __nv_bfloat162*>(&q_hi);
+      __nv_bfloat162* rl = reinterpret_cast<__nv_bfloat162*>(&r_lo);
+      __nv_bfloat162* rh = reinterpret_cast<__nv_bfloat162*>(&r_hi);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 lo = __bfloat1622float2(ql[e]), hi = __bfloat1622float2(qh[e]);
+        rl[e] = __floats2bfloat162_rn(lo.x * cs[2 * e] - hi.x * sn[2 * e], lo.y * cs[2 * e + 1] - hi.y * sn[2 * e + 1]);
+        rh[e] = __floats2bfloat162_rn(hi.x * cs[2 * e] + lo.x * sn[2 * e], hi.y * cs[2 * e + 1] + lo.y * sn[2 * e + 1]);
+      }
+    }
+    __nv_bfloat16* dst = q_rot + (((size_t)b * H + h) * T + t) * 96;
+    *reinterpret_cast<uint4*>(dst + 8 * l) = r_lo;
+    *reinterpret_cast<uint4*>(dst + 48 + 8 * l) = r_hi;
+  }
+  // delta: sum of the 6 lane partials of the row (every lane of the warp takes part in the shuffles)
+  float dl = 0.f;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) dl += __shfl_sync(0xffffffffu, part, min(6 * g + k, 31));
+  if (active && l == 0) {
+    __nv_bfloat16 qa[8], da[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { qa[e] = __float2bfloat16(0.f); da[e] = __float2bfloat16(0.f); }
+    float v = -1e30f;
+    if (live) {
+      const size_t idx = ((size_t)b * H + h) * T + t;
+      delta[idx] = dl;
+      const float L = lse[idx];
+      if (L < 3.0e38f) {
+        v = -L * inv_scale;
+        split3_bf16(v, qa[0], qa[1], qa[2]);
+      } else {
+        qa[0] = __float2bfloat16(v);
+      }
+      split3_bf16(-dl, da[0], da[1], da[2]);
+    } else {
+      qa[0] = __float2bfloat16(v);
+    }
+    const size_t ar = (((size_t)b * H + h) * t_pad + t) * 8;
+    *reinterpret_cast<uint4*>(q_aug + ar) = *reinterpret_cast<const uint4*>(qa);
+    *reinterpret_cast<uint4*>(do_aug + ar) = *reinterpret_cast<const uint4*>(da);
   }
 }
 
@@ -257,8 +328,12 @@ int check_attn_params(const AkiMmaAttnParams& p) {
 
 int launch_bwd_preprocess(const AkiMmaAttnBwdParams& p, const BwdWorkspace& w, cudaStream_t st) {
   const AkiMmaAttnParams& f = p.fwd;
-  bwd_preprocess_kernel<<<dim3(f.T, f.B), 128, 0, st>>>(view_of(f.q), view_of(f.o), view_of(p.d_o), f.rope_cos,
-                                                         f.rope_sin, f.rope_stride_b, f.T, f.H, w.q_rot, w.delta);
+  const long long n_rows = (long long)f.B * w.t_pad * f.H;
+  const long long blocks = (n_rows + 19) / 20;
+  if (blocks <= 0 || blocks >= (1ll << 31)) return AKI_ERR_BAD_SHAPE;
+  bwd_preprocess_kernel<<<(unsigned)blocks, 128, 0, st>>>(view_of(f.q), view_of(f.o), view_of(p.d_o), f.lse, f.rope_cos,
+                                                           f.rope_sin, f.rope_stride_b, f.B, f.T, w.t_pad, f.H,
+                                                           1.0f / f.scale, w.q_rot, w.delta, w.q_aug, w.do_aug);
   return check_launch();
 }
 
