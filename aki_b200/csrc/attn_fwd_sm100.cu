@@ -11,14 +11,16 @@
 // CTA = 2 query tiles x 128 rows of one (batch, head), key tiles of 64; 12 warps:
 //   warp 0      TMA producer (Q once, then K_j / V_j through two 4-deep rings of 12 KB tiles)
 //   warp 1      MMA issuer: S_t[j&1] = Q_t K_j^T (SS, N=64), O_t += P_t V_j (TS, P read from TMEM)
-//   warp 2      TMEM allocator;   warp 3 idle
+//   warp 2      TMEM allocator;   warp 3 finds the first key tile that holds padding
 //   warps 4-7   softmax of tile 0 (thread r <-> row r <-> TMEM lane r), warps 8-11 softmax of tile 1
-// S is DOUBLE-BUFFERED per query tile (that is why the key tile is 64 wide: 4 x 64 S columns + 2 x 96 O + 2 x 32 P
-// = 512 TMEM columns exactly): QK^T of key tile j+2 is issued as soon as the softmax has read S(j), so a softmax
-// warp goes straight from tile j to tile j+1 and the chain softmax -> PV -> QK -> softmax of the single-buffered
-// design (measured: 1200 idle cycles per tile) disappears.  P has its own columns, so PV(j) never blocks QK(j+2).
+// S is DOUBLE-BUFFERED per query tile and P_t(j) (bf16 pairs) is written IN PLACE over the first 32 columns of
+// the buffer S_t(j) was read from: QK^T(j+2) is issued right behind PV(j) on the in-order tensor pipe, so the
+// buffer is free again exactly when its P has been consumed and a softmax warp never waits for the tensor pipe
+// (only the rare O rescale and the epilogue wait for PV).  Per key tile a softmax warp runs one straight-line
+// chain: start the TMEM load of S(j+1) -> row max of S(j) (3-input max) -> exp2/sum/pack of S(j) -> P store ->
+// arrive.  Tiles below the diagonal that hold no padding (j < n_full, one comparison) skip the predicate.
 // The exp2 (MUFU) pipe is the real bound of this head_dim: 64 exp vs 384 tensor cycles per row per key tile.
-// TMEM columns: S0a S0b S1a S1b [0,256) | O0 [256,352) O1 [352,448) | P0 [448,480) P1 [480,512).
+// TMEM columns: S0a S0b S1a S1b [0,256) | O0 [256,352) O1 [352,448).
 // Shared memory: Q 2x24 KB; K ring 4x12 KB; V ring 4x12 KB.  Every tile is 3 SWIZZLE_64B atoms [rows][64 B]
 // (head_dim 96 = 3 x 32), the layout both the TMA boxes and the UMMA descriptors use (tools/umma_probe.cu).
 #include <math.h>
@@ -40,7 +42,7 @@ constexpr int SMEM_K = SMEM_Q + 2 * Q_TILE;
 constexpr int SMEM_V = SMEM_K + STAGES * KV_TILE;
 constexpr int SMEM_TOTAL = SMEM_V + STAGES * KV_TILE;     // 147456
 constexpr int SMEM_ALLOC = SMEM_TOTAL + 1024;             // slack for 1024-byte alignment
-constexpr uint32_t TM_S = 0, TM_O = 256, TM_P = 448;      // S: tile t buffer u at 128 t + 64 u; O: 96 t; P: 32 t
+constexpr uint32_t TM_S = 0, TM_O = 256;                  // S: tile t buffer u at 128 t + 64 u (P in place); O: 96 t
 constexpr int REGS_CTRL = 64, REGS_SOFTMAX = 216;         // CTA pool: 128*64 + 256*216 = 63488 <= 384*168
 constexpr float RESCALE_THRESHOLD = 8.0f;  // log2 units: P may grow to 2^8 before O is rescaled
 }  // namespace fwd
@@ -54,15 +56,46 @@ struct FwdKernelParams {
   MaskMeta mm;
   int B, H, T, n_qt, n_qp;
   float scale_log2, scale;
-  unsigned long long* trace;  // debug: per-iteration clock64 stamps of one CTA (AKI_MMA_FWD_TRACE=<cta>)
-  int trace_cta;
 };
 
 __device__ __forceinline__ uint32_t low_mask(int n) {  // n low bits set, n clamped to [0,32]
   return n <= 0 ? 0u : (n >= 32 ? 0xffffffffu : ((1u << n) - 1u));
 }
 
-#define TR(slot, j, k) do { if (tracing && (j) < 128) P.trace[((slot) * 128 + (j)) * 8 + (k)] = clock64(); } while (0)
+// D[tmem] (+)= A[smem] * B[smem] with descriptors given as (low word, shared high word)
+__device__ __forceinline__ void umma_ss_lh(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi,
+                                           uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %5, 0;\n\t"
+      "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}\n" ::"r"(d_tmem),
+      "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_ts_lh(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t desc_hi,
+                                           uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\tsetp.ne.b32 p, %5, 0;\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n\t}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// Rare path of the online softmax: the running max grew by more than the threshold, O_t (96 fp32 columns of this
+// thread's TMEM lane) is rescaled by alpha.  Kept out of line so that the per-tile loop stays compact.
+__device__ __noinline__ void rescale_o(uint32_t tm_o, float alpha) {
+  uint32_t o[32];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    tmem_ld_x32(tm_o + 32 * c, o);
+    tmem_wait_ld();
+#pragma unroll
+    for (int x = 0; x < 32; ++x) o[x] = __float_as_uint(__uint_as_float(o[x]) * alpha);
+    tmem_st_x32(tm_o + 32 * c, o);
+  }
+  tmem_wait_st();
+}
 
 template <bool ROPE>
 __global__ void __launch_bounds__(fwd::THREADS, 1)
@@ -77,6 +110,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
                 O_FULL = P_FULL + 2, N_BARS = O_FULL + 2;
   __shared__ __align__(8) uint64_t bars[N_BARS];
   __shared__ uint32_t tmem_base_s;
+  __shared__ int first_bad_s;
   const uint32_t bar0 = smem_u32(bars);
   auto BAR = [&](int i) { return bar0 + 8u * i; };
 
@@ -112,6 +146,26 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
   }
   if (warp == 2) tmem_alloc<512>(smem_u32(&tmem_base_s));
   if (warp == 0 && elect_one()) { tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_k); tma_prefetch_desc(&map_v); }
+  if (warp == 3) {
+    // first 64-key tile (among those this CTA visits) that is not entirely inside the sequence and causally valid
+    const int lane = tid & 31;
+    const int len = meta_len(P.mm, b, P.T);
+    int first = n_max;
+    for (int base = 0; base < n_max; base += 32) {
+      const int jt = base + lane;
+      bool bad = false;
+      if (jt < n_max) {
+        bad = (jt * BN + BN > len);
+        if (!bad && P.mm.vbits) {
+          const uint32_t* w = P.mm.vbits + (size_t)b * P.mm.bits_pitch + 2 * jt;
+          bad = (__ldg(w) != 0xffffffffu) || (__ldg(w + 1) != 0xffffffffu);
+        }
+      }
+      const uint32_t m = __ballot_sync(0xffffffffu, bad);
+      if (m) { first = base + __ffs(m) - 1; break; }
+    }
+    if (lane == 0) first_bad_s = first;
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -155,31 +209,32 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
     // issues the tcgen05 instructions.
     setmaxnreg_dec<REGS_CTRL>();
     const bool leader = elect_one();
-    const bool tracing = P.trace && (int)blockIdx.x == P.trace_cta && leader;
     constexpr uint32_t IDESC_QK = umma_idesc_bf16(BM, BN, 0, 0);
     constexpr uint32_t IDESC_PV = umma_idesc_bf16(BM, HD, 0, 1);
-    // descriptors differ only in the 14-bit start-address field (units of 16 B)
+    // descriptors differ only in the 14-bit start-address field (units of 16 B) of the low word
     const uint64_t DESC_KMAJ = umma_smem_desc(0, 16, 512, UMMA_SW64);
     const uint64_t DESC_V = umma_smem_desc(0, KV_ATOM, 512, UMMA_SW64);     // MN-major: LBO = atom stride
-    const uint32_t q_lo = (smem_base + SMEM_Q) >> 4, k_lo = (smem_base + SMEM_K) >> 4, v_lo = (smem_base + SMEM_V) >> 4;
+    const uint32_t HI = (uint32_t)(DESC_KMAJ >> 32);                         // identical for both forms
+    const uint32_t KMAJ_LO = (uint32_t)DESC_KMAJ, V_LO = (uint32_t)DESC_V;
+    const uint32_t q_lo = KMAJ_LO + ((smem_base + SMEM_Q) >> 4), k_lo = KMAJ_LO + ((smem_base + SMEM_K) >> 4),
+                   v_lo = V_LO + ((smem_base + SMEM_V) >> 4);
     auto issue_qk = [&](int t, int j) {      // S_t[j&1] = Q_t K_j^T
       const uint32_t qa = q_lo + t * (Q_TILE >> 4), ka = k_lo + (j % STAGES) * (KV_TILE >> 4);
       const uint32_t d = tmem + TM_S + 128 * t + 64 * (j & 1);
       if (leader) {
 #pragma unroll
         for (int k = 0; k < 6; ++k)
-          umma_ss(d, DESC_KMAJ | (uint64_t)(qa + (((k >> 1) * Q_ATOM + (k & 1) * 32) >> 4)),
-                  DESC_KMAJ | (uint64_t)(ka + (((k >> 1) * KV_ATOM + (k & 1) * 32) >> 4)), IDESC_QK, k > 0);
+          umma_ss_lh(d, qa + (((k >> 1) * Q_ATOM + (k & 1) * 32) >> 4), ka + (((k >> 1) * KV_ATOM + (k & 1) * 32) >> 4), HI,
+                     IDESC_QK, k > 0);
         umma_commit(BAR(S_FULL + 2 * t + (j & 1)));
       }
     };
-    auto issue_pv = [&](int t, int j) {      // O_t += P_t V_j
+    auto issue_pv = [&](int t, int j) {      // O_t += P_t V_j   (P_t(j) sits in the first 32 columns of S_t[j&1])
       const uint32_t va = v_lo + (j % STAGES) * (KV_TILE >> 4);
-      const uint32_t d = tmem + TM_O + 96 * t, a = tmem + TM_P + 32 * t;
+      const uint32_t d = tmem + TM_O + 96 * t, a = tmem + TM_S + 128 * t + 64 * (j & 1);
       if (leader) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_ts(d, a + 8 * k, DESC_V | (uint64_t)(va + k * 64), IDESC_PV, (j > 0 || k > 0));
+        for (int k = 0; k < 4; ++k) umma_ts_lh(d, a + 8 * k, va + k * 64, HI, IDESC_PV, (j > 0 || k > 0));
         umma_commit(BAR(O_FULL + t));
       }
     };
@@ -202,20 +257,16 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
       for (int t = 0; t < 2; ++t) {
         const int nk = t ? n_kv1 : n_kv0, nk_other = t ? n_kv0 : n_kv1;
         if (j >= nk) continue;
-        TR(2 + t, j, 0);
         mbar_wait(BAR(P_FULL + t), j & 1);
         tc_fence_after();
-        TR(2 + t, j, 1);
         issue_pv(t, j);
         // V_j is released by its last user: tile 1 if it uses j, else tile 0
         if (leader && (t == 1 || j >= nk_other)) umma_commit(BAR(V_EMPTY + sv));
-        TR(2 + t, j, 2);
-        if (jn < nk) {                 // the softmax has read S_t(j): its buffer can take key tile j+2
+        if (jn < nk) {                 // behind PV(j) on the in-order pipe: the buffer of S_t(j) / P_t(j) is free again
           issue_qk(t, jn);
           if (leader && (t == 1 || jn >= nk_other)) umma_commit(BAR(K_EMPTY + sk));
         }
         __syncwarp();
-        TR(2 + t, j, 3);
       }
     }
   } else if (warp < 4) {
@@ -231,9 +282,9 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     const uint32_t tm_s = tmem + TM_S + 128 * t + lane_base;
     const uint32_t tm_o = tmem + TM_O + 96 * t + lane_base;
-    const uint32_t tm_p = tmem + TM_P + 32 * t + lane_base;
     const int nk = t ? n_kv1 : n_kv0;
-    const bool tracing = P.trace && (int)blockIdx.x == P.trace_cta && r == 0;
+    // key tiles j < n_full lie entirely below the diagonal of this query tile and hold no padding
+    const int n_full = min(first_bad_s, 2 * qt);
 
     if (ROPE && nk > 0) {
       mbar_wait(BAR(Q_FULL + t), 0);
@@ -295,26 +346,27 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
 
     // one key tile: s holds S_t(j) (already in registers); nxt receives S_t(j+1) while the exponentials run
     auto body = [&](float (&s)[64], float (&nxt)[64], int j) {
-      TR(t, j, 0);
-      // ---- tile classification (warp-uniform): fully visible tiles skip the predicate
       const int j0 = j * BN;
-      uint32_t vw[2], mw[2];
-      bool full = (j0 + BN <= qt * BM) && (j0 + BN <= len);
+      const bool partial = (j >= n_full);            // warp-uniform
+      uint32_t vw[2] = {0xffffffffu, 0xffffffffu}, mw[2] = {0xffffffffu, 0xffffffffu};
+      if (partial) {                                  // issue the bit-vector loads before the TMEM traffic
 #pragma unroll
-      for (int w = 0; w < 2; ++w) {
-        const int jw = j0 + 32 * w;
-        const uint32_t in_len = low_mask(len - jw);
-        vw[w] = P.mm.vbits ? (__ldg(P.mm.vbits + (size_t)b * P.mm.bits_pitch + (jw >> 5)) & in_len) : in_len;
-        mw[w] = P.mm.mbits ? (__ldg(P.mm.mbits + (size_t)b * P.mm.bits_pitch + (jw >> 5)) & in_len) : in_len;
-        full = full && (vw[w] == 0xffffffffu);
+        for (int w = 0; w < 2; ++w) {
+          const int jw = j0 + 32 * w;
+          if (P.mm.vbits) vw[w] = __ldg(P.mm.vbits + (size_t)b * P.mm.bits_pitch + (jw >> 5));
+          if (P.mm.mbits) mw[w] = __ldg(P.mm.mbits + (size_t)b * P.mm.bits_pitch + (jw >> 5));
+        }
       }
-      if (!full) {
+      // ---- S_t(j+1) from the other TMEM buffer; its latency hides behind the max and the exponentials
+      if (j + 1 < nk) load_s(nxt, j + 1);
+      if (partial) {
         const int d = row_live ? (i - j0) : -1;             // causal: column c visible iff c <= d
         const int a = row_lo - j0, e = row_hi - j0;         // mutual: a <= c < e
 #pragma unroll
         for (int w = 0; w < 2; ++w) {
-          const uint32_t causal = low_mask(d + 1 - 32 * w) & vw[w];
-          const uint32_t mutual = row_live ? (low_mask(e - 32 * w) & ~low_mask(a - 32 * w) & mw[w]) : 0u;
+          const uint32_t in_len = low_mask(len - j0 - 32 * w);
+          const uint32_t causal = low_mask(d + 1 - 32 * w) & vw[w] & in_len;
+          const uint32_t mutual = row_live ? (low_mask(e - 32 * w) & ~low_mask(a - 32 * w) & mw[w] & in_len) : 0u;
           const uint32_t ok = causal | mutual;
 #pragma unroll
           for (int c = 0; c < 32; ++c)
@@ -327,7 +379,6 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
         mx0 = fmaxf(mx0, s[c]); mx1 = fmaxf(mx1, s[c + 1]); mx2 = fmaxf(mx2, s[c + 2]); mx3 = fmaxf(mx3, s[c + 3]);
       }
       const float m_new = fmaxf(m_used, fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)));
-      TR(t, j, 1);
       // ---- lazy rescale of O (correction merged into the softmax warps; rare after the first tiles)
       if (j == 0) {
         m_used = m_new;
@@ -340,21 +391,9 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
           l *= alpha;
           if (o_waited < j) { mbar_wait(BAR(O_FULL + t), (j - 1) & 1); o_waited = j; }   // PV(j-1) has landed
           tc_fence_after();
-          uint32_t o[32];
-#pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            tmem_ld_x32(tm_o + 32 * c, o);
-            tmem_wait_ld();
-#pragma unroll
-            for (int x = 0; x < 32; ++x) o[x] = __float_as_uint(__uint_as_float(o[x]) * alpha);
-            tmem_st_x32(tm_o + 32 * c, o);
-          }
-          tmem_wait_st();
+          rescale_o(tm_o, alpha);
         }
       }
-      // ---- prefetch S_t(j+1) from the other TMEM buffer; its latency hides behind the exponentials
-      if (j + 1 < nk) load_s(nxt, j + 1);
-      TR(t, j, 2);
       // ---- P = exp2((S - m) * scale*log2e), row sum, bf16 pack
       const float neg_m = (m_used == -INFINITY) ? 0.f : -m_used * P.scale_log2;
       float sum0 = 0.f, sum1 = 0.f;
@@ -367,16 +406,12 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
         pk[x] = pack_bf16x2(p0, p1);
       }
       l += sum0 + sum1;
-      TR(t, j, 3);
-      // ---- P_t has its own TMEM columns, single-buffered: PV(j-1) must have consumed P(j-1)
-      if (j > 0 && o_waited < j) { mbar_wait(BAR(O_FULL + t), (j - 1) & 1); o_waited = j; }
-      tmem_st_x32(tm_p, pk);
-      tmem_wait_st();            // (tcgen05.wait::st; the S prefetch is covered by wait::ld below)
+      // ---- P_t(j) in place over the buffer S_t(j) came from (this thread's own lane; nobody else reads it)
+      tmem_st_x32(tm_s + 64 * (j & 1), pk);
+      tmem_wait_st();
       tc_fence_before();
       mbar_arrive(BAR(P_FULL + t));
-      TR(t, j, 4);
       if (j + 1 < nk) tmem_wait_ld();
-      TR(t, j, 5);
     };
 
     if (nk > 0) {
@@ -507,15 +542,6 @@ extern "C" int aki_mma_attn_fwd(const AkiMmaAttnParams* p, aki_stream_t stream) 
   kp.n_qp = (kp.n_qt + 1) / 2;
   kp.scale = p->scale;
   kp.scale_log2 = p->scale * 1.4426950408889634f;
-  kp.trace = nullptr; kp.trace_cta = -1;
-  // Debug only (tools/fwd_trace.py): AKI_MMA_FWD_TRACE=<cta> dumps clock64 stamps of one CTA and SYNCHRONISES.
-  const char* trace_env = getenv("AKI_MMA_FWD_TRACE");
-  const size_t trace_bytes = 4 * 128 * 8 * sizeof(unsigned long long);
-  if (trace_env) {
-    kp.trace_cta = atoi(trace_env);
-    cudaMalloc(&kp.trace, trace_bytes);
-    cudaMemset(kp.trace, 0, trace_bytes);
-  }
   const long long grid = (long long)kp.n_qp * p->H * p->B;
   AKI_REQUIRE(grid > 0 && grid < (1ll << 31), AKI_ERR_BAD_SHAPE);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -532,21 +558,5 @@ extern "C" int aki_mma_attn_fwd(const AkiMmaAttnParams* p, aki_stream_t stream) 
     attn_fwd_sm100_kernel<true><<<(unsigned)grid, fwd::THREADS, fwd::SMEM_ALLOC, st>>>(mq, mk, mv, kp);
   else
     attn_fwd_sm100_kernel<false><<<(unsigned)grid, fwd::THREADS, fwd::SMEM_ALLOC, st>>>(mq, mk, mv, kp);
-  if (trace_env) {
-    cudaDeviceSynchronize();
-    static unsigned long long host[4 * 128 * 8];
-    cudaMemcpy(host, kp.trace, trace_bytes, cudaMemcpyDeviceToHost);
-    cudaFree(kp.trace);
-    unsigned long long t0 = ~0ull;
-    for (size_t i = 0; i < 4 * 128 * 8; ++i) if (host[i] && host[i] < t0) t0 = host[i];
-    const char* names[4] = {"softmax0", "softmax1", "mma_t0", "mma_t1"};
-    for (int slot = 0; slot < 4; ++slot)
-      for (int j = 0; j < 128; ++j) {
-        if (!host[(slot * 128 + j) * 8]) continue;
-        fprintf(stderr, "TRACE %s j=%d:", names[slot], j);
-        for (int k = 0; k < 6; ++k) fprintf(stderr, " %llu", host[(slot * 128 + j) * 8 + k] ? host[(slot * 128 + j) * 8 + k] - t0 : 0ull);
-        fprintf(stderr, "\n");
-      }
-  }
   return check_launch();
 }
