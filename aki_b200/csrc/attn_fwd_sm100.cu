@@ -13,14 +13,16 @@
 //   warp 1      MMA issuer: S_t[j&1] = Q_t K_j^T (SS, N=64), O_t += P_t V_j (TS, P read from TMEM)
 //   warp 2      TMEM allocator;   warp 3 finds the first key tile that holds padding
 //   warps 4-7   softmax of tile 0 (thread r <-> row r <-> TMEM lane r), warps 8-11 softmax of tile 1
-// S is DOUBLE-BUFFERED per query tile and P_t(j) (bf16 pairs) is written IN PLACE over the first 32 columns of
-// the buffer S_t(j) was read from: QK^T(j+2) is issued right behind PV(j) on the in-order tensor pipe, so the
-// buffer is free again exactly when its P has been consumed and a softmax warp never waits for the tensor pipe
-// (only the rare O rescale and the epilogue wait for PV).  Per key tile a softmax warp runs one straight-line
-// chain: start the TMEM load of S(j+1) -> row max of S(j) (3-input max) -> exp2/sum/pack of S(j) -> P store ->
-// arrive.  Tiles below the diagonal that hold no padding (j < n_full, one comparison) skip the predicate.
+// S is DOUBLE-BUFFERED per query tile (that is why the key tile is 64 wide: 4 x 64 S columns + 2 x 96 O + 2 x 32 P
+// = 512 TMEM columns exactly) and a buffer is handed back to the MMA warp (S_FREE) as soon as its scores sit in
+// registers, i.e. one whole key tile before they are used: QK^T(j+2) is in flight while the softmax still works on
+// tile j, S(j+1) has always landed when it is fetched, and a softmax warp never waits for the tensor pipe (ncu on
+// the previous layout, P written in place over S: 22% of the softmax time was spent waiting for S).  Per key tile
+// a softmax warp runs one straight-line chain: start the TMEM load of S(j+1) -> row max of S(j) (3-input max) ->
+// release the buffer -> exp2/sum/pack of S(j) -> P store -> arrive.  Tiles below the diagonal that hold no padding
+// (j < n_full, one comparison) skip the predicate.
 // The exp2 (MUFU) pipe is the real bound of this head_dim: 64 exp vs 384 tensor cycles per row per key tile.
-// TMEM columns: S0a S0b S1a S1b [0,256) | O0 [256,352) O1 [352,448).
+// TMEM columns: S0a S0b S1a S1b [0,256) | O0 [256,352) O1 [352,448) | P0 [448,480) P1 [480,512).
 // Shared memory: Q 2x24 KB; K ring 4x12 KB; V ring 4x12 KB.  Every tile is 3 SWIZZLE_64B atoms [rows][64 B]
 // (head_dim 96 = 3 x 32), the layout both the TMA boxes and the UMMA descriptors use (tools/umma_probe.cu).
 #include <math.h>
@@ -42,7 +44,7 @@ constexpr int SMEM_K = SMEM_Q + 2 * Q_TILE;
 constexpr int SMEM_V = SMEM_K + STAGES * KV_TILE;
 constexpr int SMEM_TOTAL = SMEM_V + STAGES * KV_TILE;     // 147456
 constexpr int SMEM_ALLOC = SMEM_TOTAL + 1024;             // slack for 1024-byte alignment
-constexpr uint32_t TM_S = 0, TM_O = 256;                  // S: tile t buffer u at 128 t + 64 u (P in place); O: 96 t
+constexpr uint32_t TM_S = 0, TM_O = 256, TM_P = 448;      // S: tile t buffer u at 128 t + 64 u; O: 96 t; P: 32 t
 constexpr int REGS_CTRL = 64, REGS_SOFTMAX = 216;         // CTA pool: 128*64 + 256*216 = 63488 <= 384*168
 constexpr float RESCALE_THRESHOLD = 8.0f;  // log2 units: P may grow to 2^8 before O is rescaled
 }  // namespace fwd
@@ -106,8 +108,8 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   // barrier indices
   constexpr int Q_FULL = 0, Q_READY = 2, K_FULL = 4, K_EMPTY = K_FULL + STAGES, V_FULL = K_EMPTY + STAGES,
-                V_EMPTY = V_FULL + STAGES, S_FULL = V_EMPTY + STAGES /* [t][buf] */, P_FULL = S_FULL + 4,
-                O_FULL = P_FULL + 2, N_BARS = O_FULL + 2;
+                V_EMPTY = V_FULL + STAGES, S_FULL = V_EMPTY + STAGES /* [t][buf] */, S_FREE = S_FULL + 4,
+                P_FULL = S_FREE + 4, O_FULL = P_FULL + 2, N_BARS = O_FULL + 2;
   __shared__ __align__(8) uint64_t bars[N_BARS];
   __shared__ uint32_t tmem_base_s;
   __shared__ int first_bad_s;
@@ -140,7 +142,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
       mbar_init(BAR(K_FULL + i), 1); mbar_init(BAR(K_EMPTY + i), 1);
       mbar_init(BAR(V_FULL + i), 1); mbar_init(BAR(V_EMPTY + i), 1);
     }
-    for (int i = 0; i < 4; ++i) mbar_init(BAR(S_FULL + i), 1);
+    for (int i = 0; i < 4; ++i) { mbar_init(BAR(S_FULL + i), 1); mbar_init(BAR(S_FREE + i), 128); }
     for (int i = 0; i < 2; ++i) { mbar_init(BAR(P_FULL + i), 128); mbar_init(BAR(O_FULL + i), 1); }
     fence_barrier_init();
   }
@@ -229,9 +231,9 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
         umma_commit(BAR(S_FULL + 2 * t + (j & 1)));
       }
     };
-    auto issue_pv = [&](int t, int j) {      // O_t += P_t V_j   (P_t(j) sits in the first 32 columns of S_t[j&1])
+    auto issue_pv = [&](int t, int j) {      // O_t += P_t V_j
       const uint32_t va = v_lo + (j % STAGES) * (KV_TILE >> 4);
-      const uint32_t d = tmem + TM_O + 96 * t, a = tmem + TM_S + 128 * t + 64 * (j & 1);
+      const uint32_t d = tmem + TM_O + 96 * t, a = tmem + TM_P + 32 * t;
       if (leader) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) umma_ts_lh(d, a + 8 * k, va + k * 64, HI, IDESC_PV, (j > 0 || k > 0));
@@ -257,15 +259,19 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
       for (int t = 0; t < 2; ++t) {
         const int nk = t ? n_kv1 : n_kv0, nk_other = t ? n_kv0 : n_kv1;
         if (j >= nk) continue;
+        // QK^T of key tile j+2 first: its buffer was handed back while the softmax was still on tile j-1, so this
+        // MMA is in flight a whole key tile before its scores are fetched
+        if (jn < nk) {
+          mbar_wait(BAR(S_FREE + 2 * t + (j & 1)), (j >> 1) & 1);
+          tc_fence_after();
+          issue_qk(t, jn);
+          if (leader && (t == 1 || jn >= nk_other)) umma_commit(BAR(K_EMPTY + sk));
+        }
         mbar_wait(BAR(P_FULL + t), j & 1);
         tc_fence_after();
         issue_pv(t, j);
         // V_j is released by its last user: tile 1 if it uses j, else tile 0
         if (leader && (t == 1 || j >= nk_other)) umma_commit(BAR(V_EMPTY + sv));
-        if (jn < nk) {                 // behind PV(j) on the in-order pipe: the buffer of S_t(j) / P_t(j) is free again
-          issue_qk(t, jn);
-          if (leader && (t == 1 || jn >= nk_other)) umma_commit(BAR(K_EMPTY + sk));
-        }
         __syncwarp();
       }
     }
@@ -282,6 +288,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     const uint32_t tm_s = tmem + TM_S + 128 * t + lane_base;
     const uint32_t tm_o = tmem + TM_O + 96 * t + lane_base;
+    const uint32_t tm_p = tmem + TM_P + 32 * t + lane_base;
     const int nk = t ? n_kv1 : n_kv0;
     // key tiles j < n_full lie entirely below the diagonal of this query tile and hold no padding
     const int n_full = min(first_bad_s, 2 * qt);
@@ -373,12 +380,15 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
             if (!((ok >> c) & 1u)) s[32 * w + c] = -INFINITY;
         }
       }
-      float mx0 = s[0], mx1 = s[1], mx2 = s[2], mx3 = s[3];
+      float mx[8];
 #pragma unroll
-      for (int c = 4; c < 64; c += 4) {
-        mx0 = fmaxf(mx0, s[c]); mx1 = fmaxf(mx1, s[c + 1]); mx2 = fmaxf(mx2, s[c + 2]); mx3 = fmaxf(mx3, s[c + 3]);
-      }
-      const float m_new = fmaxf(m_used, fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)));
+      for (int c = 0; c < 8; ++c) mx[c] = s[c];
+#pragma unroll
+      for (int c = 8; c < 64; c += 8)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) mx[e] = fmaxf(mx[e], s[c + e]);
+      const float m_new = fmaxf(fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])),
+                                fmaxf(fmaxf(fmaxf(mx[4], mx[5]), fmaxf(mx[6], mx[7])), m_used));
       // ---- lazy rescale of O (correction merged into the softmax warps; rare after the first tiles)
       if (j == 0) {
         m_used = m_new;
@@ -394,6 +404,12 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
           rescale_o(tm_o, alpha);
         }
       }
+      // ---- S_t(j+1) sits in registers: hand its TMEM buffer back for key tile j+3
+      if (j + 1 < nk) {
+        tmem_wait_ld();
+        tc_fence_before();
+        mbar_arrive(BAR(S_FREE + 2 * t + ((j + 1) & 1)));
+      }
       // ---- P = exp2((S - m) * scale*log2e), row sum, bf16 pack
       const float neg_m = (m_used == -INFINITY) ? 0.f : -m_used * P.scale_log2;
       float sum0 = 0.f, sum1 = 0.f;
@@ -406,18 +422,20 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
         pk[x] = pack_bf16x2(p0, p1);
       }
       l += sum0 + sum1;
-      // ---- P_t(j) in place over the buffer S_t(j) came from (this thread's own lane; nobody else reads it)
-      tmem_st_x32(tm_s + 64 * (j & 1), pk);
+      // ---- P_t has its own TMEM columns, single-buffered: PV(j-1), issued a whole key tile ago, has consumed P(j-1)
+      if (j > 0 && o_waited < j) { mbar_wait(BAR(O_FULL + t), (j - 1) & 1); o_waited = j; }
+      tmem_st_x32(tm_p, pk);
       tmem_wait_st();
       tc_fence_before();
       mbar_arrive(BAR(P_FULL + t));
-      if (j + 1 < nk) tmem_wait_ld();
     };
 
     if (nk > 0) {
       float sA[64], sB[64];
       load_s(sA, 0);
       tmem_wait_ld();
+      tc_fence_before();
+      mbar_arrive(BAR(S_FREE + 2 * t + 0));
       for (int j = 0; j < nk; j += 2) {
         body(sA, sB, j);
         if (j + 1 < nk) body(sB, sA, j + 1);
