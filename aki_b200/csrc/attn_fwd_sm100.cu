@@ -8,11 +8,15 @@
 // is evaluated in registers on the few tiles that are not fully visible, and key tiles beyond
 // q_tile_kv_end[b][qt] are never visited.  RoPE is applied to Q in shared memory right after the TMA load.
 //
-// CTA = 2 query tiles x 128 rows of one (batch, head), key tiles of 64; 12 warps:
+// CTA = 2 query tiles x 128 rows of one (batch, head), key tiles of 64; 20 warps:
 //   warp 0      TMA producer (Q once, then K_j / V_j through two 4-deep rings of 12 KB tiles)
 //   warp 1      MMA issuer: S_t[j&1] = Q_t K_j^T (SS, N=64), O_t += P_t V_j (TS, P read from TMEM)
 //   warp 2      TMEM allocator;   warp 3 finds the first key tile that holds padding
-//   warps 4-7   softmax of tile 0 (thread r <-> row r <-> TMEM lane r), warps 8-11 softmax of tile 1
+//   warps 4-19  softmax: warp = (tile t, column half c, lane group g); thread <-> row 32g+lane <-> TMEM lane,
+//               32 of the 64 key columns.  FOUR softmax warps per SM sub-partition: ncu on the 2-warp layout showed
+//               the exp2 pipe 47% busy because one warp's fixed latencies (mbarrier probes, TMEM round trips, max
+//               chain) exceed its own exp2 time, so a second warp could not cover them.  The two column halves of a
+//               row agree on the tile maximum through shared memory and a 64-thread named barrier.
 // S is DOUBLE-BUFFERED per query tile (that is why the key tile is 64 wide: 4 x 64 S columns + 2 x 96 O + 2 x 32 P
 // = 512 TMEM columns exactly) and a buffer is handed back to the MMA warp (S_FREE) as soon as its scores sit in
 // registers, i.e. one whole key tile before they are used: QK^T(j+2) is in flight while the softmax still works on
@@ -38,14 +42,14 @@ constexpr int BM = 128, BN = 64, HD = 96;
 constexpr int Q_ATOM = 128 * 64, Q_TILE = 3 * Q_ATOM;     // 24576
 constexpr int KV_ATOM = BN * 64, KV_TILE = 3 * KV_ATOM;   // 12288
 constexpr int STAGES = 4;
-constexpr int THREADS = 384;
+constexpr int THREADS = 640;
 constexpr int SMEM_Q = 0;
 constexpr int SMEM_K = SMEM_Q + 2 * Q_TILE;
 constexpr int SMEM_V = SMEM_K + STAGES * KV_TILE;
 constexpr int SMEM_TOTAL = SMEM_V + STAGES * KV_TILE;     // 147456
 constexpr int SMEM_ALLOC = SMEM_TOTAL + 1024;             // slack for 1024-byte alignment
 constexpr uint32_t TM_S = 0, TM_O = 256, TM_P = 448;      // S: tile t buffer u at 128 t + 64 u; O: 96 t; P: 32 t
-constexpr int REGS_CTRL = 64, REGS_SOFTMAX = 216;         // CTA pool: 128*64 + 256*216 = 63488 <= 384*168
+constexpr int REGS_CTRL = 56, REGS_SOFTMAX = 104;         // CTA pool (640 x 96 = 61440): 128*56 + 512*104 = 60416
 constexpr float RESCALE_THRESHOLD = 8.0f;  // log2 units: P may grow to 2^8 before O is rescaled
 }  // namespace fwd
 
@@ -58,7 +62,15 @@ struct FwdKernelParams {
   MaskMeta mm;
   int B, H, T, n_qt, n_qp;
   float scale_log2, scale;
+  unsigned long long* trace;  // debug (AKI_MMA_FWD_TRACE=<cta>, tools/fwd_trace.py): clock64 stamps of one CTA
+  int trace_cta;
 };
+
+#ifdef AKI_FWD_TRACE
+#define TR(slot, j, k) do { if (tracing && (j) < 64) P.trace[((slot) * 64 + (j)) * 8 + (k)] = clock64(); } while (0)
+#else
+#define TR(slot, j, k) do { } while (0)
+#endif
 
 __device__ __forceinline__ uint32_t low_mask(int n) {  // n low bits set, n clamped to [0,32]
   return n <= 0 ? 0u : (n >= 32 ? 0xffffffffu : ((1u << n) - 1u));
@@ -84,18 +96,20 @@ __device__ __forceinline__ void umma_ts_lh(uint32_t d_tmem, uint32_t a_tmem, uin
       : "memory");
 }
 
-// Rare path of the online softmax: the running max grew by more than the threshold, O_t (96 fp32 columns of this
-// thread's TMEM lane) is rescaled by alpha.  Kept out of line so that the per-tile loop stays compact.
-__device__ __noinline__ void rescale_o(uint32_t tm_o, float alpha) {
+// Rare path of the online softmax: the running max grew by more than the threshold, this thread's 48 columns of O_t
+// are rescaled by alpha.  Kept out of line so that the per-tile loop stays compact.
+__device__ __noinline__ void rescale_o48(uint32_t tm_o, float alpha) {
   uint32_t o[32];
+  tmem_ld_x32(tm_o, o);
+  tmem_wait_ld();
 #pragma unroll
-  for (int c = 0; c < 3; ++c) {
-    tmem_ld_x32(tm_o + 32 * c, o);
-    tmem_wait_ld();
+  for (int x = 0; x < 32; ++x) o[x] = __float_as_uint(__uint_as_float(o[x]) * alpha);
+  tmem_st_x32(tm_o, o);
+  tmem_ld_x16(tm_o + 32, o);
+  tmem_wait_ld();
 #pragma unroll
-    for (int x = 0; x < 32; ++x) o[x] = __float_as_uint(__uint_as_float(o[x]) * alpha);
-    tmem_st_x32(tm_o + 32 * c, o);
-  }
+  for (int x = 0; x < 16; ++x) o[x] = __float_as_uint(__uint_as_float(o[x]) * alpha);
+  tmem_st_x16(tm_o + 32, o);
   tmem_wait_st();
 }
 
@@ -113,6 +127,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
   __shared__ __align__(8) uint64_t bars[N_BARS];
   __shared__ uint32_t tmem_base_s;
   __shared__ int first_bad_s;
+  __shared__ float xch[2][2][2][128];   // [key-tile parity][query tile][column half][row]: tile maxima, then row sums
   const uint32_t bar0 = smem_u32(bars);
   auto BAR = [&](int i) { return bar0 + 8u * i; };
 
@@ -137,13 +152,13 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
   const int n_max = max(n_kv0, n_kv1);
 
   if (tid == 0) {
-    for (int i = 0; i < 2; ++i) { mbar_init(BAR(Q_FULL + i), 1); mbar_init(BAR(Q_READY + i), 128); }
+    for (int i = 0; i < 2; ++i) { mbar_init(BAR(Q_FULL + i), 1); mbar_init(BAR(Q_READY + i), 256); }
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(BAR(K_FULL + i), 1); mbar_init(BAR(K_EMPTY + i), 1);
       mbar_init(BAR(V_FULL + i), 1); mbar_init(BAR(V_EMPTY + i), 1);
     }
-    for (int i = 0; i < 4; ++i) { mbar_init(BAR(S_FULL + i), 1); mbar_init(BAR(S_FREE + i), 128); }
-    for (int i = 0; i < 2; ++i) { mbar_init(BAR(P_FULL + i), 128); mbar_init(BAR(O_FULL + i), 1); }
+    for (int i = 0; i < 4; ++i) { mbar_init(BAR(S_FULL + i), 1); mbar_init(BAR(S_FREE + i), 256); }
+    for (int i = 0; i < 2; ++i) { mbar_init(BAR(P_FULL + i), 256); mbar_init(BAR(O_FULL + i), 1); }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<512>(smem_u32(&tmem_base_s));
@@ -211,6 +226,9 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
     // issues the tcgen05 instructions.
     setmaxnreg_dec<REGS_CTRL>();
     const bool leader = elect_one();
+#ifdef AKI_FWD_TRACE
+    const bool tracing = P.trace && (int)blockIdx.x == P.trace_cta && leader;
+#endif
     constexpr uint32_t IDESC_QK = umma_idesc_bf16(BM, BN, 0, 0);
     constexpr uint32_t IDESC_PV = umma_idesc_bf16(BM, HD, 0, 1);
     // descriptors differ only in the 14-bit start-address field (units of 16 B) of the low word
@@ -261,15 +279,20 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
         if (j >= nk) continue;
         // QK^T of key tile j+2 first: its buffer was handed back while the softmax was still on tile j-1, so this
         // MMA is in flight a whole key tile before its scores are fetched
+        TR(4 + t, j, 0);
         if (jn < nk) {
           mbar_wait(BAR(S_FREE + 2 * t + (j & 1)), (j >> 1) & 1);
           tc_fence_after();
+          TR(4 + t, j, 1);
           issue_qk(t, jn);
           if (leader && (t == 1 || jn >= nk_other)) umma_commit(BAR(K_EMPTY + sk));
         }
+        TR(4 + t, j, 2);
         mbar_wait(BAR(P_FULL + t), j & 1);
         tc_fence_after();
+        TR(4 + t, j, 3);
         issue_pv(t, j);
+        TR(4 + t, j, 4);
         // V_j is released by its last user: tile 1 if it uses j, else tile 0
         if (leader && (t == 1 || j >= nk_other)) umma_commit(BAR(V_EMPTY + sv));
         __syncwarp();
@@ -280,15 +303,17 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
   } else {
     // ------------------------------------------------------------------ softmax / correction / epilogue
     setmaxnreg_inc<REGS_SOFTMAX>();
-    const int t = (warp - 4) >> 2;
-    const int r = tid - 128 - t * 128;           // row within the tile == TMEM lane
+    const int sw = warp - 4;
+    const int t = sw >> 3, ch = (sw >> 2) & 1, g = sw & 3;   // query tile, column half, lane group (== warp % 4)
+    const int r = 32 * g + (tid & 31);            // row within the tile == TMEM lane
     const int qt = 2 * qp + t;
     const int i = qt * BM + r;                    // query index in mask coordinates
     const int len = meta_len(P.mm, b, P.T);
-    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-    const uint32_t tm_s = tmem + TM_S + 128 * t + lane_base;
-    const uint32_t tm_o = tmem + TM_O + 96 * t + lane_base;
-    const uint32_t tm_p = tmem + TM_P + 32 * t + lane_base;
+    const uint32_t lane_base = (uint32_t)(g * 32) << 16;
+    const uint32_t tm_s = tmem + TM_S + 128 * t + 32 * ch + lane_base;
+    const uint32_t tm_o = tmem + TM_O + 96 * t + 48 * ch + lane_base;
+    const uint32_t tm_p = tmem + TM_P + 32 * t + 16 * ch + lane_base;
+    const int pair_bar = 1 + 4 * t + g;           // named barrier of the two warps that share these rows
     const int nk = t ? n_kv1 : n_kv0;
     // key tiles j < n_full lie entirely below the diagonal of this query tile and hold no padding
     const int n_full = min(first_bad_s, 2 * qt);
@@ -300,7 +325,8 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
         const float* cr = P.rope_cos + (size_t)b * P.rope_stride_b + (size_t)i * 48;
         const float* sr = P.rope_sin + (size_t)b * P.rope_stride_b + (size_t)i * 48;
 #pragma unroll
-        for (int c = 0; c < 6; ++c) {             // 16-byte chunk c pairs with chunk c+6 (d <-> d+48)
+        for (int cc = 0; cc < 3; ++cc) {          // 16-byte chunk c pairs with chunk c+6 (d <-> d+48)
+          const int c = 3 * ch + cc;
           const uint32_t a_lo = qa + (c >> 2) * Q_ATOM + sw64_offset(r, c & 3);
           const uint32_t a_hi = qa + ((c + 6) >> 2) * Q_ATOM + sw64_offset(r, (c + 6) & 3);
           uint4 lo, hi;
@@ -335,65 +361,91 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
       row_hi = P.mm.row_hi[(size_t)b * P.mm.meta_pitch + i];
     }
     float m_used = -INFINITY;  // running max (raw score units) the accumulators are expressed against
-    float l = 0.f;
+    float l = 0.f;             // row sum over this warp's column halves
     int o_waited = 0;          // number of O_FULL phases this thread has already observed
 
-    // Both tiles share the 4 MUFU lanes of each SM sub-partition.  Start tile 1 half an iteration late so that
-    // one warp's exp2 phase overlaps the other's TMEM traffic / max / bookkeeping instead of colliding with it.
-    if (n_kv0 > 0 && n_kv1 > 0) {
-      if (t == 1) named_bar_sync(3, 256);
-    }
-
-    auto load_s = [&](float (&dst)[64], int j) {     // S_t(j): wait for the MMA, start the TMEM load (no wait)
-      mbar_wait(BAR(S_FULL + 2 * t + (j & 1)), (j >> 1) & 1);
-      tc_fence_after();
-      tmem_ld_x32(tm_s + 64 * (j & 1), reinterpret_cast<uint32_t*>(dst));
-      tmem_ld_x32(tm_s + 64 * (j & 1) + 32, reinterpret_cast<uint32_t*>(dst) + 32);
-    };
-
-    // one key tile: s holds S_t(j) (already in registers); nxt receives S_t(j+1) while the exponentials run
-    auto body = [&](float (&s)[64], float (&nxt)[64], int j) {
-      const int j0 = j * BN;
-      const bool partial = (j >= n_full);            // warp-uniform
-      uint32_t vw[2] = {0xffffffffu, 0xffffffffu}, mw[2] = {0xffffffffu, 0xffffffffu};
-      if (partial) {                                  // issue the bit-vector loads before the TMEM traffic
-#pragma unroll
-        for (int w = 0; w < 2; ++w) {
-          const int jw = j0 + 32 * w;
-          if (P.mm.vbits) vw[w] = __ldg(P.mm.vbits + (size_t)b * P.mm.bits_pitch + (jw >> 5));
-          if (P.mm.mbits) mw[w] = __ldg(P.mm.mbits + (size_t)b * P.mm.bits_pitch + (jw >> 5));
-        }
+#ifdef AKI_FWD_TRACE
+    const bool tracing = P.trace && (int)blockIdx.x == P.trace_cta && g == 0 && (tid & 31) == 0;
+    const int slot = 2 * t + ch;
+#endif
+    // All four softmax warps of an SM sub-partition share its 4 MUFU lanes.  Tile 1 starts when tile 0 has finished
+    // its first batch of exponentials, so that from then on one tile's exp2 phase covers the other tile's barrier
+    // probes / TMEM round trips (clock64 trace: started together, the tiles stay in phase and the exp2 phase of
+    // all four warps takes 1240 cycles while the pipe idles for the other 1100 of each key tile).
+    const bool stagger = (n_kv0 > 0 && n_kv1 > 0);
+    if (stagger && t == 1) named_bar_sync(9, 512);
+    bool s_ready = false;                           // result of the early probe of S_FULL for the next key tile
+    for (int j = 0; j < nk; ++j) {
+      TR(slot, j, 0);
+      const int j0 = j * BN + 32 * ch;              // first key column of this thread's half tile
+      const bool partial = (j >= n_full);           // warp-uniform
+      uint32_t vw = 0xffffffffu, mw = 0xffffffffu;
+      if (partial) {                                 // one 32-bit word of each bit-vector covers the half tile
+        if (P.mm.vbits) vw = __ldg(P.mm.vbits + (size_t)b * P.mm.bits_pitch + (j0 >> 5));
+        if (P.mm.mbits) mw = __ldg(P.mm.mbits + (size_t)b * P.mm.bits_pitch + (j0 >> 5));
       }
-      // ---- S_t(j+1) from the other TMEM buffer; its latency hides behind the max and the exponentials
-      if (j + 1 < nk) load_s(nxt, j + 1);
+      // probe "PV(j-1) has consumed P(j-1)" now, use the answer just before the P store
+      const bool o_known = (j == 0) || (o_waited >= j) || mbar_test(BAR(O_FULL + t), (j - 1) & 1);
+      // ---- S_t(j), this half: TMEM -> registers, then the buffer goes back to the MMA warp for key tile j+2
+      float s[32];
+      if (!s_ready) mbar_wait(BAR(S_FULL + 2 * t + (j & 1)), (j >> 1) & 1);
+      tc_fence_after();
+      TR(slot, j, 1);
+      tmem_ld_x32(tm_s + 64 * (j & 1), reinterpret_cast<uint32_t*>(s));
+      tmem_wait_ld();
+      TR(slot, j, 2);
+      tc_fence_before();
+      mbar_arrive(BAR(S_FREE + 2 * t + (j & 1)));
       if (partial) {
         const int d = row_live ? (i - j0) : -1;             // causal: column c visible iff c <= d
         const int a = row_lo - j0, e = row_hi - j0;         // mutual: a <= c < e
+        const uint32_t in_len = low_mask(len - j0);
+        const uint32_t causal = low_mask(d + 1) & vw & in_len;
+        const uint32_t mutual = row_live ? (low_mask(e) & ~low_mask(a) & mw & in_len) : 0u;
+        const uint32_t ok = causal | mutual;
 #pragma unroll
-        for (int w = 0; w < 2; ++w) {
-          const uint32_t in_len = low_mask(len - j0 - 32 * w);
-          const uint32_t causal = low_mask(d + 1 - 32 * w) & vw[w] & in_len;
-          const uint32_t mutual = row_live ? (low_mask(e - 32 * w) & ~low_mask(a - 32 * w) & mw[w] & in_len) : 0u;
-          const uint32_t ok = causal | mutual;
-#pragma unroll
-          for (int c = 0; c < 32; ++c)
-            if (!((ok >> c) & 1u)) s[32 * w + c] = -INFINITY;
-        }
+        for (int c = 0; c < 32; ++c)
+          if (!((ok >> c) & 1u)) s[c] = -INFINITY;
       }
-      float mx[8];
+      // ---- row max of this half; the two column halves of a row agree on the tile maximum through shared memory
+      auto half_max = [&]() {
+        float mx[4] = {s[0], s[1], s[2], s[3]};
 #pragma unroll
-      for (int c = 0; c < 8; ++c) mx[c] = s[c];
+        for (int c = 4; c < 32; c += 4) {
+          mx[0] = fmaxf(mx[0], s[c]); mx[1] = fmaxf(mx[1], s[c + 1]); mx[2] = fmaxf(mx[2], s[c + 2]); mx[3] = fmaxf(mx[3], s[c + 3]);
+        }
+        return fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+      };
+      auto tile_max = [&](float m_half) {
+        xch[j & 1][t][ch][r] = m_half;
+        named_bar_sync(pair_bar, 64);
+        return fmaxf(m_half, xch[j & 1][t][ch ^ 1][r]);
+      };
+      float sum0, sum1;
+      uint32_t pk[16];
+      auto exps = [&]() {   // P = exp2((S - m_used) * scale*log2e), row sum, bf16 pack
+        const float neg_m = (m_used == -INFINITY) ? 0.f : -m_used * P.scale_log2;
+        sum0 = 0.f; sum1 = 0.f;
 #pragma unroll
-      for (int c = 8; c < 64; c += 8)
-#pragma unroll
-        for (int e = 0; e < 8; ++e) mx[e] = fmaxf(mx[e], s[c + e]);
-      const float m_new = fmaxf(fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])),
-                                fmaxf(fmaxf(fmaxf(mx[4], mx[5]), fmaxf(mx[6], mx[7])), m_used));
-      // ---- lazy rescale of O (correction merged into the softmax warps; rare after the first tiles)
+        for (int x = 0; x < 16; ++x) {
+          const float p0 = ex2_approx(fmaf(s[2 * x], P.scale_log2, neg_m));
+          const float p1 = ex2_approx(fmaf(s[2 * x + 1], P.scale_log2, neg_m));
+          sum0 += p0; sum1 += p1;
+          pk[x] = pack_bf16x2(p0, p1);
+        }
+      };
       if (j == 0) {
-        m_used = m_new;
-        if (t == 0 && n_kv1 > 0) asm volatile("bar.arrive 3, 256;" ::: "memory");   // release tile 1 (stagger)
+        m_used = tile_max(half_max());
+        exps();
       } else {
+        // Optimistic: exponentiate against the running max of the EARLIER tiles while this tile's max is still
+        // being reduced and exchanged (the max chain and the pair barrier leave the critical path).  If the tile
+        // max turns out to exceed the reference by more than the threshold (rare after the first tiles), O and l are
+        // rescaled and the exponentials of this tile are redone -- accepted P values never exceed 2^threshold.
+        const float m_half = half_max();
+        exps();
+        const float m_new = fmaxf(m_used, tile_max(m_half));
+        TR(slot, j, 3);
         const bool need = (m_new - m_used) * P.scale_log2 > RESCALE_THRESHOLD || (m_used == -INFINITY && m_new > -INFINITY);
         if (__any_sync(0xffffffffu, need)) {
           const float alpha = (m_used == -INFINITY) ? 0.f : ex2_approx((m_used - m_new) * P.scale_log2);
@@ -401,78 +453,61 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
           l *= alpha;
           if (o_waited < j) { mbar_wait(BAR(O_FULL + t), (j - 1) & 1); o_waited = j; }   // PV(j-1) has landed
           tc_fence_after();
-          rescale_o(tm_o, alpha);
+          rescale_o48(tm_o, alpha);
+          exps();
         }
       }
-      // ---- S_t(j+1) sits in registers: hand its TMEM buffer back for key tile j+3
-      if (j + 1 < nk) {
-        tmem_wait_ld();
-        tc_fence_before();
-        mbar_arrive(BAR(S_FREE + 2 * t + ((j + 1) & 1)));
-      }
-      // ---- P = exp2((S - m) * scale*log2e), row sum, bf16 pack
-      const float neg_m = (m_used == -INFINITY) ? 0.f : -m_used * P.scale_log2;
-      float sum0 = 0.f, sum1 = 0.f;
-      uint32_t pk[32];
-#pragma unroll
-      for (int x = 0; x < 32; ++x) {
-        const float p0 = ex2_approx(fmaf(s[2 * x], P.scale_log2, neg_m));
-        const float p1 = ex2_approx(fmaf(s[2 * x + 1], P.scale_log2, neg_m));
-        sum0 += p0; sum1 += p1;
-        pk[x] = pack_bf16x2(p0, p1);
-      }
       l += sum0 + sum1;
+      if (stagger && t == 0 && j == 0) asm volatile("bar.arrive 9, 512;" ::: "memory");   // release tile 1
+      TR(slot, j, 4);
       // ---- P_t has its own TMEM columns, single-buffered: PV(j-1), issued a whole key tile ago, has consumed P(j-1)
-      if (j > 0 && o_waited < j) { mbar_wait(BAR(O_FULL + t), (j - 1) & 1); o_waited = j; }
-      tmem_st_x32(tm_p, pk);
+      if (o_waited < j) {
+        if (!o_known) mbar_wait(BAR(O_FULL + t), (j - 1) & 1);
+        o_waited = j;
+      }
+      TR(slot, j, 5);
+      tmem_st_x16(tm_p, pk);
+      // probe S_FULL of the next key tile while the P store drains
+      s_ready = (j + 1 < nk) && mbar_test(BAR(S_FULL + 2 * t + ((j + 1) & 1)), ((j + 1) >> 1) & 1);
       tmem_wait_st();
       tc_fence_before();
       mbar_arrive(BAR(P_FULL + t));
-    };
-
-    if (nk > 0) {
-      float sA[64], sB[64];
-      load_s(sA, 0);
-      tmem_wait_ld();
-      tc_fence_before();
-      mbar_arrive(BAR(S_FREE + 2 * t + 0));
-      for (int j = 0; j < nk; j += 2) {
-        body(sA, sB, j);
-        if (j + 1 < nk) body(sB, sA, j + 1);
-      }
+      TR(slot, j, 6);
     }
 
     // ---- epilogue: O / l -> bf16 -> global; LSE
     if (qt < P.n_qt) {
       float inv_l = 0.f;
       if (nk > 0) {
+        // total row sum = sum of the two halves
+        xch[nk & 1][t][ch][r] = l;
+        named_bar_sync(pair_bar, 64);
+        l += xch[nk & 1][t][ch ^ 1][r];
         mbar_wait(BAR(O_FULL + t), (nk - 1) & 1);
         tc_fence_after();
         inv_l = (row_live && l > 0.f) ? 1.f / l : 0.f;  // batch-padding rows: zeros
       }
       // tcgen05.ld is warp-collective (.sync.aligned): load unconditionally, predicate only the global stores
       const bool store_row = (i < P.T);
-      __nv_bfloat16* orow = P.o.row(b, store_row ? i : 0, h);
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        uint32_t o[32];
-        if (nk > 0) {
-          tmem_ld_x32(tm_o + 32 * c, o);
-          tmem_wait_ld();
-        }
-#pragma unroll
-        for (int x = 0; x < 4; ++x) {
-          uint4 u;
-          uint32_t* w = reinterpret_cast<uint32_t*>(&u);
-#pragma unroll
-          for (int e = 0; e < 4; ++e)
-            w[e] = (inv_l > 0.f) ? pack_bf16x2(__uint_as_float(o[8 * x + 2 * e]) * inv_l,
-                                                 __uint_as_float(o[8 * x + 2 * e + 1]) * inv_l)
-                                 : 0u;
-          if (store_row) *reinterpret_cast<uint4*>(orow + 32 * c + 8 * x) = u;
-        }
+      __nv_bfloat16* orow = P.o.row(b, store_row ? i : 0, h) + 48 * ch;
+      uint32_t o[48];
+      if (nk > 0) {
+        tmem_ld_x32(tm_o, o);
+        tmem_ld_x16(tm_o + 32, o + 32);
+        tmem_wait_ld();
       }
-      if (P.lse && store_row)
+#pragma unroll
+      for (int x = 0; x < 6; ++x) {
+        uint4 u;
+        uint32_t* w = reinterpret_cast<uint32_t*>(&u);
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          w[e] = (inv_l > 0.f) ? pack_bf16x2(__uint_as_float(o[8 * x + 2 * e]) * inv_l,
+                                               __uint_as_float(o[8 * x + 2 * e + 1]) * inv_l)
+                               : 0u;
+        if (store_row) *reinterpret_cast<uint4*>(orow + 8 * x) = u;
+      }
+      if (P.lse && store_row && ch == 0)
         P.lse[((size_t)b * P.H + h) * P.T + i] = (inv_l > 0.f) ? (m_used * P.scale + __logf(l)) : INFINITY;
     }
   }
@@ -560,6 +595,17 @@ extern "C" int aki_mma_attn_fwd(const AkiMmaAttnParams* p, aki_stream_t stream) 
   kp.n_qp = (kp.n_qt + 1) / 2;
   kp.scale = p->scale;
   kp.scale_log2 = p->scale * 1.4426950408889634f;
+  kp.trace = nullptr; kp.trace_cta = -1;
+#ifdef AKI_FWD_TRACE
+  // Debug build only (make TRACE=1; tools/fwd_trace.py): dumps clock64 stamps of one CTA and SYNCHRONISES.
+  const char* trace_env = getenv("AKI_MMA_FWD_TRACE");
+  const size_t trace_bytes = 6 * 64 * 8 * sizeof(unsigned long long);
+  if (trace_env) {
+    kp.trace_cta = atoi(trace_env);
+    cudaMalloc(&kp.trace, trace_bytes);
+    cudaMemset(kp.trace, 0, trace_bytes);
+  }
+#endif
   const long long grid = (long long)kp.n_qp * p->H * p->B;
   AKI_REQUIRE(grid > 0 && grid < (1ll << 31), AKI_ERR_BAD_SHAPE);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -576,5 +622,23 @@ extern "C" int aki_mma_attn_fwd(const AkiMmaAttnParams* p, aki_stream_t stream) 
     attn_fwd_sm100_kernel<true><<<(unsigned)grid, fwd::THREADS, fwd::SMEM_ALLOC, st>>>(mq, mk, mv, kp);
   else
     attn_fwd_sm100_kernel<false><<<(unsigned)grid, fwd::THREADS, fwd::SMEM_ALLOC, st>>>(mq, mk, mv, kp);
+#ifdef AKI_FWD_TRACE
+  if (trace_env) {
+    cudaDeviceSynchronize();
+    static unsigned long long host[6 * 64 * 8];
+    cudaMemcpy(host, kp.trace, trace_bytes, cudaMemcpyDeviceToHost);
+    cudaFree(kp.trace);
+    unsigned long long t0 = ~0ull;
+    for (size_t i = 0; i < 6 * 64 * 8; ++i) if (host[i] && host[i] < t0) t0 = host[i];
+    const char* names[6] = {"sm_t0c0", "sm_t0c1", "sm_t1c0", "sm_t1c1", "mma_t0", "mma_t1"};
+    for (int slot = 0; slot < 6; ++slot)
+      for (int j = 0; j < 64; ++j) {
+        if (!host[(slot * 64 + j) * 8]) continue;
+        fprintf(stderr, "TRACE %s j=%d:", names[slot], j);
+        for (int k = 0; k < 7; ++k) fprintf(stderr, " %llu", host[(slot * 64 + j) * 8 + k] ? host[(slot * 64 + j) * 8 + k] - t0 : 0ull);
+        fprintf(stderr, "\n");
+      }
+  }
+#endif
   return check_launch();
 }

@@ -43,6 +43,19 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// Non-blocking probe: true iff the phase with this parity has completed.  Issued early, its ~100-cycle round trip
+// overlaps with independent work; the caller falls back to mbar_wait only when it returns false.
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, P;\n\t}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 // Spin on try_wait (a hardware-suspended wait with a time limit).  A protocol bug would otherwise hang the GPU
 // until the watchdog of the box kills the job; trap after ~seconds instead so it surfaces as a CUDA error.
 #ifndef AKI_MBAR_SPIN_LIMIT
