@@ -5,11 +5,15 @@
 // on a (B,32,T,T) tensor).  One CTA owns one 128-key tile of one (batch, head) and walks exactly the query tiles
 // that can see it (kv_tile_q_mask: with MMA that set is the image-row tiles before the diagonal plus everything
 // from the diagonal on), with everything transposed so that keys sit on TMEM lanes:
-//     S^T  = K Q_i^T  - LSE_i/scale       (SS)        P^T = exp2(S^T * scale*log2e)   -> TMEM (bf16, own columns)
-//     dP^T = V dO_i^T - delta_i           (SS)        dS^T = P^T o dP^T               -> smem (bf16)
+//     S^T  = K Q_i^T  - LSE_i/scale       (SS)        P^T = exp2(S^T * scale*log2e)   -> TMEM (bf16, in place over S^T)
+//     dP^T = V dO_i^T - delta_i           (SS)        dS^T = P^T o dP^T               -> TMEM (bf16) and smem (bf16)
 //     dV  += P^T dO_i                     (TS)
-//     dQ_i = dS K                         (SS, A MN-major = the dS^T buffer, B MN-major = K)
-//     dK  += dS^T Q_i                     (SS, A K-major = dS^T, B MN-major = Q_i)       (x scale in the epilogue)
+//     dQ_i = dS K                         (SS, A MN-major = the dS^T smem buffer, B MN-major = K)
+//     dK  += dS^T Q_i                     (TS, A = dS^T in TMEM, B MN-major = Q_i)       (x scale in the epilogue)
+// The kernel is bound by SHARED-MEMORY bandwidth, not by the tensor pipe: an SS MMA with M = N = 128 reads 8 KB of
+// operands per 64-cycle k-step = the full 128 B/clk of the SM, and the TMA fills, the dS^T stores and the dQ
+// staging share the same port (ncu: tensor pipe 48% active, the MMA warp stalled on a full issue queue).  Hence
+// every A operand that can live in TMEM does: P^T (dV) and dS^T (dK).
 // The per-query statistics are folded INTO the two score MMAs: a 7th k-step multiplies a constant "ones" operand
 // [1,1,1,0..] on the key side with a [128][8] bf16 row-statistics operand on the query side that holds -LSE/scale
 // (resp. -delta) split into three bf16 terms (hi + mid + lo: 2^-24 relative).  In this transposed layout LSE and
@@ -26,7 +30,8 @@
 // visible read them) | 4-11 compute (thread <-> key row r; the two warpgroups split the 128 query columns of a
 // tile in halves) | 12-15 dQ drain.  Tensor-pipe order per query tile: dV(i) S(i+1) dQ(i) dK(i) dP(i+1) -- the dQ
 // drain overlaps dK, the exponentials of tile i+1 overlap dQ/dK/dP.
-// TMEM columns: S^T [0,128)  dP^T/dQ [128,256)  dV [256,352)  dK [352,448)  P^T (bf16 pairs) [448,512).
+// TMEM columns: S^T / P^T [0,128) (each half writes its P^T over the first 32 columns of the 64 S^T columns it
+// read)  dP^T/dQ [128,256)  dV [256,352)  dK [352,448)  dS^T (bf16 pairs) [448,512).
 // Shared memory: K, V 24 KB each (resident), Q ring 2x24 KB, dO ring 2x24 KB, dS^T 32 KB, dQ staging 2x16 KB,
 // row-statistics operands 2x2 KB + 2x2 KB, ones/zero core matrices, mask statistics, query-tile list.
 #include <math.h>
@@ -60,7 +65,7 @@ constexpr int SMEM_QLIST = SMEM_STATS + 2 * STATS_STAGE_INTS * 4 + 32;   // uint
 constexpr int SMEM_TOTAL = SMEM_QLIST + MAX_TILES * 2;
 constexpr int SMEM_ALLOC = SMEM_TOTAL + 1024;
 static_assert(SMEM_ALLOC + 256 <= 232448, "shared memory budget");
-constexpr uint32_t TM_S = 0, TM_DP = 128, TM_DV = 256, TM_DK = 352, TM_P = 448;
+constexpr uint32_t TM_S = 0, TM_DP = 128, TM_DV = 256, TM_DK = 352, TM_DS = 448;
 constexpr int REGS_CTRL = 64, REGS_COMPUTE = 168, REGS_DRAIN = 112;   // 128*64 + 256*168 + 128*112 = 65536
 }  // namespace bwd
 
@@ -213,7 +218,7 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
     setmaxnreg_dec<REGS_CTRL>();
     if (elect_one() && n_q > 0) {
       constexpr uint32_t IDESC_SS_KK = umma_idesc_bf16(128, 128, 0, 0);       // S^T, dP^T
-      constexpr uint32_t IDESC_N96_BMN = umma_idesc_bf16(128, 96, 0, 1);      // dV (TS), dK (SS)
+      constexpr uint32_t IDESC_N96_BMN = umma_idesc_bf16(128, 96, 0, 1);      // dV, dK (TS)
       constexpr uint32_t IDESC_N96_AMN_BMN = umma_idesc_bf16(128, 96, 1, 1);  // dQ
       const uint32_t sK = smem_base + SMEM_K, sV = smem_base + SMEM_V, sDS = smem_base + SMEM_DS;
       // descriptors differ only in the 14-bit start-address field: build the constant parts once
@@ -260,10 +265,10 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
         mbar_wait(BAR(P_READY), it & 1);
         tc_fence_after();
 #pragma unroll
-        for (int k = 0; k < 8; ++k)
-          umma_ts(tmem + TM_DV, tmem + TM_P + 8 * k, mnmajor(sDO, k), IDESC_N96_BMN, (it > 0 || k > 0));
+        for (int k = 0; k < 8; ++k)   // P^T of query columns [16k,16k+16): half k/4 keeps it at S^T + 64 (k/4) + 8 (k%4)
+          umma_ts(tmem + TM_DV, tmem + TM_S + 64 * (k >> 2) + 8 * (k & 3), mnmajor(sDO, k), IDESC_N96_BMN, (it > 0 || k > 0));
         umma_commit(BAR(DO_EMPTY + it % DO_STAGES));
-        // S^T of the next query tile (the S region is free once P^T(it) has been written)
+        // S^T of the next query tile: behind dV(it) on the in-order pipe, so P^T(it) has been consumed
         if (it + 1 < n_q) {
           mbar_wait(BAR(Q_FULL + (it + 1) % Q_STAGES), ((it + 1) / Q_STAGES) & 1);
           tc_fence_after();
@@ -279,7 +284,7 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
         umma_commit(BAR(DQ_FULL));
 #pragma unroll
         for (int k = 0; k < 8; ++k)
-          umma_ss(tmem + TM_DK, kmajor(sDS, k), mnmajor(sQ, k), IDESC_N96_BMN, (it > 0 || k > 0));
+          umma_ts(tmem + TM_DK, tmem + TM_DS + 8 * k, mnmajor(sQ, k), IDESC_N96_BMN, (it > 0 || k > 0));
         umma_commit(BAR(Q_EMPTY + it % Q_STAGES));
         // dP^T of the next query tile overwrites the dQ region: wait until it has been drained
         if (it + 1 < n_q) {
@@ -381,7 +386,7 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
       uint32_t pk[32];
 #pragma unroll
       for (int x = 0; x < 32; ++x) pk[x] = pack_bf16x2(p[2 * x], p[2 * x + 1]);
-      tmem_st_x32(tmem + TM_P + lane_base + 32 * hq, pk);   // own columns: the other half may still be reading S^T
+      tmem_st_x32(tmem + TM_S + lane_base + 64 * hq, pk);   // in place: only this thread reads these columns
       tmem_wait_st();
       tc_fence_before();
       mbar_arrive(BAR(P_READY));
@@ -396,20 +401,23 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
       tmem_ld_x32(tmem + TM_DP + lane_base + 64 * hq + 32, draw + 32);
       tmem_wait_ld();
       const uint32_t ds_base = smem_base + SMEM_DS;
+      uint32_t dsw[32];
 #pragma unroll
       for (int c8 = 0; c8 < 8; ++c8) {   // 8 query columns -> one 16-byte chunk of the dS^T row
-        uint32_t w[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const int c = 8 * c8 + 2 * e;
           float d0, d1;
           f32x2_mul(d0, d1, p[c], p[c + 1], __uint_as_float(draw[c]), __uint_as_float(draw[c + 1]));
-          w[e] = pack_bf16x2(d0, d1);
+          dsw[4 * c8 + e] = pack_bf16x2(d0, d1);
         }
         const int col = 64 * hq + 8 * c8;          // query column of this chunk
         const uint32_t addr = ds_base + (col >> 5) * ATOM_BYTES + sw64_offset(r, (col & 31) >> 3);
-        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]));
+        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(dsw[4 * c8]), "r"(dsw[4 * c8 + 1]),
+                     "r"(dsw[4 * c8 + 2]), "r"(dsw[4 * c8 + 3]));
       }
+      tmem_st_x32(tmem + TM_DS + lane_base + 32 * hq, dsw);   // A operand of dK (TS); the smem copy feeds dQ
+      tmem_wait_st();
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(BAR(DS_READY));
