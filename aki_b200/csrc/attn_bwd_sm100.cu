@@ -119,11 +119,12 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
 
   if (tid == 0) {
     mbar_init(BAR(KV_FULL), 1);
-    for (int i = 0; i < Q_STAGES; ++i) { mbar_init(BAR(Q_FULL + i), 1); mbar_init(BAR(Q_EMPTY + i), 1); }
-    for (int i = 0; i < DO_STAGES; ++i) { mbar_init(BAR(DO_FULL + i), 1); mbar_init(BAR(DO_EMPTY + i), 1); }
+    // every Q / dO stage is read by both MMA warps: two commits free it
+    for (int i = 0; i < Q_STAGES; ++i) { mbar_init(BAR(Q_FULL + i), 1); mbar_init(BAR(Q_EMPTY + i), 2); }
+    for (int i = 0; i < DO_STAGES; ++i) { mbar_init(BAR(DO_FULL + i), 1); mbar_init(BAR(DO_EMPTY + i), 2); }
     mbar_init(BAR(S_FULL), 1); mbar_init(BAR(P_READY), 256); mbar_init(BAR(DP_FULL), 1);
     mbar_init(BAR(DS_READY), 256); mbar_init(BAR(DQ_FULL), 1); mbar_init(BAR(DQ_DRAINED), 128);
-    mbar_init(BAR(ALL_DONE), 1);
+    mbar_init(BAR(ALL_DONE), 2);
     for (int i = 0; i < 2; ++i) { mbar_init(BAR(ST_FULL + i), 1); mbar_init(BAR(ST_EMPTY + i), 256); }
     fence_barrier_init();
   }
@@ -213,8 +214,15 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
         tma_load_4d(smem_base + SMEM_DOAUG + sd * AUG_BYTES, &map_doaug, BAR(DO_FULL + sd), 0, i0, h, b);
       }
     }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
+  } else if (warp == 1 || warp == 2) {
+    // ------------------------------------------------------------------ MMA issuers
+    // TWO issuing warps: an M=128, K=16 tcgen05.mma costs ~64-70 cycles whatever N is when a single thread
+    // streams them (tools/mma_mix_bench.cu: this step takes 2337 cycles from one thread, ~1650-2050 from two), so
+    // the step is split into two independent in-order streams that the barrier protocol already separates:
+    //   warp 1 (A): dV(i) += P^T dO_i ; S^T(i+1)           warp 2 (B): dQ_i ; dK += dS^T Q_i ; dP^T(i+1)
+    // TMEM hazards stay inside one stream: S^T(i+1) overwrites P^T(i) behind dV(i) (A); dQ_i overwrites dP^T(i) after
+    // DS_READY, dP^T(i+1) overwrites dQ_i after DQ_DRAINED and sits behind dK(i), so dS^T(i) is consumed before the
+    // compute warps can see DP_FULL(i+1) (B).  Q / dO stages are freed by one commit from each stream.
     setmaxnreg_dec<REGS_CTRL>();
     if (elect_one() && n_q > 0) {
       constexpr uint32_t IDESC_SS_KK = umma_idesc_bf16(128, 128, 0, 0);       // S^T, dP^T
@@ -235,70 +243,77 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
       auto mnmajor = [&](uint32_t base, int k) {  // 16-row K step k of a tile read as MN-major
         return DESC_MNMAJ | (uint64_t)(((base + k * 1024) >> 4) & 0x3FFFu);
       };
-      auto issue_s = [&](int it) {
-        const uint32_t sQ = smem_base + SMEM_Q + (it % Q_STAGES) * TILE_BYTES;
-        const uint32_t sA = smem_base + SMEM_QAUG + (it % Q_STAGES) * AUG_BYTES;
+      if (warp == 1) {
+        // ---------------- stream A
+        auto issue_s = [&](int it) {
+          const uint32_t sQ = smem_base + SMEM_Q + (it % Q_STAGES) * TILE_BYTES;
+          const uint32_t sA = smem_base + SMEM_QAUG + (it % Q_STAGES) * AUG_BYTES;
 #pragma unroll
-        for (int k = 0; k < 6; ++k) umma_ss(tmem + TM_S, kmajor(sK, k), kmajor(sQ, k), IDESC_SS_KK, k > 0);
-        umma_ss(tmem + TM_S, DESC_ONES, DESC_AUG | (uint64_t)((sA >> 4) & 0x3FFFu), IDESC_SS_KK, 1);
-      };
-      auto issue_dp = [&](int it) {
-        const uint32_t sDO = smem_base + SMEM_DO + (it % DO_STAGES) * TILE_BYTES;
-        const uint32_t sA = smem_base + SMEM_DOAUG + (it % DO_STAGES) * AUG_BYTES;
-#pragma unroll
-        for (int k = 0; k < 6; ++k) umma_ss(tmem + TM_DP, kmajor(sV, k), kmajor(sDO, k), IDESC_SS_KK, k > 0);
-        umma_ss(tmem + TM_DP, DESC_ONES, DESC_AUG | (uint64_t)((sA >> 4) & 0x3FFFu), IDESC_SS_KK, 1);
-      };
-      mbar_wait(BAR(KV_FULL), 0);
-      mbar_wait(BAR(Q_FULL + 0), 0);
-      tc_fence_after();
-      issue_s(0);
-      umma_commit(BAR(S_FULL));
-      mbar_wait(BAR(DO_FULL + 0), 0);
-      tc_fence_after();
-      issue_dp(0);
-      umma_commit(BAR(DP_FULL));
-      for (int it = 0; it < n_q; ++it) {
-        const uint32_t sQ = smem_base + SMEM_Q + (it % Q_STAGES) * TILE_BYTES;
-        const uint32_t sDO = smem_base + SMEM_DO + (it % DO_STAGES) * TILE_BYTES;
-        // dV += P^T dO_it
-        mbar_wait(BAR(P_READY), it & 1);
-        tc_fence_after();
-#pragma unroll
-        for (int k = 0; k < 8; ++k)   // P^T of query columns [16k,16k+16): half k/4 keeps it at S^T + 64 (k/4) + 8 (k%4)
-          umma_ts(tmem + TM_DV, tmem + TM_S + 64 * (k >> 2) + 8 * (k & 3), mnmajor(sDO, k), IDESC_N96_BMN, (it > 0 || k > 0));
-        umma_commit(BAR(DO_EMPTY + it % DO_STAGES));
-        // S^T of the next query tile: behind dV(it) on the in-order pipe, so P^T(it) has been consumed
-        if (it + 1 < n_q) {
-          mbar_wait(BAR(Q_FULL + (it + 1) % Q_STAGES), ((it + 1) / Q_STAGES) & 1);
-          tc_fence_after();
-          issue_s(it + 1);
+          for (int k = 0; k < 6; ++k) umma_ss(tmem + TM_S, kmajor(sK, k), kmajor(sQ, k), IDESC_SS_KK, k > 0);
+          umma_ss(tmem + TM_S, DESC_ONES, DESC_AUG | (uint64_t)((sA >> 4) & 0x3FFFu), IDESC_SS_KK, 1);
           umma_commit(BAR(S_FULL));
-        }
-        // dQ_it = dS K first (its drain then overlaps dK), dK += dS^T Q_it
-        mbar_wait(BAR(DS_READY), it & 1);
+          umma_commit(BAR(Q_EMPTY + it % Q_STAGES));   // this stream's half of the release (the other: dK on B)
+        };
+        mbar_wait(BAR(KV_FULL), 0);
+        mbar_wait(BAR(Q_FULL + 0), 0);
         tc_fence_after();
-#pragma unroll
-        for (int k = 0; k < 8; ++k)
-          umma_ss(tmem + TM_DP, mnmajor(sDS, k), mnmajor(sK, k), IDESC_N96_AMN_BMN, k > 0);
-        umma_commit(BAR(DQ_FULL));
-#pragma unroll
-        for (int k = 0; k < 8; ++k)
-          umma_ts(tmem + TM_DK, tmem + TM_DS + 8 * k, mnmajor(sQ, k), IDESC_N96_BMN, (it > 0 || k > 0));
-        umma_commit(BAR(Q_EMPTY + it % Q_STAGES));
-        // dP^T of the next query tile overwrites the dQ region: wait until it has been drained
-        if (it + 1 < n_q) {
-          mbar_wait(BAR(DO_FULL + (it + 1) % DO_STAGES), ((it + 1) / DO_STAGES) & 1);
-          mbar_wait(BAR(DQ_DRAINED), it & 1);
+        issue_s(0);
+        for (int it = 0; it < n_q; ++it) {
+          const uint32_t sDO = smem_base + SMEM_DO + (it % DO_STAGES) * TILE_BYTES;
+          // dV += P^T dO_it
+          mbar_wait(BAR(P_READY), it & 1);
           tc_fence_after();
-          issue_dp(it + 1);
-          umma_commit(BAR(DP_FULL));
+#pragma unroll
+          for (int k = 0; k < 8; ++k)   // P^T of query columns [16k,16k+16): half k/4 keeps it at S^T + 64 (k/4) + 8 (k%4)
+            umma_ts(tmem + TM_DV, tmem + TM_S + 64 * (k >> 2) + 8 * (k & 3), mnmajor(sDO, k), IDESC_N96_BMN, (it > 0 || k > 0));
+          umma_commit(BAR(DO_EMPTY + it % DO_STAGES));
+          // S^T of the next query tile: behind dV(it) on this stream, so P^T(it) has been consumed
+          if (it + 1 < n_q) {
+            mbar_wait(BAR(Q_FULL + (it + 1) % Q_STAGES), ((it + 1) / Q_STAGES) & 1);
+            tc_fence_after();
+            issue_s(it + 1);
+          }
         }
+        umma_commit(BAR(ALL_DONE));
+      } else {
+        // ---------------- stream B
+        auto issue_dp = [&](int it) {
+          const uint32_t sDO = smem_base + SMEM_DO + (it % DO_STAGES) * TILE_BYTES;
+          const uint32_t sA = smem_base + SMEM_DOAUG + (it % DO_STAGES) * AUG_BYTES;
+#pragma unroll
+          for (int k = 0; k < 6; ++k) umma_ss(tmem + TM_DP, kmajor(sV, k), kmajor(sDO, k), IDESC_SS_KK, k > 0);
+          umma_ss(tmem + TM_DP, DESC_ONES, DESC_AUG | (uint64_t)((sA >> 4) & 0x3FFFu), IDESC_SS_KK, 1);
+          umma_commit(BAR(DP_FULL));
+          umma_commit(BAR(DO_EMPTY + it % DO_STAGES));
+        };
+        mbar_wait(BAR(KV_FULL), 0);
+        mbar_wait(BAR(DO_FULL + 0), 0);
+        tc_fence_after();
+        issue_dp(0);
+        for (int it = 0; it < n_q; ++it) {
+          const uint32_t sQ = smem_base + SMEM_Q + (it % Q_STAGES) * TILE_BYTES;
+          // dQ_it = dS K first (its drain then overlaps dK), dK += dS^T Q_it
+          mbar_wait(BAR(DS_READY), it & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            umma_ss(tmem + TM_DP, mnmajor(sDS, k), mnmajor(sK, k), IDESC_N96_AMN_BMN, k > 0);
+          umma_commit(BAR(DQ_FULL));
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            umma_ts(tmem + TM_DK, tmem + TM_DS + 8 * k, mnmajor(sQ, k), IDESC_N96_BMN, (it > 0 || k > 0));
+          umma_commit(BAR(Q_EMPTY + it % Q_STAGES));
+          // dP^T of the next query tile overwrites the dQ region: wait until it has been drained
+          if (it + 1 < n_q) {
+            mbar_wait(BAR(DO_FULL + (it + 1) % DO_STAGES), ((it + 1) / DO_STAGES) & 1);
+            mbar_wait(BAR(DQ_DRAINED), it & 1);
+            tc_fence_after();
+            issue_dp(it + 1);
+          }
+        }
+        umma_commit(BAR(ALL_DONE));
       }
-      umma_commit(BAR(ALL_DONE));
     }
-  } else if (warp == 2) {
-    setmaxnreg_dec<REGS_CTRL>();
   } else if (warp == 3) {
     // ------------------------------------------------------------------ mask statistics of each query tile
     setmaxnreg_dec<REGS_CTRL>();

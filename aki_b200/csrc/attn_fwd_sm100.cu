@@ -10,8 +10,8 @@
 //
 // CTA = 2 query tiles x 128 rows of one (batch, head), key tiles of 64; 20 warps:
 //   warp 0      TMA producer (Q once, then K_j / V_j through two 4-deep rings of 12 KB tiles)
-//   warp 1      MMA issuer: S_t[j&1] = Q_t K_j^T (SS, N=64), O_t += P_t V_j (TS, P read from TMEM)
-//   warp 2      TMEM allocator;   warp 3 finds the first key tile that holds padding
+//   warp 1 / 3  MMA issuers of query tile 0 / 1: S_t[j&1] = Q_t K_j^T (SS, N=64), O_t += P_t V_j (TS, P read from TMEM)
+//   warp 2      TMEM allocator;   warp 3 first finds the first key tile that holds padding
 //   warps 4-19  softmax: warp = (tile t, column half c, lane group g); thread <-> row 32g+lane <-> TMEM lane,
 //               32 of the 64 key columns.  FOUR softmax warps per SM sub-partition: ncu on the 2-warp layout showed
 //               the exp2 pipe 47% busy because one warp's fixed latencies (mbarrier probes, TMEM round trips, max
@@ -154,8 +154,8 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
   if (tid == 0) {
     for (int i = 0; i < 2; ++i) { mbar_init(BAR(Q_FULL + i), 1); mbar_init(BAR(Q_READY + i), 256); }
     for (int i = 0; i < STAGES; ++i) {
-      mbar_init(BAR(K_FULL + i), 1); mbar_init(BAR(K_EMPTY + i), 1);
-      mbar_init(BAR(V_FULL + i), 1); mbar_init(BAR(V_EMPTY + i), 1);
+      mbar_init(BAR(K_FULL + i), 1); mbar_init(BAR(K_EMPTY + i), 2);   // one release per MMA warp (query tile)
+      mbar_init(BAR(V_FULL + i), 1); mbar_init(BAR(V_EMPTY + i), 2);
     }
     for (int i = 0; i < 4; ++i) { mbar_init(BAR(S_FULL + i), 1); mbar_init(BAR(S_FREE + i), 256); }
     for (int i = 0; i < 2; ++i) { mbar_init(BAR(P_FULL + i), 256); mbar_init(BAR(O_FULL + i), 1); }
@@ -220,11 +220,16 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
         if (j + 2 < n_max) load_k(j + 2);
       }
     }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    // The whole warp runs the loop so that addresses / descriptors stay in uniform registers; one elected lane
-    // issues the tcgen05 instructions.
+  } else if (warp == 1 || warp == 3) {
+    // ------------------------------------------------------------------ MMA issuers: warp 1 -> query tile 0, warp 3 -> tile 1
+    // One issuing warp per query tile: a single thread streams M=128,K=16 MMAs at ~64-80 cycles each whatever N is
+    // (tools/mma_mix_bench.cu: this step costs 1267 cycles from one thread, 925 from two).  The whole warp runs the
+    // loop so that addresses / descriptors stay in uniform registers; one elected lane issues.  Every K / V stage is
+    // released by one arrival from each warp: a commit behind the MMA that read it, or a plain arrive when this
+    // tile does not visit that key tile.
     setmaxnreg_dec<REGS_CTRL>();
+    const int t = (warp == 3) ? 1 : 0;
+    const int nk = t ? n_kv1 : n_kv0;
     const bool leader = elect_one();
 #ifdef AKI_FWD_TRACE
     const bool tracing = P.trace && (int)blockIdx.x == P.trace_cta && leader;
@@ -236,69 +241,61 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
     const uint64_t DESC_V = umma_smem_desc(0, KV_ATOM, 512, UMMA_SW64);     // MN-major: LBO = atom stride
     const uint32_t HI = (uint32_t)(DESC_KMAJ >> 32);                         // identical for both forms
     const uint32_t KMAJ_LO = (uint32_t)DESC_KMAJ, V_LO = (uint32_t)DESC_V;
-    const uint32_t q_lo = KMAJ_LO + ((smem_base + SMEM_Q) >> 4), k_lo = KMAJ_LO + ((smem_base + SMEM_K) >> 4),
+    const uint32_t qa = KMAJ_LO + ((smem_base + SMEM_Q + t * Q_TILE) >> 4), k_lo = KMAJ_LO + ((smem_base + SMEM_K) >> 4),
                    v_lo = V_LO + ((smem_base + SMEM_V) >> 4);
-    auto issue_qk = [&](int t, int j) {      // S_t[j&1] = Q_t K_j^T
-      const uint32_t qa = q_lo + t * (Q_TILE >> 4), ka = k_lo + (j % STAGES) * (KV_TILE >> 4);
-      const uint32_t d = tmem + TM_S + 128 * t + 64 * (j & 1);
-      if (leader) {
-#pragma unroll
-        for (int k = 0; k < 6; ++k)
-          umma_ss_lh(d, qa + (((k >> 1) * Q_ATOM + (k & 1) * 32) >> 4), ka + (((k >> 1) * KV_ATOM + (k & 1) * 32) >> 4), HI,
-                     IDESC_QK, k > 0);
-        umma_commit(BAR(S_FULL + 2 * t + (j & 1)));
-      }
-    };
-    auto issue_pv = [&](int t, int j) {      // O_t += P_t V_j
-      const uint32_t va = v_lo + (j % STAGES) * (KV_TILE >> 4);
-      const uint32_t d = tmem + TM_O + 96 * t, a = tmem + TM_P + 32 * t;
-      if (leader) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) umma_ts_lh(d, a + 8 * k, va + k * 64, HI, IDESC_PV, (j > 0 || k > 0));
-        umma_commit(BAR(O_FULL + t));
-      }
-    };
-    if (n_kv0 > 0) mbar_wait(BAR((ROPE ? Q_READY : Q_FULL) + 0), 0);
-    if (n_kv1 > 0) mbar_wait(BAR((ROPE ? Q_READY : Q_FULL) + 1), 0);
-    for (int jj = 0; jj < 2 && jj < n_max; ++jj) {
-      mbar_wait(BAR(K_FULL + jj), 0);
-      tc_fence_after();
-      if (jj < n_kv0) issue_qk(0, jj);
-      if (jj < n_kv1) issue_qk(1, jj);
-      if (leader) umma_commit(BAR(K_EMPTY + jj));
-      __syncwarp();
-    }
-    for (int j = 0; j < n_max; ++j) {
-      const int sv = j % STAGES, jn = j + 2, sk = jn % STAGES;
-      // operand-ready waits first: long complete in steady state, keep them off the P_FULL -> issue path
-      mbar_wait(BAR(V_FULL + sv), (j / STAGES) & 1);
-      if (jn < n_max) mbar_wait(BAR(K_FULL + sk), (jn / STAGES) & 1);
-#pragma unroll
-      for (int t = 0; t < 2; ++t) {
-        const int nk = t ? n_kv1 : n_kv0, nk_other = t ? n_kv0 : n_kv1;
-        if (j >= nk) continue;
-        // QK^T of key tile j+2 first: its buffer was handed back while the softmax was still on tile j-1, so this
-        // MMA is in flight a whole key tile before its scores are fetched
+    const uint32_t d_o = tmem + TM_O + 96 * t, a_p = tmem + TM_P + 32 * t;
+    auto k_use = [&](int j) {        // S_t[j&1] = Q_t K_j^T, then this warp's release of the K stage
+      const int s = j % STAGES;
+      mbar_wait(BAR(K_FULL + s), (j / STAGES) & 1);
+      if (j < nk) {
+        if (j >= 2) mbar_wait(BAR(S_FREE + 2 * t + (j & 1)), ((j - 2) >> 1) & 1);   // the softmax holds S_t(j-2) in registers
+        tc_fence_after();
         TR(4 + t, j, 0);
-        if (jn < nk) {
-          mbar_wait(BAR(S_FREE + 2 * t + (j & 1)), (j >> 1) & 1);
-          tc_fence_after();
-          TR(4 + t, j, 1);
-          issue_qk(t, jn);
-          if (leader && (t == 1 || jn >= nk_other)) umma_commit(BAR(K_EMPTY + sk));
+        const uint32_t ka = k_lo + s * (KV_TILE >> 4);
+        const uint32_t d = tmem + TM_S + 128 * t + 64 * (j & 1);
+        if (leader) {
+#pragma unroll
+          for (int k = 0; k < 6; ++k)
+            umma_ss_lh(d, qa + (((k >> 1) * Q_ATOM + (k & 1) * 32) >> 4), ka + (((k >> 1) * KV_ATOM + (k & 1) * 32) >> 4), HI,
+                       IDESC_QK, k > 0);
+          umma_commit(BAR(S_FULL + 2 * t + (j & 1)));
+          umma_commit(BAR(K_EMPTY + s));
         }
+        TR(4 + t, j, 1);
+      } else if (leader) {
+        mbar_arrive(BAR(K_EMPTY + s));
+      }
+      __syncwarp();
+    };
+    auto v_use = [&](int j) {        // O_t += P_t V_j, then this warp's release of the V stage
+      const int s = j % STAGES;
+      mbar_wait(BAR(V_FULL + s), (j / STAGES) & 1);
+      if (j < nk) {
         TR(4 + t, j, 2);
         mbar_wait(BAR(P_FULL + t), j & 1);
         tc_fence_after();
         TR(4 + t, j, 3);
-        issue_pv(t, j);
+        const uint32_t va = v_lo + s * (KV_TILE >> 4);
+        if (leader) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_ts_lh(d_o, a_p + 8 * k, va + k * 64, HI, IDESC_PV, (j > 0 || k > 0));
+          umma_commit(BAR(O_FULL + t));
+          umma_commit(BAR(V_EMPTY + s));
+        }
         TR(4 + t, j, 4);
-        // V_j is released by its last user: tile 1 if it uses j, else tile 0
-        if (leader && (t == 1 || j >= nk_other)) umma_commit(BAR(V_EMPTY + sv));
-        __syncwarp();
+      } else if (leader) {
+        mbar_arrive(BAR(V_EMPTY + s));
       }
+      __syncwarp();
+    };
+    if (nk > 0) mbar_wait(BAR((ROPE ? Q_READY : Q_FULL) + t), 0);
+    if (n_max > 0) k_use(0);
+    if (n_max > 1) k_use(1);
+    for (int j = 0; j < n_max; ++j) {
+      if (j + 2 < n_max) k_use(j + 2);   // QK^T two key tiles ahead: in flight a whole key tile before its scores are fetched
+      v_use(j);
     }
-  } else if (warp < 4) {
+  } else if (warp == 2) {
     setmaxnreg_dec<REGS_CTRL>();
   } else {
     // ------------------------------------------------------------------ softmax / correction / epilogue

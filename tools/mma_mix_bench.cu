@@ -8,6 +8,8 @@
 //   mode 2  forward step:   2 x [QK^T 6xSS(128x64) + PV 4xTS(128x96)]                 (nominal 768 cycles)
 //   mode 10 SS128x64 with ONE constant descriptor pair (no per-instruction descriptor arithmetic), mode 11 the same
 //           for SS128x128, mode 12 SS128x64 issued by TWO warps at once (thread 0 and thread 32, own accumulators)
+//   mode 13 backward step split over two issuing warps: {dV, S^T} on thread 0, {dQ, dK, dP^T} on thread 32
+//   mode 14 forward step split per query tile: {QK^T0, PV0} on thread 0, {QK^T1, PV1} on thread 32
 //   mode 3..9 single op types: 3 SS128x128 K-major/K-major | 4 TS128x96 B MN-major | 5 SS128x96 A MN/B MN
 //                              | 6 SS128x96 A K-major/B MN | 7 SS128x64 | 8 TS128x96 with B K-major | 9 SS128x256
 // usage: mma_mix_bench <mode> [iters]
@@ -70,6 +72,8 @@ __global__ void __launch_bounds__(128, 1) mix_kernel(int mode, int iters, long l
 #pragma unroll
                    for (int k = 0; k < 8; ++k) umma_ss(tmem, a, b, I128, 1); } break;
         case 12: ss64(0, 6); break;
+        case 13: ts96(256, 0, 8); ss128(0, 7); break;
+        case 14: ss64(0, 6); ts96(256, 448, 4); break;
       }
     }
     umma_commit(smem_u32(&bar));
@@ -83,6 +87,27 @@ __global__ void __launch_bounds__(128, 1) mix_kernel(int mode, int iters, long l
     auto km = [&](uint32_t b, int k) { return KMAJ | (uint64_t)(((b + (k >> 1) * 8192 + (k & 1) * 32) >> 4) & 0x3FFFu); };
     for (int it = 0; it < iters; ++it)
       for (int k = 0; k < 6; ++k) umma_ss(tmem + 256, km(sC, k), km(sD, k), I64, k > 0);
+    umma_commit(smem_u32(&bar2));
+    mbar_wait(smem_u32(&bar2), 0);
+  }
+  if (tid == 32 && (mode == 13 || mode == 14)) {
+    constexpr int ATOM = 8192;
+    const uint32_t sA = base, sB = base + 32768, sC = base + 65536, sD = base + 98304;
+    const uint64_t KMAJ = umma_smem_desc(0, 16, 512, UMMA_SW64), MNMAJ = umma_smem_desc(0, ATOM, 512, UMMA_SW64);
+    auto km = [&](uint32_t b, int k) { return KMAJ | (uint64_t)(((b + (k >> 1) * ATOM + (k & 1) * 32) >> 4) & 0x3FFFu); };
+    auto mn = [&](uint32_t b, int k) { return MNMAJ | (uint64_t)(((b + k * 1024) >> 4) & 0x3FFFu); };
+    const uint32_t I128 = umma_idesc_bf16(128, 128, 0, 0), I96B = umma_idesc_bf16(128, 96, 0, 1),
+                   I96AB = umma_idesc_bf16(128, 96, 1, 1), I64 = umma_idesc_bf16(128, 64, 0, 0);
+    for (int it = 0; it < iters; ++it) {
+      if (mode == 13) {
+        for (int k = 0; k < 8; ++k) umma_ss(tmem + 128, mn(sD, k), mn(sA, k), I96AB, k > 0);          // dQ
+        for (int k = 0; k < 8; ++k) umma_ts(tmem + 352, tmem + 448 + 8 * k, mn(sC, k), I96B, 1);       // dK
+        for (int k = 0; k < 7; ++k) umma_ss(tmem + 128, km(sA, k % 6), km(sB, k % 6), I128, k > 0);    // dP
+      } else {
+        for (int k = 0; k < 6; ++k) umma_ss(tmem + 128, km(sA, k), km(sB, k), I64, k > 0);
+        for (int k = 0; k < 4; ++k) umma_ts(tmem + 352, tmem + 480 + 8 * k, mn(sC, k), I96B, 1);
+      }
+    }
     umma_commit(smem_u32(&bar2));
     mbar_wait(smem_u32(&bar2), 0);
   }
@@ -104,7 +129,7 @@ int main(int argc, char** argv) {
   }
   long long h;
   CK(cudaMemcpy(&h, d, 8, cudaMemcpyDeviceToHost));
-  const double nominal[] = {2048, 2048, 768, 512, 384, 384, 384, 192, 384, 1024, 192, 512, 384};
+  const double nominal[] = {2048, 2048, 768, 512, 384, 384, 384, 192, 384, 1024, 192, 512, 384, 2048, 768};
   printf("mode %d: %.1f cycles per iteration (nominal tensor math %.0f)\n", mode, (double)h / iters, nominal[mode]);
   return 0;
 }
