@@ -8,7 +8,22 @@ void set_last_cuda_error(const char* msg) {
   strncpy(g_last_cuda_error, msg ? msg : "", sizeof(g_last_cuda_error) - 1);
   g_last_cuda_error[sizeof(g_last_cuda_error) - 1] = 0;
 }
+static thread_local cudaEvent_t g_ev_begin = nullptr, g_ev_end = nullptr;
+void timing_hook_begin(cudaStream_t st) {
+  if (g_ev_begin) cudaEventRecord(g_ev_begin, st);
+}
+void timing_hook_end(cudaStream_t st) {
+  if (g_ev_end) cudaEventRecord(g_ev_end, st);
+  g_ev_begin = nullptr; g_ev_end = nullptr;
+}
 }  // namespace aki
+
+extern "C" int aki_mma_set_timing_events(void* ev_begin, void* ev_end) {
+  if ((ev_begin == nullptr) != (ev_end == nullptr)) return AKI_ERR_NULL;
+  aki::g_ev_begin = static_cast<cudaEvent_t>(ev_begin);
+  aki::g_ev_end = static_cast<cudaEvent_t>(ev_end);
+  return AKI_OK;
+}
 
 extern "C" int aki_mma_abi_version(void) { return AKI_MMA_ABI_VERSION; }
 

@@ -8,6 +8,9 @@
 namespace aki {
 
 void set_last_cuda_error(const char* msg);
+// aki_mma_set_timing_events: one-shot pair of events recorded around the next tcgen05 attention kernel
+void timing_hook_begin(cudaStream_t st);
+void timing_hook_end(cudaStream_t st);
 
 inline int check_launch() {
   cudaError_t e = cudaGetLastError();

@@ -614,7 +614,9 @@ extern "C" int aki_mma_attn_bwd(const AkiMmaAttnBwdParams* p, aki_stream_t strea
     }
     attr_done = true;
   }
+  timing_hook_begin(st);
   attn_bwd_sm100_kernel<<<(unsigned)grid, bwd::THREADS, bwd::SMEM_ALLOC, st>>>(mq, mk, mv, mdo, mdq, mqa, mda, kp);
+  timing_hook_end(st);
   if ((rc = check_launch())) return rc;
   return launch_dq_finalize(*p, w, f.scale, st);   // dS^T is kept unscaled inside the kernel
 }

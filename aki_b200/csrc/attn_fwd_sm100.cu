@@ -615,10 +615,12 @@ extern "C" int aki_mma_attn_fwd(const AkiMmaAttnParams* p, aki_stream_t stream) 
     }
     attr_done = true;
   }
+  timing_hook_begin(st);
   if (p->rope_cos)
     attn_fwd_sm100_kernel<true><<<(unsigned)grid, fwd::THREADS, fwd::SMEM_ALLOC, st>>>(mq, mk, mv, kp);
   else
     attn_fwd_sm100_kernel<false><<<(unsigned)grid, fwd::THREADS, fwd::SMEM_ALLOC, st>>>(mq, mk, mv, kp);
+  timing_hook_end(st);
 #ifdef AKI_FWD_TRACE
   if (trace_env) {
     cudaDeviceSynchronize();

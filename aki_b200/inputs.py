@@ -41,5 +41,9 @@ def prepare_inputs_for_forward(self, vision_tokens: Optional[torch.Tensor], lang
                               text_only=text_only, exact_shape=exact_shape)
     embeds, new_labels = ops.splice(lang_embeds.to(torch.bfloat16), vision_tokens, labels, segs,
                                     pad_value=float(self.pad_token_id), padding_side=padding_side)
+    if torch.is_grad_enabled() and padding_side == "right" and (
+            lang_embeds.requires_grad or (vision_tokens is not None and vision_tokens.requires_grad)):
+        # training: same values, but with the scatter-add backward so that the embedding table / vision side train
+        embeds = ops.splice_trainable(lang_embeds.to(torch.bfloat16), vision_tokens, segs, float(self.pad_token_id))
     return {"inputs_embeds": embeds.to(lang_embeds.dtype), "attention_mask": segs.spliced_mask_2d(),
             "labels": new_labels, "mma_segments": segs}

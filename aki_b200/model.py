@@ -87,3 +87,37 @@ class AkiPhi3Runner(nn.Module):
             logits = self.decode_step(tok, cache)
             tok = logits[:, -1].argmax(-1, keepdim=True)
         return torch.cat(out, dim=1), cache
+
+
+class AkiPhi3SFT(nn.Module):
+    """Training-side counterpart of the LM half of AKI.forward (codes/open_flamingo/src/aki.py:125-130) with the
+    reference's `amp_bf16` precision (configs/sft.yaml:55): fp32 master parameters, bf16 autocast compute.  Returns
+    the shifted next-token cross-entropy HF computes for `labels` (-100 = ignored).  Wrap it in torch DDP for the
+    data-parallel SFT step (train/instruction_finetune.py:128-130); the attention op itself has no collective."""
+
+    def __init__(self, config, device="cuda", seed: int = 0):
+        super().__init__()
+        from transformers import Phi3ForCausalLM
+        torch.manual_seed(seed)
+        with torch.device(device):
+            self.lm = Phi3ForCausalLM(config)           # fp32 master weights
+        replace_phi3_attention(self.lm)
+        self.config = config
+        rp = config.rope_parameters
+        self.rope = LongRope(96, rp["rope_theta"], rp["short_factor"], rp["long_factor"], config.max_position_embeddings,
+                             rp["original_max_position_embeddings"], device=device)
+
+    def forward(self, inputs_embeds: torch.Tensor, segs: Optional[ops.MMASegments], labels: torch.Tensor):
+        B, T, _ = inputs_embeds.shape
+        cos, sin = self.rope.tables(torch.arange(T, device=inputs_embeds.device)[None], max_position=T - 1)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            h = inputs_embeds
+            for layer in self.lm.model.layers:
+                h = layer(h, attention_mask=None, position_ids=None, past_key_values=None, use_cache=False,
+                          position_embeddings=None, mma_segments=segs, mma_rope=(cos, sin))
+                if isinstance(h, tuple):
+                    h = h[0]
+            logits = self.lm.lm_head(self.lm.model.norm(h))
+        logits = logits[:, :-1].float()
+        return nn.functional.cross_entropy(logits.reshape(-1, logits.shape[-1]), labels[:, 1:].reshape(-1),
+                                           ignore_index=-100)

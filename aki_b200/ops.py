@@ -158,6 +158,41 @@ def splice(lang_embeds: torch.Tensor, vision_tokens: Optional[torch.Tensor], lab
     return out, labels_out
 
 
+class _SpliceFn(torch.autograd.Function):
+    """splice() with a backward pass: the gather is one-to-one, so the gradient of the embeddings / vision tokens is
+    a scatter-add of the output gradient through `src` (training path, padding_side="right" only)."""
+
+    @staticmethod
+    def forward(ctx, lang_embeds, vision_tokens, segs, pad_value):
+        out, _ = splice(lang_embeds, vision_tokens, None, segs, pad_value, "right")
+        ctx.save_for_backward(segs.src)
+        ctx.shapes = (lang_embeds.shape, None if vision_tokens is None else vision_tokens.shape)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        (src,) = ctx.saved_tensors
+        (B, L, E), vshape = ctx.shapes
+        src = src[:, : d_out.shape[1]].to(torch.int64)
+        is_text = src >= 0
+        is_vis = (src < 0) & (src > -(1 << 31))
+        d_lang = torch.zeros(B, L, E, dtype=d_out.dtype, device=d_out.device)
+        d_lang.scatter_add_(1, src.clamp(min=0)[..., None].expand(-1, -1, E), d_out * is_text[..., None])
+        d_vis = None
+        if vshape is not None:
+            n_tok = vshape[1] * vshape[2]
+            d_vis = torch.zeros(B, n_tok, E, dtype=d_out.dtype, device=d_out.device)
+            d_vis.scatter_add_(1, (-1 - src).clamp(0, n_tok - 1)[..., None].expand(-1, -1, E), d_out * is_vis[..., None])
+            d_vis = d_vis.view(vshape)
+        return d_lang, d_vis, None, None
+
+
+def splice_trainable(lang_embeds: torch.Tensor, vision_tokens: Optional[torch.Tensor], segs: MMASegments,
+                     pad_value: float) -> torch.Tensor:
+    """Differentiable splice for the SFT step (bf16 in, bf16 out; right padding)."""
+    return _SpliceFn.apply(lang_embeds, vision_tokens, segs, pad_value)
+
+
 # --------------------------------------------------------------------------------------------------
 # rope
 # --------------------------------------------------------------------------------------------------

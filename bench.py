@@ -44,7 +44,9 @@ def parse():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="attn", choices=["attn", "prefill"])
+    ap.add_argument("--workload", default="attn", choices=["attn", "sft"],
+                    help="attn: the headline line (+ AKI-4B prefill/decode section); sft: BASELINE config 4, DDP step")
+    ap.add_argument("--sft-layers", type=int, default=32)
     ap.add_argument("--seq", type=int, default=8192)
     ap.add_argument("--batch", type=int, default=2)
     ap.add_argument("--images", type=int, default=4)
@@ -248,6 +250,85 @@ def prefill_section(dev, rank, world, steps, warmup):
             "decode_attn_kv_bytes_per_step": kv_bytes}
 
 
+# ------------------------------------------------------------------------------------------------ SFT step (config 4)
+def sft_main(args, rank, world, local):
+    """BASELINE config 4: AKI-4B language model (random init, Phi-3.5-mini geometry) instruction-finetune step in the
+    reference's amp_bf16 precision, per-GPU batch 4, L = 513 tokens with one <image> (144 vision tokens) -> T = 656,
+    labels -100 up to <|assistant|> (sft.yaml:19-21, base.py:81-87), AdamW, grad-norm clip 1.0 every step
+    (train_utils.py:143-158); torch DDP over NCCL is the only collective.  Vision tokens are synthetic N(0,0.02)."""
+    import torch.distributed as dist
+    from torch.nn.parallel import DistributedDataParallel as DDP
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    import aki_b200
+    from aki_b200.model import AkiPhi3SFT, phi35_mini_config
+    Bp, L, N = 4, 513, 144
+    T = L - 1 + N
+    model = AkiPhi3SFT(phi35_mini_config(num_layers=args.sft_layers), device=dev, seed=0)
+    n_params = sum(p.numel() for p in model.parameters())
+    net = DDP(model, device_ids=[local], gradient_as_bucket_view=True) if world > 1 else model
+    opt = torch.optim.AdamW(model.parameters(), lr=2e-5, weight_decay=1e-4, fused=True)
+    g = np.random.default_rng(1000 + rank)
+    me = type("M", (), {})()
+    me.lang_model = model.lm; me.media_token_id = MEDIA_ID; me.num_tokens_per_vis = N; me.pad_token_id = 32000
+    host = []
+    for _ in range(4):                      # a few distinct pinned host batches, cycled
+        lang = g.integers(3, 31000, size=(Bp, L)).astype(np.int64)
+        lang[:, 10] = MEDIA_ID; lang[:, 120] = ASST_ID
+        labels = lang.copy(); labels[:, :121] = -100
+        host.append((torch.from_numpy(lang).pin_memory(), torch.ones(Bp, L, dtype=torch.int64).pin_memory(),
+                     torch.from_numpy(labels).pin_memory(),
+                     (torch.randn(Bp, 1, N, 3072) * 0.02).to(torch.bfloat16).pin_memory()))
+    host_loss = torch.empty(1, dtype=torch.float32).pin_memory()
+
+    def step(i):
+        ids, am, lab, vis = (x.to(dev, non_blocking=True) for x in host[i % len(host)])
+        pr = aki_b200.prepare_inputs_for_forward(me, vis, ids, am, labels=lab, padding_side="right")
+        loss = net(pr["inputs_embeds"].float(), pr["mma_segments"], pr["labels"])
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
+        opt.step(); opt.zero_grad(set_to_none=True)
+        host_loss.copy_(loss.detach().reshape(1), non_blocking=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(i)
+    sampler = ClockSampler(local)
+    barrier(); sampler.start()
+    a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for i in range(args.steps):
+        step(i)
+    b_.record()
+    barrier()
+    clocks = sampler.stop()
+    ms = a.elapsed_time(b_) / args.steps
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t[0])
+    if rank == 0:
+        print(json.dumps({
+            "metric": "sft_tokens_per_s", "value": world * Bp * T / (ms * 1e-3), "unit": "tokens/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16 autocast, fp32 master weights", "data": "synthetic",
+            "config": {"workload": f"AKI-4B LM SFT step ({args.sft_layers} layers, {n_params / 1e9:.2f} B params, random "
+                                   f"init) B={Bp}/gpu L={L} 1 image x {N} -> T={T}, AdamW(fused), clip 1.0, host batches "
+                                   "copied in and loss read back every step",
+                       "parallelism": f"DDP x{world} (NCCL gradient all-reduce, {n_params * 4 / 1e9:.1f} GB fp32 per step)"},
+            "loss": float(host_loss[0]), "clocks": clocks,
+            "e2e": {"value": world * Bp * T / (ms * 1e-3), "unit": "tokens/s",
+                    "h2d_bytes_per_step": int(Bp * L * 8 * 3 + Bp * N * 3072 * 2), "d2h_bytes_per_step": 4}}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 # ------------------------------------------------------------------------------------------------ main
 def main():
     args = parse()
@@ -258,6 +339,8 @@ def main():
            "l2": "inputs (q,k,v,o,dO: 5 x %.0f MB per GPU) larger than the 126 MB L2" % (B * T * H * D * 2 / 1e6),
            "parallelism": f"batch-sharded x{world}, no collective"}
 
+    if args.workload == "sft" and args.impl != "reference":
+        return sft_main(args, rank, world, local)
     if args.impl == "reference":
         if rank != 0:
             return
@@ -300,18 +383,29 @@ def main():
     dviews = [d_qkv[..., i * H * D:(i + 1) * H * D].unflatten(-1, (H, D)) for i in range(3)]
 
     ev = lambda: torch.cuda.Event(enable_timing=True)
-    per_fwd, per_bwd = [], []
+    per_fwd, per_bwd, per_fwd_k, per_bwd_k = [], [], [], []
+    from aki_b200._lib import lib as _clib
+
+    def hook():
+        """Pair of events the C library records right around its next tcgen05 attention kernel
+        (aki_mma_set_timing_events): the kernel-only duration the roofline is computed from."""
+        a, b_ = ev(), ev()
+        a.record(); b_.record()                       # creates the cudaEvent_t handles
+        _clib.aki_mma_set_timing_events(a.cuda_event, b_.cuda_event)
+        return a, b_
 
     def step(timed):
         e0, e1, e2 = ev(), ev(), ev()
         e0.record()
         ops.rope_kv_write(qkv, cos, sin, k_rot, None, 0, H)
+        kf = hook() if timed else None
         o, lse = ops.attn_fwd_raw(q4, k_rot.transpose(1, 2), v4, cos, sin, meta, scale)
         e1.record()
+        kb = hook() if timed else None
         ops.attn_bwd_raw(d_o, q4, k_rot.transpose(1, 2), v4, o, lse, cos, sin, meta, scale, *dviews)
         e2.record()
         if timed:
-            per_fwd.append((e0, e1)); per_bwd.append((e1, e2))
+            per_fwd.append((e0, e1)); per_bwd.append((e1, e2)); per_fwd_k.append(kf); per_bwd_k.append(kb)
 
     def barrier():
         if world > 1:
@@ -334,6 +428,28 @@ def main():
     ms_step = ms_total / args.steps
     fwd_ms = statistics.mean(a.elapsed_time(b) for a, b in per_fwd)
     bwd_ms = statistics.mean(a.elapsed_time(b) for a, b in per_bwd)
+    fwd_k_ms = statistics.mean(a.elapsed_time(b) for a, b in per_fwd_k)
+    bwd_k_ms = statistics.mean(a.elapsed_time(b) for a, b in per_bwd_k)
+
+    # ---- decode attention kernel alone (HBM-bound): B=8 sequences x 32 heads against an 8K-token cache --------
+    Bd, Td = 8, 8192
+    kc = torch.randn(Bd, H, Td, D, device=dev, dtype=torch.float32).to(torch.bfloat16)
+    vc = torch.randn(Bd, H, Td, D, device=dev, dtype=torch.float32).to(torch.bfloat16)
+    qd = torch.randn(Bd, H, D, device=dev, dtype=torch.float32).to(torch.bfloat16)
+    kvl = torch.full((Bd,), Td, dtype=torch.int32, device=dev)
+    for _ in range(3):
+        ops.decode_op(qd, kc, vc, kvl, Td, scale)
+    torch.cuda.synchronize()
+    d0, d1 = ev(), ev()
+    n_dec_rep = 20
+    d0.record()
+    for _ in range(n_dec_rep):
+        ops.decode_op(qd, kc, vc, kvl, Td, scale)
+    d1.record()
+    torch.cuda.synchronize()
+    dec_ms = d0.elapsed_time(d1) / n_dec_rep
+    dec_bytes = 2.0 * Bd * H * Td * D * 2
+    del kc, vc
 
     # ---- e2e: public module API with host inputs --------------------------------------------------
     e2e = None
@@ -369,12 +485,13 @@ def main():
     flops = 43008.0 * nnz
 
     # ---- max over ranks, aggregate ----------------------------------------------------------------
-    stats = torch.tensor([ms_step, fwd_ms, bwd_ms, e2e_ms if not args.no_e2e else 0.0, float(flops)],
-                         dtype=torch.float64, device=dev)
+    stats = torch.tensor([ms_step, fwd_ms, bwd_ms, e2e_ms if not args.no_e2e else 0.0, float(flops), fwd_k_ms, bwd_k_ms,
+                          dec_ms], dtype=torch.float64, device=dev)
     if world > 1:
         mx = stats.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         sm = stats.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
         ms_step, fwd_ms, bwd_ms, e2e_ms_r = (float(x) for x in mx[:4])
+        fwd_k_ms, bwd_k_ms, dec_ms = (float(x) for x in mx[5:8])
         total_flops = float(sm[4])
     else:
         e2e_ms_r = float(stats[3]); total_flops = flops
@@ -392,16 +509,31 @@ def main():
     value = total_flops / (ms_step * 1e-3) / 1e12
     bwd_tf = 30720.0 * nnz / (bwd_ms * 1e-3) / 1e12
     fwd_tf = 12288.0 * nnz / (fwd_ms * 1e-3) / 1e12
+    bwd_k_tf = 30720.0 * nnz / (bwd_k_ms * 1e-3) / 1e12      # attn_bwd_sm100_kernel alone (events from the C library)
+    fwd_k_tf = 12288.0 * nnz / (fwd_k_ms * 1e-3) / 1e12
+    traffic = None                                           # dram bytes per launch of the dominant kernel (ncu --set full)
+    tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tp) and T == 8192 and B == 2 and n_img == 4:
+        traffic = json.load(open(tp)).get("attn_bwd_sm100_kernel")
     line = {
         "metric": "mma_attn_fwd_bwd_tflops", "value": value, "unit": "TFLOP/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": cfg,
         "frac_of_bf16_peak": value / (pk["bf16_tflops"] * world),
-        "kernels": {"fwd_ms": fwd_ms, "fwd_tflops": fwd_tf, "bwd_ms": bwd_ms, "bwd_tflops": bwd_tf, "nnz_per_gpu": nnz},
-        "roofline": {"bound": "tensor", "kernel": "attn_bwd_sm100_kernel (+preprocess/finalize, whole backward call)",
-                     "achieved": bwd_tf, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                     "frac": bwd_tf / pk["bf16_tflops_sustained"], "frac_of_burst_peak": bwd_tf / pk["bf16_tflops"],
-                     "peak_source": pk_src + ", sustained (kernel timed inside a long step)", "traffic": None},
+        "kernels": {"fwd_ms": fwd_ms, "fwd_tflops": fwd_tf, "bwd_ms": bwd_ms, "bwd_tflops": bwd_tf, "nnz_per_gpu": nnz,
+                    "attn_fwd_sm100_kernel_ms": fwd_k_ms, "attn_fwd_sm100_kernel_tflops": fwd_k_tf,
+                    "attn_bwd_sm100_kernel_ms": bwd_k_ms, "attn_bwd_sm100_kernel_tflops": bwd_k_tf,
+                    "note": "fwd/bwd = whole C-ABI calls (rope_kv_write + forward; preprocess + memset + backward + "
+                            "finalize); *_kernel = the tcgen05 kernel alone between events recorded by the library"},
+        "roofline": {"bound": "tensor", "kernel": "attn_bwd_sm100_kernel",
+                     "achieved": bwd_k_tf, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                     "frac": bwd_k_tf / pk["bf16_tflops_sustained"], "frac_of_burst_peak": bwd_k_tf / pk["bf16_tflops"],
+                     "peak_source": pk_src + ", sustained (kernel timed inside a long step)",
+                     "algorithmic": "30720 * nnz FLOP per launch (SURVEY 8d)", "traffic": traffic},
+        "decode_kernel": {"bound": "hbm", "workload": f"aki_mma_decode B={Bd} H={H} T_kv={Td} D={D} (one layer)",
+                          "ms": dec_ms, "achieved": dec_bytes / (dec_ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"],
+                          "unit": "GB/s", "frac": dec_bytes / (dec_ms * 1e-3) / 1e9 / pk["hbm_gbs"],
+                          "algorithmic": "2*B*H*T_kv*D*2 bytes (K and V read once)"},
         "clocks": clocks, "gpu_launches": 5 * args.steps,
     }
     if not args.no_e2e:

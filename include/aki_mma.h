@@ -177,6 +177,13 @@ int aki_mma_decode(const void* q, const void* k_cache, const void* v_cache, int6
                    int64_t cache_stride_h, const int32_t* kv_len, int max_kv_len, int B, int H, int D, float scale,
                    void* out, void* workspace, size_t workspace_bytes, aki_stream_t stream);
 
+/* Measurement hook (bench.py roofline): the NEXT aki_mma_attn_fwd / aki_mma_attn_bwd call of this host thread
+ * records `ev_begin` right before and `ev_end` right after its tcgen05 attention kernel on the call's stream (the
+ * preprocess / memset / finalize launches of the backward stay outside), then the hook clears itself.
+ * Both are cudaEvent_t created by the caller with timing enabled; pass NULL, NULL to cancel.  No reference
+ * counterpart (the reference has no profiling hooks). */
+int aki_mma_set_timing_events(void* ev_begin, void* ev_end);
+
 /* ------------------------------------------------------------------------------------------------------
  * Verification kernels (tests only): the same maths as (4) written as plain SIMT CUDA with no tensor cores,
  * used to cross-check the tcgen05 kernels on-device at sizes the CPU oracle cannot reach. */

@@ -210,3 +210,39 @@ def test_phi3_model_with_swapped_attention_matches_hf_eager_on_reference_mask():
     scale = float(ref.float()[rows].abs().max())
     assert float(d.abs().max()) < 0.06 * max(scale, 1.0), (float(d.abs().max()), scale)
     assert float(d.pow(2).mean().sqrt()) < 0.01 * max(scale, 1.0)
+
+
+@pytest.mark.gpu
+def test_trainable_splice_gradient_matches_torch_cat_reference():
+    """Training path of the splice: values equal the gather kernel, gradients equal autograd through
+    the reference's torch.cat construction (vlm.py:539-545)."""
+    import aki_b200
+    from aki_b200 import ops
+    dev = torch.device("cuda", 0)
+    B, L, N, E = 2, 40, 16, 64
+    g = np.random.default_rng(5)
+    lang = g.integers(3, 31000, size=(B, L)).astype(np.int64)
+    lang[0, 3] = Hp.MEDIA_ID; lang[1, 7] = Hp.MEDIA_ID; lang[1, 20] = Hp.MEDIA_ID
+    am = np.ones_like(lang)
+    ids = torch.from_numpy(lang).to(dev); amt = torch.from_numpy(am).to(dev)
+    emb = torch.randn(B, L, E, device=dev).to(torch.bfloat16).requires_grad_(True)
+    vis = torch.randn(B, 2, N, E, device=dev).to(torch.bfloat16).requires_grad_(True)
+    segs = ops.build_segments(ids, amt, N, Hp.MEDIA_ID)
+    out = ops.splice_trainable(emb, vis, segs, 0.0)
+    w = torch.randn_like(out)
+    (out.float() * w.float()).sum().backward()
+    # reference: per-sample torch.cat, right-padded with zeros
+    emb_r = emb.detach().clone().requires_grad_(True); vis_r = vis.detach().clone().requires_grad_(True)
+    rows = []
+    for b in range(B):
+        parts, k, prev = [], 0, 0
+        for pos in np.where(lang[b] == Hp.MEDIA_ID)[0]:
+            parts += [emb_r[b, prev:pos], vis_r[b, k]]; prev = pos + 1; k += 1
+        parts.append(emb_r[b, prev:])
+        row = torch.cat(parts, 0)
+        rows.append(torch.cat([row, row.new_zeros(segs.T - row.shape[0], E)], 0))
+    ref = torch.stack(rows)
+    assert torch.equal(out.detach(), ref.detach())
+    (ref.float() * w.float()).sum().backward()
+    assert torch.allclose(emb.grad.float(), emb_r.grad.float(), atol=1e-6)
+    assert torch.allclose(vis.grad.float(), vis_r.grad.float(), atol=1e-6)
