@@ -11,8 +11,8 @@ struct BwdWorkspace {
   __nv_bfloat16* q_rot;   // (B,H,T,D) bf16, post-RoPE queries
   float* delta;           // (B,H,T)
   float* dq_accum;        // (B,H,T,D) fp32
-  __nv_bfloat16* q_aug;   // (B,H,t_pad,8) bf16: -LSE/scale as hi+mid+lo, 0 x5   (statistics k-step of S^T)
-  __nv_bfloat16* do_aug;  // (B,H,t_pad,8) bf16: -delta as hi+mid+lo, 0 x5       (statistics k-step of dP^T)
+  __nv_bfloat16* row_stats;  // (B,H,t_pad,8) bf16: [-LSE/scale hi,mid,lo, 0, -delta hi,mid,lo, 0]: the B operand of the
+                             // statistics k-step of S^T (selected by ones [1,1,1,0,0,0,0,0]) and of dP^T ([0,0,0,0,1,1,1,0])
   int t_pad;              // T rounded up to the 128-row tile: the statistics tiles are never out of bounds
   size_t bytes;
 };
@@ -29,8 +29,7 @@ inline BwdWorkspace carve_bwd_workspace(void* base, int B, int H, int T, int D) 
   w.dq_accum = reinterpret_cast<float*>(p + off);      off += align256(n * D * 4);
   w.t_pad = (T + 127) / 128 * 128;
   const size_t na = (size_t)B * H * w.t_pad;
-  w.q_aug = reinterpret_cast<__nv_bfloat16*>(p + off);  off += align256(na * 16);
-  w.do_aug = reinterpret_cast<__nv_bfloat16*>(p + off); off += align256(na * 16);
+  w.row_stats = reinterpret_cast<__nv_bfloat16*>(p + off);  off += align256(na * 16);
   w.bytes = off;
   return w;
 }

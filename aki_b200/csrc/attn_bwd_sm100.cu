@@ -5,15 +5,14 @@
 // on a (B,32,T,T) tensor).  One CTA owns one 128-key tile of one (batch, head) and walks exactly the query tiles
 // that can see it (kv_tile_q_mask: with MMA that set is the image-row tiles before the diagonal plus everything
 // from the diagonal on), with everything transposed so that keys sit on TMEM lanes:
-//     S^T  = K Q_i^T  - LSE_i/scale       (SS)        P^T = exp2(S^T * scale*log2e)   -> TMEM (bf16, in place over S^T)
-//     dP^T = V dO_i^T - delta_i           (SS)        dS^T = P^T o dP^T               -> TMEM (bf16) and smem (bf16)
+//     S^T  = K Q_i^T  - LSE_i/scale       (SS)        P^T = exp2(S^T * scale*log2e)   -> TMEM (bf16, own columns)
+//     dP^T = V dO_i^T - delta_i           (SS)        dS^T = P^T o dP^T               -> smem (bf16)
 //     dV  += P^T dO_i                     (TS)
 //     dQ_i = dS K                         (SS, A MN-major = the dS^T smem buffer, B MN-major = K)
-//     dK  += dS^T Q_i                     (TS, A = dS^T in TMEM, B MN-major = Q_i)       (x scale in the epilogue)
-// The kernel is bound by SHARED-MEMORY bandwidth, not by the tensor pipe: an SS MMA with M = N = 128 reads 8 KB of
-// operands per 64-cycle k-step = the full 128 B/clk of the SM, and the TMA fills, the dS^T stores and the dQ
-// staging share the same port (ncu: tensor pipe 48% active, the MMA warp stalled on a full issue queue).  Hence
-// every A operand that can live in TMEM does: P^T (dV) and dS^T (dK).
+//     dK  += dS^T Q_i                     (SS, A K-major = dS^T, B MN-major = Q_i)       (x scale in the epilogue)
+// (A variant that wrote P^T in place over S^T and kept dS^T in TMEM for a TS dK was no faster and showed a rare
+// dV mismatch -- S^T(i+1) overwriting columns that dV(i) still reads as its A operand -- so every TMEM region that
+// an MMA reads is only ever rewritten after an explicit mbarrier round trip.)
 // The per-query statistics are folded INTO the two score MMAs: a 7th k-step multiplies a constant "ones" operand
 // [1,1,1,0..] on the key side with a [128][8] bf16 row-statistics operand on the query side that holds -LSE/scale
 // (resp. -delta) split into three bf16 terms (hi + mid + lo: 2^-24 relative).  In this transposed layout LSE and
@@ -30,11 +29,12 @@
 // visible read them) | 4-11 compute (thread <-> key row r; the two warpgroups split the 128 query columns of a
 // tile in halves) | 12-15 dQ drain.  Tensor-pipe order per query tile: dV(i) S(i+1) dQ(i) dK(i) dP(i+1) -- the dQ
 // drain overlaps dK, the exponentials of tile i+1 overlap dQ/dK/dP.
-// TMEM columns: S^T / P^T [0,128) (each half writes its P^T over the first 32 columns of the 64 S^T columns it
-// read)  dP^T/dQ [128,256)  dV [256,352)  dK [352,448)  dS^T (bf16 pairs) [448,512).
-// Shared memory: K, V 24 KB each (resident), Q ring 2x24 KB, dO ring 2x24 KB, dS^T 32 KB, dQ staging 2x16 KB,
-// row-statistics operands 2x2 KB + 2x2 KB, ones/zero core matrices, mask statistics, query-tile list.
+// TMEM columns: S^T [0,128)  dP^T/dQ [128,256)  dV [256,352)  dK [352,448)  P^T (bf16 pairs) [448,512).
+// Shared memory: K, V 24 KB each (resident), Q ring 2x(24+2) KB (the [128][8] row statistics travel with Q), dO ring
+// 2x24 KB, dS^T 32 KB, dQ staging 2x16 KB, ones/zero core matrices, mask statistics, query-tile list.
 #include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
 #include "attn_aux.cuh"
 #include "sm100_ptx.cuh"
 
@@ -46,26 +46,29 @@ constexpr int ATOM_BYTES = 128 * 64;          // bf16 operand atom [128 rows][64
 constexpr int TILE_BYTES = 3 * ATOM_BYTES;
 constexpr int AUG_BYTES = 128 * 16;           // row-statistics operand [16 groups][8 rows][16 B], no swizzle
 constexpr int DQ_ATOM_BYTES = 128 * 128;      // fp32 staging atom [128 rows][32 floats], SWIZZLE_128B
+// Q(it) lives from S^T(it) to dK(it), ~1.5 steps plus the TMA latency: a third Q stage removes the ~700-cycle wait of
+// stream A for Q(it+1) (clock64 trace), but only fits next to 2 x 8 KB of dQ staging, and the drain then becomes the
+// bottleneck (6 proxy-fenced rounds per tile; measured 2.67 ms vs 2.57 ms) -- kept at 2 stages + 2 x 16 KB staging.
 constexpr int Q_STAGES = 2, DO_STAGES = 2;
 constexpr int THREADS = 512;
-constexpr int MAX_TILES = 1024;
+constexpr int MAX_TILES = 512;                // T <= 65536
 constexpr int SMEM_K = 0;
 constexpr int SMEM_V = SMEM_K + TILE_BYTES;
 constexpr int SMEM_Q = SMEM_V + TILE_BYTES;
 constexpr int SMEM_DO = SMEM_Q + Q_STAGES * TILE_BYTES;
 constexpr int SMEM_DS = SMEM_DO + DO_STAGES * TILE_BYTES;   // 4 atoms [128][64 B]
 constexpr int SMEM_DQ = SMEM_DS + 4 * ATOM_BYTES;           // 2 staging atoms
-constexpr int SMEM_QAUG = SMEM_DQ + 2 * DQ_ATOM_BYTES;      // Q_STAGES x AUG_BYTES
-constexpr int SMEM_DOAUG = SMEM_QAUG + Q_STAGES * AUG_BYTES;
-constexpr int SMEM_ONES = SMEM_DOAUG + DO_STAGES * AUG_BYTES;   // one core matrix [8][16 B] = [1,1,1,0,0,0,0,0] x 8
-constexpr int SMEM_ZERO = SMEM_ONES + 128;                      // one all-zero core matrix
+constexpr int SMEM_QAUG = SMEM_DQ + 2 * DQ_ATOM_BYTES;      // Q_STAGES x AUG_BYTES: [-LSE/scale x3, 0, -delta x3, 0] per query row
+constexpr int SMEM_ONES = SMEM_QAUG + Q_STAGES * AUG_BYTES; // core matrix [8][16 B] of [1,1,1,0,0,0,0,0] rows (selects -LSE/scale)
+constexpr int SMEM_ONES_D = SMEM_ONES + 128;                // core matrix of [0,0,0,0,1,1,1,0] rows (selects -delta)
+constexpr int SMEM_ZERO = SMEM_ONES_D + 128;                // one all-zero core matrix
 constexpr int SMEM_STATS = SMEM_ZERO + 128;                 // 2 stages x {lo[128], width[128], flags[4]} int32
 constexpr int STATS_STAGE_INTS = 260;
 constexpr int SMEM_QLIST = SMEM_STATS + 2 * STATS_STAGE_INTS * 4 + 32;   // uint16[MAX_TILES]
 constexpr int SMEM_TOTAL = SMEM_QLIST + MAX_TILES * 2;
 constexpr int SMEM_ALLOC = SMEM_TOTAL + 1024;
 static_assert(SMEM_ALLOC + 256 <= 232448, "shared memory budget");
-constexpr uint32_t TM_S = 0, TM_DP = 128, TM_DV = 256, TM_DK = 352, TM_DS = 448;
+constexpr uint32_t TM_S = 0, TM_DP = 128, TM_DV = 256, TM_DK = 352, TM_P = 448;
 constexpr int REGS_CTRL = 64, REGS_COMPUTE = 168, REGS_DRAIN = 112;   // 128*64 + 256*168 + 128*112 = 65536
 }  // namespace bwd
 
@@ -77,7 +80,15 @@ struct BwdKernelParams {
   MaskMeta mm;
   int B, H, T, n_t, n_words;
   float scale_log2, scale;
+  unsigned long long* trace;  // debug build (make TRACE=1, tools/bwd_trace.py): clock64 stamps of one CTA
+  int trace_cta;
 };
+
+#ifdef AKI_FWD_TRACE
+#define TRB(slot, j, k) do { if (tracing && (j) < 64) P.trace[((slot) * 64 + (j)) * 8 + (k)] = clock64(); } while (0)
+#else
+#define TRB(slot, j, k) do { } while (0)
+#endif
 
 __device__ __forceinline__ uint64_t f32x2_pack(float lo, float hi) {
   uint64_t r;
@@ -94,7 +105,7 @@ __global__ void __launch_bounds__(bwd::THREADS, 1)
 attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                       const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_do,
                       const __grid_constant__ CUtensorMap map_dq, const __grid_constant__ CUtensorMap map_qaug,
-                      const __grid_constant__ CUtensorMap map_doaug, const BwdKernelParams P) {
+                      const BwdKernelParams P) {
   using namespace bwd;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -133,12 +144,13 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
     // constant operands of the statistics k-step: one core matrix of [1,1,1,0,0,0,0,0] rows, one of zeros
     const int lane = tid & 31;
     if (lane < 8) *reinterpret_cast<uint4*>(smem_gen + SMEM_ONES + lane * 16) = make_uint4(0x3f803f80u, 0x00003f80u, 0u, 0u);
-    else if (lane < 16) *reinterpret_cast<uint4*>(smem_gen + SMEM_ZERO + (lane - 8) * 16) = make_uint4(0u, 0u, 0u, 0u);
+    else if (lane < 16) *reinterpret_cast<uint4*>(smem_gen + SMEM_ONES_D + (lane - 8) * 16) = make_uint4(0u, 0u, 0x3f803f80u, 0x00003f80u);
+    else if (lane < 24) *reinterpret_cast<uint4*>(smem_gen + SMEM_ZERO + (lane - 16) * 16) = make_uint4(0u, 0u, 0u, 0u);
     fence_proxy_async_smem();
   }
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_k); tma_prefetch_desc(&map_v); tma_prefetch_desc(&map_do);
-    tma_prefetch_desc(&map_dq); tma_prefetch_desc(&map_qaug); tma_prefetch_desc(&map_doaug);
+    tma_prefetch_desc(&map_dq); tma_prefetch_desc(&map_qaug);
   }
   if (warp == 3) {
     // list of query tiles to visit, ascending
@@ -208,10 +220,9 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
           tma_load_4d(smem_base + SMEM_Q + sq * TILE_BYTES + a * ATOM_BYTES, &map_q, BAR(Q_FULL + sq), a * 32, i0, h, b);
         tma_load_4d(smem_base + SMEM_QAUG + sq * AUG_BYTES, &map_qaug, BAR(Q_FULL + sq), 0, i0, h, b);
         mbar_wait(BAR(DO_EMPTY + sd), ((it / DO_STAGES) & 1) ^ 1);
-        mbar_arrive_expect_tx(BAR(DO_FULL + sd), TILE_BYTES + AUG_BYTES);
+        mbar_arrive_expect_tx(BAR(DO_FULL + sd), TILE_BYTES);
         for (int a = 0; a < 3; ++a)
           tma_load_4d(smem_base + SMEM_DO + sd * TILE_BYTES + a * ATOM_BYTES, &map_do, BAR(DO_FULL + sd), a * 32, i0, h, b);
-        tma_load_4d(smem_base + SMEM_DOAUG + sd * AUG_BYTES, &map_doaug, BAR(DO_FULL + sd), 0, i0, h, b);
       }
     }
   } else if (warp == 1 || warp == 2) {
@@ -220,13 +231,14 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
     // streams them (tools/mma_mix_bench.cu: this step takes 2337 cycles from one thread, ~1650-2050 from two), so
     // the step is split into two independent in-order streams that the barrier protocol already separates:
     //   warp 1 (A): dV(i) += P^T dO_i ; S^T(i+1)           warp 2 (B): dQ_i ; dK += dS^T Q_i ; dP^T(i+1)
-    // TMEM hazards stay inside one stream: S^T(i+1) overwrites P^T(i) behind dV(i) (A); dQ_i overwrites dP^T(i) after
-    // DS_READY, dP^T(i+1) overwrites dQ_i after DQ_DRAINED and sits behind dK(i), so dS^T(i) is consumed before the
-    // compute warps can see DP_FULL(i+1) (B).  Q / dO stages are freed by one commit from each stream.
+    // Every TMEM / smem region an MMA reads is rewritten only after an mbarrier round trip: S^T(i+1) after P_READY(i)
+    // (A); dQ_i over dP^T(i) after DS_READY, dP^T(i+1) over dQ_i after DQ_DRAINED, and dP^T(i+1) sits behind dK(i), so
+    // the dS^T buffer is consumed before the compute warps can see DP_FULL(i+1) (B).  Q / dO stages are freed by one
+    // commit from each stream.
     setmaxnreg_dec<REGS_CTRL>();
     if (elect_one() && n_q > 0) {
       constexpr uint32_t IDESC_SS_KK = umma_idesc_bf16(128, 128, 0, 0);       // S^T, dP^T
-      constexpr uint32_t IDESC_N96_BMN = umma_idesc_bf16(128, 96, 0, 1);      // dV, dK (TS)
+      constexpr uint32_t IDESC_N96_BMN = umma_idesc_bf16(128, 96, 0, 1);      // dV (TS), dK (SS)
       constexpr uint32_t IDESC_N96_AMN_BMN = umma_idesc_bf16(128, 96, 1, 1);  // dQ
       const uint32_t sK = smem_base + SMEM_K, sV = smem_base + SMEM_V, sDS = smem_base + SMEM_DS;
       // descriptors differ only in the 14-bit start-address field: build the constant parts once
@@ -236,6 +248,7 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
       // second K chunk = the zero core matrix (LBO); row statistics = [16 groups][128 B], second K chunk aliases
       // the first (LBO 0) and meets the zero chunk of the ones operand.  Validated in tools/umma_probe.cu (5-7).
       const uint64_t DESC_ONES = umma_smem_desc(smem_base + SMEM_ONES, SMEM_ZERO - SMEM_ONES, 0, UMMA_SW_NONE);
+      const uint64_t DESC_ONES_D = umma_smem_desc(smem_base + SMEM_ONES_D, SMEM_ZERO - SMEM_ONES_D, 0, UMMA_SW_NONE);
       const uint64_t DESC_AUG = umma_smem_desc(0, 0, 128, UMMA_SW_NONE);
       auto kmajor = [&](uint32_t base, int k) {   // 16-element K step k of a [rows][96|128] K-major SW64 tile
         return DESC_KMAJ | (uint64_t)(((base + (k >> 1) * ATOM_BYTES + (k & 1) * 32) >> 4) & 0x3FFFu);
@@ -243,6 +256,9 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
       auto mnmajor = [&](uint32_t base, int k) {  // 16-row K step k of a tile read as MN-major
         return DESC_MNMAJ | (uint64_t)(((base + k * 1024) >> 4) & 0x3FFFu);
       };
+#ifdef AKI_FWD_TRACE
+      const bool tracing = P.trace && (int)blockIdx.x == P.trace_cta;
+#endif
       if (warp == 1) {
         // ---------------- stream A
         auto issue_s = [&](int it) {
@@ -261,17 +277,23 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
         for (int it = 0; it < n_q; ++it) {
           const uint32_t sDO = smem_base + SMEM_DO + (it % DO_STAGES) * TILE_BYTES;
           // dV += P^T dO_it
+          TRB(2, it, 0);
+          mbar_wait(BAR(DO_FULL + it % DO_STAGES), (it / DO_STAGES) & 1);   // dO_it has landed (stream B waits for it too)
           mbar_wait(BAR(P_READY), it & 1);
           tc_fence_after();
+          TRB(2, it, 1);
 #pragma unroll
-          for (int k = 0; k < 8; ++k)   // P^T of query columns [16k,16k+16): half k/4 keeps it at S^T + 64 (k/4) + 8 (k%4)
-            umma_ts(tmem + TM_DV, tmem + TM_S + 64 * (k >> 2) + 8 * (k & 3), mnmajor(sDO, k), IDESC_N96_BMN, (it > 0 || k > 0));
+          for (int k = 0; k < 8; ++k)
+            umma_ts(tmem + TM_DV, tmem + TM_P + 8 * k, mnmajor(sDO, k), IDESC_N96_BMN, (it > 0 || k > 0));
           umma_commit(BAR(DO_EMPTY + it % DO_STAGES));
-          // S^T of the next query tile: behind dV(it) on this stream, so P^T(it) has been consumed
+          TRB(2, it, 2);
+          // S^T of the next query tile (the S region is free once P^T(it) has been written to its own columns)
           if (it + 1 < n_q) {
             mbar_wait(BAR(Q_FULL + (it + 1) % Q_STAGES), ((it + 1) / Q_STAGES) & 1);
             tc_fence_after();
+            TRB(2, it, 3);
             issue_s(it + 1);
+            TRB(2, it, 4);
           }
         }
         umma_commit(BAR(ALL_DONE));
@@ -279,36 +301,44 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
         // ---------------- stream B
         auto issue_dp = [&](int it) {
           const uint32_t sDO = smem_base + SMEM_DO + (it % DO_STAGES) * TILE_BYTES;
-          const uint32_t sA = smem_base + SMEM_DOAUG + (it % DO_STAGES) * AUG_BYTES;
+          const uint32_t sA = smem_base + SMEM_QAUG + (it % Q_STAGES) * AUG_BYTES;   // row statistics travel with Q(it)
 #pragma unroll
           for (int k = 0; k < 6; ++k) umma_ss(tmem + TM_DP, kmajor(sV, k), kmajor(sDO, k), IDESC_SS_KK, k > 0);
-          umma_ss(tmem + TM_DP, DESC_ONES, DESC_AUG | (uint64_t)((sA >> 4) & 0x3FFFu), IDESC_SS_KK, 1);
+          umma_ss(tmem + TM_DP, DESC_ONES_D, DESC_AUG | (uint64_t)((sA >> 4) & 0x3FFFu), IDESC_SS_KK, 1);
           umma_commit(BAR(DP_FULL));
           umma_commit(BAR(DO_EMPTY + it % DO_STAGES));
         };
         mbar_wait(BAR(KV_FULL), 0);
         mbar_wait(BAR(DO_FULL + 0), 0);
+        mbar_wait(BAR(Q_FULL + 0), 0);
         tc_fence_after();
         issue_dp(0);
         for (int it = 0; it < n_q; ++it) {
           const uint32_t sQ = smem_base + SMEM_Q + (it % Q_STAGES) * TILE_BYTES;
           // dQ_it = dS K first (its drain then overlaps dK), dK += dS^T Q_it
+          TRB(3, it, 0);
           mbar_wait(BAR(DS_READY), it & 1);
           tc_fence_after();
+          TRB(3, it, 1);
 #pragma unroll
           for (int k = 0; k < 8; ++k)
             umma_ss(tmem + TM_DP, mnmajor(sDS, k), mnmajor(sK, k), IDESC_N96_AMN_BMN, k > 0);
           umma_commit(BAR(DQ_FULL));
 #pragma unroll
           for (int k = 0; k < 8; ++k)
-            umma_ts(tmem + TM_DK, tmem + TM_DS + 8 * k, mnmajor(sQ, k), IDESC_N96_BMN, (it > 0 || k > 0));
+            umma_ss(tmem + TM_DK, kmajor(sDS, k), mnmajor(sQ, k), IDESC_N96_BMN, (it > 0 || k > 0));
           umma_commit(BAR(Q_EMPTY + it % Q_STAGES));
+          TRB(3, it, 2);
           // dP^T of the next query tile overwrites the dQ region: wait until it has been drained
           if (it + 1 < n_q) {
             mbar_wait(BAR(DO_FULL + (it + 1) % DO_STAGES), ((it + 1) / DO_STAGES) & 1);
+            mbar_wait(BAR(Q_FULL + (it + 1) % Q_STAGES), ((it + 1) / Q_STAGES) & 1);   // -delta sits in the Q stage
+            TRB(3, it, 3);
             mbar_wait(BAR(DQ_DRAINED), it & 1);
             tc_fence_after();
+            TRB(3, it, 4);
             issue_dp(it + 1);
+            TRB(3, it, 5);
           }
         }
         umma_commit(BAR(ALL_DONE));
@@ -356,12 +386,18 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
     if (j < len && P.mm.mbits) k_mutual = (P.mm.mbits[(size_t)b * P.mm.bits_pitch + (j >> 5)] >> (j & 31)) & 1u;
 
     float p[64];   // P^T row half, kept from phase a to phase b
+#ifdef AKI_FWD_TRACE
+    const bool tracing = P.trace && (int)blockIdx.x == P.trace_cta && (tid & 127) == 0;   // warps 4 and 8 (same SMSP)
+    const int slot = hq;
+#endif
 
     auto phase_a = [&](int it) {
       const int qt = (int)qlist[it];
       const bool full = (qt > kt) && keys_all_valid;     // CTA-uniform
+      TRB(slot, it, 0);
       mbar_wait(BAR(S_FULL), it & 1);
       tc_fence_after();
+      TRB(slot, it, 1);
       uint32_t sraw[64];
       tmem_ld_x32(tmem + TM_S + lane_base + 64 * hq, sraw);
       tmem_ld_x32(tmem + TM_S + lane_base + 64 * hq + 32, sraw + 32);
@@ -401,16 +437,20 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
       uint32_t pk[32];
 #pragma unroll
       for (int x = 0; x < 32; ++x) pk[x] = pack_bf16x2(p[2 * x], p[2 * x + 1]);
-      tmem_st_x32(tmem + TM_S + lane_base + 64 * hq, pk);   // in place: only this thread reads these columns
+      TRB(slot, it, 2);
+      tmem_st_x32(tmem + TM_P + lane_base + 32 * hq, pk);   // own columns: the other half may still be reading S^T
       tmem_wait_st();
       tc_fence_before();
       mbar_arrive(BAR(P_READY));
+      TRB(slot, it, 3);
       mbar_arrive(BAR(ST_EMPTY + (it & 1)));
     };
 
     auto phase_b = [&](int it) {
+      TRB(slot, it, 4);
       mbar_wait(BAR(DP_FULL), it & 1);
       tc_fence_after();
+      TRB(slot, it, 5);
       uint32_t draw[64];
       tmem_ld_x32(tmem + TM_DP + lane_base + 64 * hq, draw);
       tmem_ld_x32(tmem + TM_DP + lane_base + 64 * hq + 32, draw + 32);
@@ -431,11 +471,10 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
         asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(dsw[4 * c8]), "r"(dsw[4 * c8 + 1]),
                      "r"(dsw[4 * c8 + 2]), "r"(dsw[4 * c8 + 3]));
       }
-      tmem_st_x32(tmem + TM_DS + lane_base + 32 * hq, dsw);   // A operand of dK (TS); the smem copy feeds dQ
-      tmem_wait_st();
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(BAR(DS_READY));
+      TRB(slot, it, 6);
     };
 
     // a(0) | b(0) a(1) | b(1) a(2) | ... | b(n_q-1)   (one instance of each phase in the instruction stream)
@@ -523,10 +562,15 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
     setmaxnreg_dec<REGS_DRAIN>();
     const int r = tid - 384;
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+#ifdef AKI_FWD_TRACE
+    const bool tracing = P.trace && (int)blockIdx.x == P.trace_cta && r == 0;
+#endif
     for (int it = 0; it < n_q; ++it) {
       const int i0 = (int)qlist[it] * BM;
+      TRB(4, it, 0);
       mbar_wait(BAR(DQ_FULL), it & 1);
       tc_fence_after();
+      TRB(4, it, 1);
       uint32_t dq[96];
       tmem_ld_x32(tmem + TM_DP + lane_base, dq);
       tmem_ld_x32(tmem + TM_DP + lane_base + 32, dq + 32);
@@ -534,6 +578,7 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
       tmem_wait_ld();
       tc_fence_before();
       mbar_arrive(BAR(DQ_DRAINED));
+      TRB(4, it, 2);
       // three [128][32 x fp32] SWIZZLE_128B atoms through two staging buffers
 #pragma unroll
       for (int a = 0; a < 3; ++a) {
@@ -555,6 +600,7 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
         }
       }
     }
+    TRB(4, n_q - 1, 3);
     if (r == 0) tma_store_wait<0>();   // all dQ reductions have landed before the CTA retires its smem
   }
   tc_fence_before();
@@ -585,14 +631,13 @@ extern "C" int aki_mma_attn_bwd(const AkiMmaAttnBwdParams* p, aki_stream_t strea
     return AKI_ERR_CUDA;
   }
   AkiMmaTensor4 qrot{w.q_rot, (int64_t)f.H * f.T * f.D, (int64_t)f.D, (int64_t)f.T * f.D};
-  CUtensorMap mq, mk, mv, mdo, mdq, mqa, mda;
+  CUtensorMap mq, mk, mv, mdo, mdq, mqa;
   if ((rc = make_tile_map(&mq, qrot, f.B, f.H, f.T, bwd::BM))) return rc;
   if ((rc = make_tile_map(&mk, f.k, f.B, f.H, f.T, bwd::BN))) return rc;
   if ((rc = make_tile_map(&mv, f.v, f.B, f.H, f.T, bwd::BN))) return rc;
   if ((rc = make_tile_map(&mdo, p->d_o, f.B, f.H, f.T, bwd::BM))) return rc;
   if ((rc = make_dq_accum_map(&mdq, w.dq_accum, f.B, f.H, f.T))) return rc;
-  if ((rc = make_row_stats_map(&mqa, w.q_aug, f.B, f.H, w.t_pad))) return rc;
-  if ((rc = make_row_stats_map(&mda, w.do_aug, f.B, f.H, w.t_pad))) return rc;
+  if ((rc = make_row_stats_map(&mqa, w.row_stats, f.B, f.H, w.t_pad))) return rc;
   BwdKernelParams kp;
   kp.d_k = view_of(p->d_k); kp.d_v = view_of(p->d_v);
   kp.rope_cos = f.rope_cos; kp.rope_sin = f.rope_sin; kp.rope_stride_b = f.rope_stride_b;
@@ -603,6 +648,16 @@ extern "C" int aki_mma_attn_bwd(const AkiMmaAttnBwdParams* p, aki_stream_t strea
   AKI_REQUIRE(kp.n_t <= bwd::MAX_TILES, AKI_ERR_UNSUPPORTED);
   kp.scale = f.scale;
   kp.scale_log2 = f.scale * 1.4426950408889634f;
+  kp.trace = nullptr; kp.trace_cta = -1;
+#ifdef AKI_FWD_TRACE
+  const char* trace_env = getenv("AKI_MMA_BWD_TRACE");
+  const size_t trace_bytes = 5 * 64 * 8 * sizeof(unsigned long long);
+  if (trace_env) {
+    kp.trace_cta = atoi(trace_env);
+    cudaMalloc(&kp.trace, trace_bytes);
+    cudaMemset(kp.trace, 0, trace_bytes);
+  }
+#endif
   const long long grid = (long long)kp.n_t * f.H * f.B;
   AKI_REQUIRE(grid > 0 && grid < (1ll << 31), AKI_ERR_BAD_SHAPE);
   static bool attr_done = false;
@@ -615,8 +670,28 @@ extern "C" int aki_mma_attn_bwd(const AkiMmaAttnBwdParams* p, aki_stream_t strea
     attr_done = true;
   }
   timing_hook_begin(st);
-  attn_bwd_sm100_kernel<<<(unsigned)grid, bwd::THREADS, bwd::SMEM_ALLOC, st>>>(mq, mk, mv, mdo, mdq, mqa, mda, kp);
+  attn_bwd_sm100_kernel<<<(unsigned)grid, bwd::THREADS, bwd::SMEM_ALLOC, st>>>(mq, mk, mv, mdo, mdq, mqa, kp);
   timing_hook_end(st);
+#ifdef AKI_FWD_TRACE
+  if (trace_env) {
+    cudaDeviceSynchronize();
+    static unsigned long long host[5 * 64 * 8];
+    cudaMemcpy(host, kp.trace, trace_bytes, cudaMemcpyDeviceToHost);
+    cudaFree(kp.trace);
+    unsigned long long t0 = ~0ull;
+    for (size_t i = 0; i < 5 * 64 * 8; ++i) if (host[i] && host[i] < t0) t0 = host[i];
+    const char* names[5] = {"cmp_h0", "cmp_h1", "mma_A", "mma_B", "drain"};
+    for (int slot = 0; slot < 5; ++slot)
+      for (int j = 0; j < 64; ++j) {
+        bool any = false;
+        for (int k = 0; k < 8; ++k) any = any || host[(slot * 64 + j) * 8 + k];
+        if (!any) continue;
+        fprintf(stderr, "TRACE %s it=%d:", names[slot], j);
+        for (int k = 0; k < 7; ++k) fprintf(stderr, " %llu", host[(slot * 64 + j) * 8 + k] ? host[(slot * 64 + j) * 8 + k] - t0 : 0ull);
+        fprintf(stderr, "\n");
+      }
+  }
+#endif
   if ((rc = check_launch())) return rc;
   return launch_dq_finalize(*p, w, f.scale, st);   // dS^T is kept unscaled inside the kernel
 }

@@ -88,7 +88,7 @@ attn_fwd_simt_kernel(TensorView q, TensorView k, TensorView v, TensorView o, flo
 
 // ------------------------------------------------------------------------------------------------ preprocess
 // Per (b,t,h) row: delta = sum_d O*dO ; q_rot = RoPE(q) (plain copy without tables) ; and the two [8] bf16
-// row-statistics operands of the tcgen05 backward: q_aug = -LSE/scale, do_aug = -delta, each split into
+// row-statistics operand of the tcgen05 backward: [-LSE/scale x3, 0, -delta x3, 0], each value split into
 // hi + mid + lo bf16 terms (rows that see nothing, and the padding rows t in [T, t_pad), get -1e30 / 0 so that
 // their P^T is exactly 0).  HBM-bound: 6 lanes per row (lane l owns the 16-byte chunks l and l+6, i.e. the RoPE
 // pair d <-> d+48), 5 rows per warp, every access a 16-byte vector.
@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(128)
 bwd_preprocess_kernel(TensorView q, TensorView o, TensorView d_o, const float* __restrict__ lse,
                       const float* __restrict__ rope_cos, const float* __restrict__ rope_sin, int64_t rope_stride_b,
                       int B, int T, int t_pad, int H, float inv_scale, __nv_bfloat16* __restrict__ q_rot,
-                      float* __restrict__ delta, __nv_bfloat16* __restrict__ q_aug, __nv_bfloat16* __restrict__ do_aug) {
+                      float* __restrict__ delta, __nv_bfloat16* __restrict__ row_stats) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane / 6, l = lane - 6 * g;
   const long long n_rows = (long long)B * t_pad * H;
@@ -165,9 +165,9 @@ bwd_preprocess_kernel(TensorView q, TensorView o, TensorView d_o, const float* _
 #pragma unroll
   for (int k = 0; k < 6; ++k) dl += __shfl_sync(0xffffffffu, part, min(6 * g + k, 31));
   if (active && l == 0) {
-    __nv_bfloat16 qa[8], da[8];
+    __nv_bfloat16 st[8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) { qa[e] = __float2bfloat16(0.f); da[e] = __float2bfloat16(0.f); }
+    for (int e = 0; e < 8; ++e) st[e] = __float2bfloat16(0.f);
     float v = -1e30f;
     if (live) {
       const size_t idx = ((size_t)b * H + h) * T + t;
@@ -175,17 +175,15 @@ bwd_preprocess_kernel(TensorView q, TensorView o, TensorView d_o, const float* _
       const float L = lse[idx];
       if (L < 3.0e38f) {
         v = -L * inv_scale;
-        split3_bf16(v, qa[0], qa[1], qa[2]);
+        split3_bf16(v, st[0], st[1], st[2]);
       } else {
-        qa[0] = __float2bfloat16(v);
+        st[0] = __float2bfloat16(v);
       }
-      split3_bf16(-dl, da[0], da[1], da[2]);
+      split3_bf16(-dl, st[4], st[5], st[6]);
     } else {
-      qa[0] = __float2bfloat16(v);
+      st[0] = __float2bfloat16(v);
     }
-    const size_t ar = (((size_t)b * H + h) * t_pad + t) * 8;
-    *reinterpret_cast<uint4*>(q_aug + ar) = *reinterpret_cast<const uint4*>(qa);
-    *reinterpret_cast<uint4*>(do_aug + ar) = *reinterpret_cast<const uint4*>(da);
+    *reinterpret_cast<uint4*>(row_stats + (((size_t)b * H + h) * t_pad + t) * 8) = *reinterpret_cast<const uint4*>(st);
   }
 }
 
@@ -333,7 +331,7 @@ int launch_bwd_preprocess(const AkiMmaAttnBwdParams& p, const BwdWorkspace& w, c
   if (blocks <= 0 || blocks >= (1ll << 31)) return AKI_ERR_BAD_SHAPE;
   bwd_preprocess_kernel<<<(unsigned)blocks, 128, 0, st>>>(view_of(f.q), view_of(f.o), view_of(p.d_o), f.lse, f.rope_cos,
                                                            f.rope_sin, f.rope_stride_b, f.B, f.T, w.t_pad, f.H,
-                                                           1.0f / f.scale, w.q_rot, w.delta, w.q_aug, w.do_aug);
+                                                           1.0f / f.scale, w.q_rot, w.delta, w.row_stats);
   return check_launch();
 }
 
