@@ -47,6 +47,7 @@ def parse():
     ap.add_argument("--workload", default="attn", choices=["attn", "sft"],
                     help="attn: the headline line (+ AKI-4B prefill/decode section); sft: BASELINE config 4, DDP step")
     ap.add_argument("--sft-layers", type=int, default=32)
+    ap.add_argument("--sft-fp32-reduce", action="store_true", help="all-reduce gradients in fp32 instead of bf16")
     ap.add_argument("--seq", type=int, default=8192)
     ap.add_argument("--batch", type=int, default=2)
     ap.add_argument("--images", type=int, default=4)
@@ -269,6 +270,11 @@ def sft_main(args, rank, world, local):
     model = AkiPhi3SFT(phi35_mini_config(num_layers=args.sft_layers), device=dev, seed=0)
     n_params = sum(p.numel() for p in model.parameters())
     net = DDP(model, device_ids=[local], gradient_as_bucket_view=True) if world > 1 else model
+    if world > 1 and not args.sft_fp32_reduce:
+        # gradients cross NVLink in bf16, as the reference's FSDP mixed-precision config reduces them
+        # (train/distributed.py:163-167); halves the 15.3 GB fp32 all-reduce
+        from torch.distributed.algorithms.ddp_comm_hooks import default_hooks
+        net.register_comm_hook(None, default_hooks.bf16_compress_hook)
     opt = torch.optim.AdamW(model.parameters(), lr=2e-5, weight_decay=1e-4, fused=True)
     g = np.random.default_rng(1000 + rank)
     me = type("M", (), {})()
@@ -321,7 +327,9 @@ def sft_main(args, rank, world, local):
             "config": {"workload": f"AKI-4B LM SFT step ({args.sft_layers} layers, {n_params / 1e9:.2f} B params, random "
                                    f"init) B={Bp}/gpu L={L} 1 image x {N} -> T={T}, AdamW(fused), clip 1.0, host batches "
                                    "copied in and loss read back every step",
-                       "parallelism": f"DDP x{world} (NCCL gradient all-reduce, {n_params * 4 / 1e9:.1f} GB fp32 per step)"},
+                       "parallelism": f"DDP x{world} (NCCL gradient all-reduce, "
+                                      f"{n_params * (4 if args.sft_fp32_reduce else 2) / 1e9:.1f} GB "
+                                      f"{'fp32' if args.sft_fp32_reduce else 'bf16'} per step)"},
             "loss": float(host_loss[0]), "clocks": clocks,
             "e2e": {"value": world * Bp * T / (ms * 1e-3), "unit": "tokens/s",
                     "h2d_bytes_per_step": int(Bp * L * 8 * 3 + Bp * N * 3072 * 2), "d2h_bytes_per_step": 4}}))
@@ -462,23 +470,44 @@ def main():
         host_x = torch.randn(B, T, H * D).to(torch.bfloat16).pin_memory()
         host_loss = torch.empty(1, dtype=torch.float32).pin_memory()
 
-        def e2e_step():
-            x = host_x.to(dev, non_blocking=True).requires_grad_(True)
+        # Host -> device copies run on their own stream into two device buffers: step i+1's input uploads while step
+        # i computes (every step still copies its own input from pinned host memory and reads its loss back).
+        copy_stream = torch.cuda.Stream(device=dev)
+        xbuf = [torch.empty(B, T, H * D, dtype=torch.bfloat16, device=dev) for _ in range(2)]
+        ready = [torch.cuda.Event() for _ in range(2)]
+        consumed = [torch.cuda.Event() for _ in range(2)]
+
+        def upload(i):
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(consumed[i % 2])
+                xbuf[i % 2].copy_(host_x, non_blocking=True)
+                ready[i % 2].record(copy_stream)
+
+        def e2e_step(i, last):
+            torch.cuda.current_stream().wait_event(ready[i % 2])
+            if not last:
+                upload(i + 1)
+            x = xbuf[i % 2].detach().requires_grad_(True)
             out, _ = mod(x, None, None, mma_segments=segs, mma_rope=(cos, sin))
             loss = out.float().pow(2).mean()
             loss.backward()
+            consumed[i % 2].record()
             host_loss.copy_(loss.detach().reshape(1), non_blocking=True)
             torch.cuda.current_stream().synchronize()
             mod.zero_grad(set_to_none=True)
 
-        for _ in range(max(3, args.warmup // 2)):
-            e2e_step()
+        for ev_ in consumed:
+            ev_.record()
+        n_warm = max(3, args.warmup // 2)
+        upload(0)
+        for i in range(n_warm):
+            e2e_step(i, False)
         barrier()
         a, b_ = ev(), ev()
         n_e2e = max(3, args.steps // 2)
         a.record()
-        for _ in range(n_e2e):
-            e2e_step()
+        for i in range(n_warm, n_warm + n_e2e):
+            e2e_step(i, False)      # every timed step also uploads one input (the one the next step would use)
         b_.record()
         barrier()
         e2e_ms = a.elapsed_time(b_) / n_e2e
@@ -539,7 +568,8 @@ def main():
     if not args.no_e2e:
         line["e2e"] = {"value": total_flops / (e2e_ms_r * 1e-3) / 1e12, "unit": "TFLOP/s",
                        "h2d_bytes_per_step": B * T * H * D * 2, "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms_r,
-                       "api": "AkiMMAAttention.forward + backward (qkv_proj, o_proj included in time, not in FLOPs)"}
+                       "api": "AkiMMAAttention.forward + backward (qkv_proj, o_proj included in time, not in FLOPs); the "
+                              "next step's pinned-host input uploads on a copy stream while this step computes"}
     if prefill is not None:
         line["prefill"] = prefill
     if not args.no_cpu and world >= 1:
