@@ -122,6 +122,90 @@ def test_backward_matches_autograd_oracle(name, B, L, N, n_img, rope, pad):
         assert ok, f"{name} {nm}: kernel err {ek:.3e} vs bf16-eager err {eb:.3e} (rms {rms:.3f})"
 
 
+def _edge_prompt(kind):
+    """Hand-built (lang_x, attention_mask, N, text_only) for geometries the CASES table does not reach."""
+    g = np.random.default_rng(21)
+    M, A, PAD = Hp.MEDIA_ID, Hp.ASST_ID, Hp.PAD_ID
+    text_only = False
+    if kind == "left-pad-generate":            # AKI.generate: padding_side="left" with in-sample padded keys
+        L, N = 150, 16
+        lang = g.integers(3, 31000, size=(2, L)).astype(np.int64); am = np.ones_like(lang)
+        lang[0, :40] = PAD; am[0, :40] = 0
+        lang[0, 50] = M; lang[0, 120] = A; lang[1, 5] = M; lang[1, 100] = A
+    elif kind == "mixed-image-counts":         # 0, 1 and 3 images in one batch, ragged lengths
+        L, N = 260, 32
+        lang = g.integers(3, 31000, size=(3, L)).astype(np.int64); am = np.ones_like(lang)
+        lang[0, 200] = A
+        lang[1, 9] = M; lang[1, 150] = A; lang[1, 230:] = PAD; am[1, 230:] = 0
+        lang[2, 3] = M; lang[2, 60] = M; lang[2, 130] = M; lang[2, 250] = A
+    elif kind == "tile-edges":                 # spliced lengths exactly 128 and 257 (one past a tile edge)
+        L, N = 130, 64
+        lang = g.integers(3, 31000, size=(2, L)).astype(np.int64); am = np.ones_like(lang)
+        lang[0, 1] = M; lang[0, 40] = A; lang[0, 65:] = PAD; am[0, 65:] = 0          # T_b = 64 + 64 = 128
+        lang[1, 0] = M; lang[1, 64] = M; lang[1, 129] = A                              # T_b = 130 + 2*63 = 256 ... 257 incl.
+    elif kind == "assistant-before-image":     # q_end <= span_end: pure causal (the reference's pre-training text)
+        L, N = 120, 24
+        lang = g.integers(3, 31000, size=(1, L)).astype(np.int64); am = np.ones_like(lang)
+        lang[0, 10] = A; lang[0, 60] = M
+    elif kind == "no-assistant":
+        L, N = 120, 24
+        lang = g.integers(3, 31000, size=(1, L)).astype(np.int64); am = np.ones_like(lang)
+        lang[0, 30] = M
+    elif kind == "text-only-variant":          # stricter multi-image rule: image rows see later TEXT keys only
+        L, N = 300, 48
+        lang = g.integers(3, 31000, size=(1, L)).astype(np.int64); am = np.ones_like(lang)
+        lang[0, 5] = M; lang[0, 100] = M; lang[0, 280] = A
+        text_only = True
+    else:
+        raise KeyError(kind)
+    return lang, am, N, text_only
+
+
+@pytest.mark.parametrize("kind", ["left-pad-generate", "mixed-image-counts", "tile-edges", "assistant-before-image",
+                                  "no-assistant", "text-only-variant"])
+def test_edge_geometries_forward_and_backward(kind):
+    """Padding inside a sample, ragged batches, 0..3 images, tile-edge lengths, degenerate <|assistant|> positions and
+    the text-only multi-image variant: bit-exact mask expansion, forward and gradients within the bf16 tolerance."""
+    ops = _ops()
+    lang, am, N, text_only = _edge_prompt(kind)
+    B = lang.shape[0]
+    S = O.segments_ref(lang, am, N, Hp.MEDIA_ID, text_only=text_only)
+    segs = ops.build_segments(torch.from_numpy(lang).to(dev), torch.from_numpy(am).to(dev), N, Hp.MEDIA_ID,
+                              text_only=text_only)
+    T = segs.T
+    m4_ref = O.expand_segments_to_4d(S, t_out=T, text_only=text_only)
+    assert np.array_equal(segs.expand_to_4d().cpu().numpy(), m4_ref), "mask mismatch"
+    q, k, v = Hp.qkv_inputs(B, T, H, D, seed=31)
+    d_o = torch.randn(B, T, H, D, generator=torch.Generator().manual_seed(32)).to(torch.bfloat16)
+    cos, sin = _rope(T)
+    rows = Hp.live_rows(S, B, T)
+    m4 = torch.from_numpy(m4_ref)
+
+    def oracle(dtype):
+        qf = q.to(dtype).requires_grad_(True); kf = k.to(dtype).requires_grad_(True); vf = v.to(dtype).requires_grad_(True)
+        c = torch.cat([cos, cos], -1).to(dtype).expand(B, -1, -1); s_ = torch.cat([sin, sin], -1).to(dtype).expand(B, -1, -1)
+        qh, kh = O.apply_rope(qf.transpose(1, 2), c, s_), O.apply_rope(kf.transpose(1, 2), c, s_)
+        out = O.eager_attention(qh, kh, vf.transpose(1, 2), O.invert_4d_mask(m4, dtype).to(dtype), SCALE)
+        out.backward((d_o.float() * rows[:, :, None, None]).to(dtype))
+        return out.detach(), qf.grad, kf.grad, vf.grad
+
+    o32, *g32 = oracle(torch.float32)
+    o16, *g16 = oracle(torch.bfloat16)
+    qd, k_in, vd, cd, sd = _gpu_inputs(q, k, v, cos, sin)
+    meta = ops.meta_tuple(segs)
+    o, lse = ops.attn_fwd_raw(qd, k_in, vd, cd, sd, meta, SCALE)
+    ok, ek, eb, rms = Hp.within_tolerance(o, o16, o32, rows)
+    assert ok, f"{kind} o: kernel err {ek:.3e} vs bf16-eager err {eb:.3e}"
+    if (~rows).any():
+        assert float(o.float().cpu()[~rows].abs().max()) == 0.0
+    dq = torch.full((B, T, H, D), float("nan"), dtype=torch.bfloat16, device=dev); dk = dq.clone(); dv = dq.clone()
+    ops.attn_bwd_raw(d_o.to(dev), qd, k_in, vd, o, lse, cd, sd, meta, SCALE, dq, dk, dv)
+    for nm, got, r32, r16 in zip(("dq", "dk", "dv"), (dq, dk, dv), g32, g16):
+        assert not torch.isnan(got.float()).any(), (kind, nm)
+        ok, ek, eb, rms = Hp.within_tolerance(got, r16, r32, None, floor=2e-3)
+        assert ok, f"{kind} {nm}: kernel err {ek:.3e} vs bf16-eager err {eb:.3e} (rms {rms:.3f})"
+
+
 def test_custom_op_autograd_packed_matches_raw():
     """aki_mma::attn_packed (what the module calls): gradient of the packed projection = [dq | dk | dv]."""
     ops = _ops()
