@@ -371,77 +371,96 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
     // all four warps takes 1240 cycles while the pipe idles for the other 1100 of each key tile).
     const bool stagger = (n_kv0 > 0 && n_kv1 > 0);
     if (stagger && t == 1) named_bar_sync(9, 512);
-    bool s_ready = false;                           // result of the early probe of S_FULL for the next key tile
-    for (int j = 0; j < nk; ++j) {
+    // Two key tiles per pass: the fixed per-tile latencies (mbarrier probes, TMEM round trips, the max exchange of the
+    // two column halves) cost ~1000 cycles against ~500 of exponentials, so they are paid once per PAIR of key tiles:
+    // both S buffers are fetched together, one exchange covers both, P(j) is published and PV(j) runs while the
+    // exponentials of tile j+1 are computed, then P(j+1) follows.  Exponentials overwrite the scores in place (bf16
+    // pairs compacted into the low registers), so the 64 scores of a pass are the only large register array.
+    bool s_ready0 = false, s_ready1 = false;        // early probes of S_FULL for the next pass
+    for (int j = 0; j < nk; j += 2) {
       TR(slot, j, 0);
-      const int j0 = j * BN + 32 * ch;              // first key column of this thread's half tile
-      const bool partial = (j >= n_full);           // warp-uniform
-      uint32_t vw = 0xffffffffu, mw = 0xffffffffu;
-      if (partial) {                                 // one 32-bit word of each bit-vector covers the half tile
-        if (P.mm.vbits) vw = __ldg(P.mm.vbits + (size_t)b * P.mm.bits_pitch + (j0 >> 5));
-        if (P.mm.mbits) mw = __ldg(P.mm.mbits + (size_t)b * P.mm.bits_pitch + (j0 >> 5));
+      const bool two = (j + 1 < nk);                // warp-uniform
+      const int xp = (j >> 1) & 1;                  // exchange-buffer parity of this pass
+      const int c0 = j * BN + 32 * ch;              // first key column of this thread's half of tile j
+      const bool partial0 = (j >= n_full), partial1 = two && (j + 1 >= n_full);
+      uint32_t vw0 = 0xffffffffu, mw0 = 0xffffffffu, vw1 = 0xffffffffu, mw1 = 0xffffffffu;
+      if (partial0) {                               // one 32-bit word of each bit-vector covers a half tile
+        if (P.mm.vbits) vw0 = __ldg(P.mm.vbits + (size_t)b * P.mm.bits_pitch + (c0 >> 5));
+        if (P.mm.mbits) mw0 = __ldg(P.mm.mbits + (size_t)b * P.mm.bits_pitch + (c0 >> 5));
+      }
+      if (partial1) {
+        if (P.mm.vbits) vw1 = __ldg(P.mm.vbits + (size_t)b * P.mm.bits_pitch + ((c0 + BN) >> 5));
+        if (P.mm.mbits) mw1 = __ldg(P.mm.mbits + (size_t)b * P.mm.bits_pitch + ((c0 + BN) >> 5));
       }
       // probe "PV(j-1) has consumed P(j-1)" now, use the answer just before the P store
       const bool o_known = (j == 0) || (o_waited >= j) || mbar_test(BAR(O_FULL + t), (j - 1) & 1);
-      // ---- S_t(j), this half: TMEM -> registers, then the buffer goes back to the MMA warp for key tile j+2
-      float s[32];
-      if (!s_ready) mbar_wait(BAR(S_FULL + 2 * t + (j & 1)), (j >> 1) & 1);
-      tc_fence_after();
-      TR(slot, j, 1);
-      tmem_ld_x32(tm_s + 64 * (j & 1), reinterpret_cast<uint32_t*>(s));
-      tmem_wait_ld();
-      TR(slot, j, 2);
-      tc_fence_before();
-      mbar_arrive(BAR(S_FREE + 2 * t + (j & 1)));
-      if (partial) {
-        const int d = row_live ? (i - j0) : -1;             // causal: column c visible iff c <= d
-        const int a = row_lo - j0, e = row_hi - j0;         // mutual: a <= c < e
-        const uint32_t in_len = low_mask(len - j0);
+
+      float s[64];                                   // [0,32): this half of S_t(j); [32,64): this half of S_t(j+1)
+      auto mask32 = [&](int off, int col0, uint32_t vw, uint32_t mw) {
+        const int d = row_live ? (i - col0) : -1;             // causal: column c visible iff c <= d
+        const int a = row_lo - col0, e = row_hi - col0;       // mutual: a <= c < e
+        const uint32_t in_len = low_mask(len - col0);
         const uint32_t causal = low_mask(d + 1) & vw & in_len;
         const uint32_t mutual = row_live ? (low_mask(e) & ~low_mask(a) & mw & in_len) : 0u;
         const uint32_t ok = causal | mutual;
 #pragma unroll
         for (int c = 0; c < 32; ++c)
-          if (!((ok >> c) & 1u)) s[c] = -INFINITY;
-      }
-      // ---- row max of this half; the two column halves of a row agree on the tile maximum through shared memory
-      auto half_max = [&]() {
-        float mx[4] = {s[0], s[1], s[2], s[3]};
+          if (!((ok >> c) & 1u)) s[off + c] = -INFINITY;
+      };
+      auto fetch0 = [&]() {                          // (re)load this half of S_t(j) and mask it
+        tmem_ld_x32(tm_s + 64 * (j & 1), reinterpret_cast<uint32_t*>(s));
+        tmem_wait_ld();
+        if (partial0) mask32(0, c0, vw0, mw0);
+      };
+      if (!s_ready0) mbar_wait(BAR(S_FULL + 2 * t + (j & 1)), (j >> 1) & 1);
+      if (two && !s_ready1) mbar_wait(BAR(S_FULL + 2 * t + ((j + 1) & 1)), ((j + 1) >> 1) & 1);
+      tc_fence_after();
+      TR(slot, j, 1);
+      tmem_ld_x32(tm_s + 64 * (j & 1), reinterpret_cast<uint32_t*>(s));
+      if (two) tmem_ld_x32(tm_s + 64 * ((j + 1) & 1), reinterpret_cast<uint32_t*>(s) + 32);
+      tmem_wait_ld();
+      TR(slot, j, 2);
+      if (partial0) mask32(0, c0, vw0, mw0);
+      if (partial1) mask32(32, c0 + BN, vw1, mw1);
+      // ---- maximum of this thread's scores of the pass; the partner half's arrives through shared memory
+      float mx[4] = {s[0], s[1], s[2], s[3]};
 #pragma unroll
-        for (int c = 4; c < 32; c += 4) {
+      for (int c = 4; c < 32; c += 4) {
+        mx[0] = fmaxf(mx[0], s[c]); mx[1] = fmaxf(mx[1], s[c + 1]); mx[2] = fmaxf(mx[2], s[c + 2]); mx[3] = fmaxf(mx[3], s[c + 3]);
+      }
+      if (two) {
+#pragma unroll
+        for (int c = 32; c < 64; c += 4) {
           mx[0] = fmaxf(mx[0], s[c]); mx[1] = fmaxf(mx[1], s[c + 1]); mx[2] = fmaxf(mx[2], s[c + 2]); mx[3] = fmaxf(mx[3], s[c + 3]);
         }
-        return fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
-      };
-      auto tile_max = [&](float m_half) {
-        xch[j & 1][t][ch][r] = m_half;
-        named_bar_sync(pair_bar, 64);
-        return fmaxf(m_half, xch[j & 1][t][ch ^ 1][r]);
-      };
-      float sum0, sum1;
-      uint32_t pk[16];
-      auto exps = [&]() {   // P = exp2((S - m_used) * scale*log2e), row sum, bf16 pack
+      }
+      const float m_half = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+      xch[xp][t][ch][r] = m_half;
+      // exp2((S - m_used) * scale*log2e) of 32 scores starting at `off`, packed IN PLACE into s[off .. off+16)
+      auto exps = [&](int off) {
         const float neg_m = (m_used == -INFINITY) ? 0.f : -m_used * P.scale_log2;
-        sum0 = 0.f; sum1 = 0.f;
+        float sum0 = 0.f, sum1 = 0.f;
 #pragma unroll
         for (int x = 0; x < 16; ++x) {
-          const float p0 = ex2_approx(fmaf(s[2 * x], P.scale_log2, neg_m));
-          const float p1 = ex2_approx(fmaf(s[2 * x + 1], P.scale_log2, neg_m));
+          const float p0 = ex2_approx(fmaf(s[off + 2 * x], P.scale_log2, neg_m));
+          const float p1 = ex2_approx(fmaf(s[off + 2 * x + 1], P.scale_log2, neg_m));
           sum0 += p0; sum1 += p1;
-          pk[x] = pack_bf16x2(p0, p1);
+          s[off + x] = __uint_as_float(pack_bf16x2(p0, p1));
         }
+        return sum0 + sum1;
       };
+      float sum_j;
       if (j == 0) {
-        m_used = tile_max(half_max());
-        exps();
+        named_bar_sync(pair_bar, 64);
+        m_used = fmaxf(m_half, xch[xp][t][ch ^ 1][r]);
+        sum_j = exps(0);
       } else {
-        // Optimistic: exponentiate against the running max of the EARLIER tiles while this tile's max is still
-        // being reduced and exchanged (the max chain and the pair barrier leave the critical path).  If the tile
-        // max turns out to exceed the reference by more than the threshold (rare after the first tiles), O and l are
-        // rescaled and the exponentials of this tile are redone -- accepted P values never exceed 2^threshold.
-        const float m_half = half_max();
-        exps();
-        const float m_new = fmaxf(m_used, tile_max(m_half));
+        // Optimistic: exponentiate tile j against the running max of the EARLIER passes while the maxima are being
+        // exchanged; if the pass maximum exceeds the reference by more than the threshold (rare after the first
+        // tiles) O and l are rescaled and tile j is redone -- published P values never exceed 2^threshold.
+        sum_j = exps(0);
+        named_bar_sync(pair_bar, 64);
+        const float m_new = fmaxf(m_used, fmaxf(m_half, xch[xp][t][ch ^ 1][r]));
         TR(slot, j, 3);
         const bool need = (m_new - m_used) * P.scale_log2 > RESCALE_THRESHOLD || (m_used == -INFINITY && m_new > -INFINITY);
         if (__any_sync(0xffffffffu, need)) {
@@ -451,24 +470,43 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
           if (o_waited < j) { mbar_wait(BAR(O_FULL + t), (j - 1) & 1); o_waited = j; }   // PV(j-1) has landed
           tc_fence_after();
           rescale_o48(tm_o, alpha);
-          exps();
+          fetch0();
+          sum_j = exps(0);
         }
       }
-      l += sum0 + sum1;
+      l += sum_j;
       if (stagger && t == 0 && j == 0) asm volatile("bar.arrive 9, 512;" ::: "memory");   // release tile 1
+      // ---- both S buffers go back to the MMA warp: QK^T(j+2), QK^T(j+3) run during the rest of this pass
+      tc_fence_before();
+      mbar_arrive(BAR(S_FREE + 2 * t + (j & 1)));
+      if (two) mbar_arrive(BAR(S_FREE + 2 * t + ((j + 1) & 1)));
       TR(slot, j, 4);
-      // ---- P_t has its own TMEM columns, single-buffered: PV(j-1), issued a whole key tile ago, has consumed P(j-1)
+      // ---- publish P(j): its own TMEM columns, single-buffered -- PV(j-1) has consumed P(j-1)
       if (o_waited < j) {
         if (!o_known) mbar_wait(BAR(O_FULL + t), (j - 1) & 1);
         o_waited = j;
       }
       TR(slot, j, 5);
-      tmem_st_x16(tm_p, pk);
-      // probe S_FULL of the next key tile while the P store drains
-      s_ready = (j + 1 < nk) && mbar_test(BAR(S_FULL + 2 * t + ((j + 1) & 1)), ((j + 1) >> 1) & 1);
+      tmem_st_x16(tm_p, reinterpret_cast<const uint32_t*>(s));
       tmem_wait_st();
       tc_fence_before();
       mbar_arrive(BAR(P_FULL + t));
+      if (two) {
+        // ---- tile j+1 while PV(j) runs, then P(j+1) into the same columns
+        l += exps(32);
+        mbar_wait(BAR(O_FULL + t), j & 1);
+        o_waited = j + 1;
+        tc_fence_after();
+        tmem_st_x16(tm_p, reinterpret_cast<const uint32_t*>(s) + 32);
+      }
+      // probe S_FULL of the next pass while the P store drains
+      s_ready0 = (j + 2 < nk) && mbar_test(BAR(S_FULL + 2 * t + (j & 1)), ((j + 2) >> 1) & 1);
+      s_ready1 = (j + 3 < nk) && mbar_test(BAR(S_FULL + 2 * t + ((j + 1) & 1)), ((j + 3) >> 1) & 1);
+      if (two) {
+        tmem_wait_st();
+        tc_fence_before();
+        mbar_arrive(BAR(P_FULL + t));
+      }
       TR(slot, j, 6);
     }
 
@@ -476,10 +514,11 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
     if (qt < P.n_qt) {
       float inv_l = 0.f;
       if (nk > 0) {
-        // total row sum = sum of the two halves
-        xch[nk & 1][t][ch][r] = l;
+        // total row sum = sum of the two halves (the exchange buffer the last pass did not use)
+        const int xe = (((nk - 1) >> 1) + 1) & 1;
+        xch[xe][t][ch][r] = l;
         named_bar_sync(pair_bar, 64);
-        l += xch[nk & 1][t][ch ^ 1][r];
+        l += xch[xe][t][ch ^ 1][r];
         mbar_wait(BAR(O_FULL + t), (nk - 1) & 1);
         tc_fence_after();
         inv_l = (row_live && l > 0.f) ? 1.f / l : 0.f;  // batch-padding rows: zeros
