@@ -10,8 +10,9 @@
 //
 // CTA = 2 query tiles x 128 rows of one (batch, head), key tiles of 64; 20 warps:
 //   warp 0      TMA producer (Q once, then K_j / V_j through two 4-deep rings of 12 KB tiles)
-//   warp 1 / 3  MMA issuers of query tile 0 / 1: S_t[j&1] = Q_t K_j^T (SS, N=64), O_t += P_t V_j (TS, P read from TMEM)
-//   warp 2      TMEM allocator;   warp 3 first finds the first key tile that holds padding
+//   warp 1 / 3  QK^T issuers of query tile 0 / 1: S_t[j&1] = Q_t K_j^T (SS, N=64)
+//   warp 2      TMEM allocator, then PV issuer of both tiles: O_t += P_t V_j (TS, P read from TMEM); polls both P_FULL
+//   (warp 3 first finds the first key tile that holds padding)
 //   warps 4-19  softmax: warp = (tile t, column half c, lane group g); thread <-> row 32g+lane <-> TMEM lane,
 //               32 of the 64 key columns.  FOUR softmax warps per SM sub-partition: ncu on the 2-warp layout showed
 //               the exp2 pipe 47% busy because one warp's fixed latencies (mbarrier probes, TMEM round trips, max
@@ -212,21 +213,23 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
         for (int a = 0; a < 3; ++a)
           tma_load_4d(smem_base + SMEM_V + s * KV_TILE + a * KV_ATOM, &map_v, BAR(V_FULL + s), a * 32, j * BN, h, b);
       };
-      // consumption order of the MMA warp: K0 K1 | V0 K2 | V1 K3 | ...
+      // consumption order of the MMA warps (two key tiles per pass): K0 K1 | K2 K3 V0 V1 | K4 K5 V2 V3 | ...
       if (n_max > 0) load_k(0);
       if (n_max > 1) load_k(1);
-      for (int j = 0; j < n_max; ++j) {
-        load_v(j);
+      for (int j = 0; j < n_max; j += 2) {
         if (j + 2 < n_max) load_k(j + 2);
+        if (j + 3 < n_max) load_k(j + 3);
+        load_v(j);
+        if (j + 1 < n_max) load_v(j + 1);
       }
     }
   } else if (warp == 1 || warp == 3) {
-    // ------------------------------------------------------------------ MMA issuers: warp 1 -> query tile 0, warp 3 -> tile 1
-    // One issuing warp per query tile: a single thread streams M=128,K=16 MMAs at ~64-80 cycles each whatever N is
-    // (tools/mma_mix_bench.cu: this step costs 1267 cycles from one thread, 925 from two).  The whole warp runs the
-    // loop so that addresses / descriptors stay in uniform registers; one elected lane issues.  Every K / V stage is
-    // released by one arrival from each warp: a commit behind the MMA that read it, or a plain arrive when this
-    // tile does not visit that key tile.
+    // ------------------------------------------------------------------ QK^T issuers: warp 1 -> query tile 0, warp 3 -> tile 1
+    // An issuing thread streams M=128,K=16 MMAs at ~64-80 cycles each whatever N is (tools/mma_mix_bench.cu), so the
+    // MMA work is spread over three warps: one QK^T issuer per query tile and one PV issuer (warp 2).  The whole warp
+    // runs the loop so that addresses / descriptors stay in uniform registers; one elected lane issues.  Every K / V
+    // stage is released by one arrival per query tile: a commit behind the MMA that read it, or a plain arrive when
+    // that tile does not visit the key tile.
     setmaxnreg_dec<REGS_CTRL>();
     const int t = (warp == 3) ? 1 : 0;
     const int nk = t ? n_kv1 : n_kv0;
@@ -235,16 +238,11 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
     const bool tracing = P.trace && (int)blockIdx.x == P.trace_cta && leader;
 #endif
     constexpr uint32_t IDESC_QK = umma_idesc_bf16(BM, BN, 0, 0);
-    constexpr uint32_t IDESC_PV = umma_idesc_bf16(BM, HD, 0, 1);
-    // descriptors differ only in the 14-bit start-address field (units of 16 B) of the low word
     const uint64_t DESC_KMAJ = umma_smem_desc(0, 16, 512, UMMA_SW64);
-    const uint64_t DESC_V = umma_smem_desc(0, KV_ATOM, 512, UMMA_SW64);     // MN-major: LBO = atom stride
-    const uint32_t HI = (uint32_t)(DESC_KMAJ >> 32);                         // identical for both forms
-    const uint32_t KMAJ_LO = (uint32_t)DESC_KMAJ, V_LO = (uint32_t)DESC_V;
-    const uint32_t qa = KMAJ_LO + ((smem_base + SMEM_Q + t * Q_TILE) >> 4), k_lo = KMAJ_LO + ((smem_base + SMEM_K) >> 4),
-                   v_lo = V_LO + ((smem_base + SMEM_V) >> 4);
-    const uint32_t d_o = tmem + TM_O + 96 * t, a_p = tmem + TM_P + 32 * t;
-    auto k_use = [&](int j) {        // S_t[j&1] = Q_t K_j^T, then this warp's release of the K stage
+    const uint32_t HI = (uint32_t)(DESC_KMAJ >> 32), KMAJ_LO = (uint32_t)DESC_KMAJ;
+    const uint32_t qa = KMAJ_LO + ((smem_base + SMEM_Q + t * Q_TILE) >> 4), k_lo = KMAJ_LO + ((smem_base + SMEM_K) >> 4);
+    if (nk > 0) mbar_wait(BAR((ROPE ? Q_READY : Q_FULL) + t), 0);
+    for (int j = 0; j < n_max; ++j) {       // S_t[j&1] = Q_t K_j^T as soon as K_j has landed and the buffer is free
       const int s = j % STAGES;
       mbar_wait(BAR(K_FULL + s), (j / STAGES) & 1);
       if (j < nk) {
@@ -266,37 +264,51 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
         mbar_arrive(BAR(K_EMPTY + s));
       }
       __syncwarp();
-    };
-    auto v_use = [&](int j) {        // O_t += P_t V_j, then this warp's release of the V stage
-      const int s = j % STAGES;
-      mbar_wait(BAR(V_FULL + s), (j / STAGES) & 1);
-      if (j < nk) {
-        TR(4 + t, j, 2);
-        mbar_wait(BAR(P_FULL + t), j & 1);
-        tc_fence_after();
-        TR(4 + t, j, 3);
-        const uint32_t va = v_lo + s * (KV_TILE >> 4);
-        if (leader) {
-#pragma unroll
-          for (int k = 0; k < 4; ++k) umma_ts_lh(d_o, a_p + 8 * k, va + k * 64, HI, IDESC_PV, (j > 0 || k > 0));
-          umma_commit(BAR(O_FULL + t));
-          umma_commit(BAR(V_EMPTY + s));
-        }
-        TR(4 + t, j, 4);
-      } else if (leader) {
-        mbar_arrive(BAR(V_EMPTY + s));
-      }
-      __syncwarp();
-    };
-    if (nk > 0) mbar_wait(BAR((ROPE ? Q_READY : Q_FULL) + t), 0);
-    if (n_max > 0) k_use(0);
-    if (n_max > 1) k_use(1);
-    for (int j = 0; j < n_max; ++j) {
-      if (j + 2 < n_max) k_use(j + 2);   // QK^T two key tiles ahead: in flight a whole key tile before its scores are fetched
-      v_use(j);
     }
   } else if (warp == 2) {
+    // ------------------------------------------------------------------ PV issuer of both query tiles
+    // O_t += P_t V_j (TS, P read from TMEM).  Polls the two tiles' P_FULL barriers and serves whichever is ready, so
+    // neither tile waits behind the other; tiles that do not visit key tile j just release the V stage.
     setmaxnreg_dec<REGS_CTRL>();
+    const bool leader = elect_one();
+#ifdef AKI_FWD_TRACE
+    const bool tracing = P.trace && (int)blockIdx.x == P.trace_cta && leader;
+#endif
+    constexpr uint32_t IDESC_PV = umma_idesc_bf16(BM, HD, 0, 1);
+    const uint64_t DESC_V = umma_smem_desc(0, KV_ATOM, 512, UMMA_SW64);     // MN-major: LBO = atom stride
+    const uint32_t HI = (uint32_t)(DESC_V >> 32), v_lo = (uint32_t)DESC_V + ((smem_base + SMEM_V) >> 4);
+    int jt[2] = {0, 0};
+    while (jt[0] < n_max || jt[1] < n_max) {
+      bool progressed = false;
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        const int j = jt[t];
+        if (j >= n_max) continue;
+        const int nk = t ? n_kv1 : n_kv0;
+        const int s = j % STAGES;
+        if (!mbar_test(BAR(V_FULL + s), (j / STAGES) & 1)) continue;
+        if (j < nk) {
+          if (!mbar_test(BAR(P_FULL + t), j & 1)) continue;
+          tc_fence_after();
+          TR(4 + t, j, 3);
+          const uint32_t va = v_lo + s * (KV_TILE >> 4);
+          const uint32_t d_o = tmem + TM_O + 96 * t, a_p = tmem + TM_P + 32 * t;
+          if (leader) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_ts_lh(d_o, a_p + 8 * k, va + k * 64, HI, IDESC_PV, (j > 0 || k > 0));
+            umma_commit(BAR(O_FULL + t));
+            umma_commit(BAR(V_EMPTY + s));
+          }
+          TR(4 + t, j, 4);
+        } else if (leader) {
+          mbar_arrive(BAR(V_EMPTY + s));
+        }
+        __syncwarp();
+        jt[t] = j + 1;
+        progressed = true;
+      }
+      if (!progressed) __nanosleep(32);
+    }
   } else {
     // ------------------------------------------------------------------ softmax / correction / epilogue
     setmaxnreg_inc<REGS_SOFTMAX>();
