@@ -66,6 +66,9 @@ _SIGNATURES = {
     "aki_mma_rope_kv_write": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_int,
                                         C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64,
                                         C.c_int, C.c_void_p, C.c_void_p]),
+    "aki_mma_rope_kv_write_dev": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_int,
+                                            C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64,
+                                            C.c_void_p, C.c_void_p, C.c_void_p]),
     "aki_mma_attn_fwd": (C.c_int, [C.POINTER(AttnParams), C.c_void_p]),
     "aki_mma_attn_bwd": (C.c_int, [C.POINTER(AttnBwdParams), C.c_void_p]),
     "aki_mma_attn_bwd_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),

@@ -71,6 +71,14 @@ class AkiMMAAttention(nn.Module):
             o, _, _ = ops.attn_packed_op(qkv, cos, sin, H, self.scaling, *(meta or ()))
         elif isinstance(past_key_values, AkiKVCache):
             cache = past_key_values
+            if T == 1 and cache.device_driven:
+                # CUDA-graph decode step: write row and key count come from device memory, nothing host-dependent
+                q_rot = torch.empty(B, H, 1, D, dtype=torch.bfloat16, device=qkv.device)
+                ops.rope_kv_write(qkv, cos, sin, cache.k[self.layer_idx], cache.v[self.layer_idx], 0, H, q_rot=q_rot,
+                                  past_len_dev=cache.past_dev)
+                o = ops.decode_op(q_rot.view(B, H, D), cache.k[self.layer_idx], cache.v[self.layer_idx], cache.kv_len,
+                                  cache.t_cap, self.scaling).view(B, 1, H * D)
+                return self.o_proj(o), None
             past = cache.reserve(self.layer_idx, T)
             if T == 1 and past > 0:
                 q_rot = torch.empty(B, H, 1, D, dtype=torch.bfloat16, device=qkv.device)

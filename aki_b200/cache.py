@@ -19,6 +19,9 @@ class AkiKVCache:
         self.v: List[torch.Tensor] = [torch.zeros_like(self.k[0]) for _ in range(num_layers)]
         self._len = [0] * num_layers
         self.kv_len = torch.zeros(batch, dtype=torch.int32, device=device)   # device copy for the decode kernel
+        # CUDA-graph decode: the step reads the write row / key count from these device tensors instead of host ints
+        self.past_dev = torch.zeros(batch, dtype=torch.int32, device=device)
+        self.device_driven = False
 
     # ---- HF Cache surface --------------------------------------------------------------------------
     def get_seq_length(self, layer_idx: int = 0) -> int:
@@ -63,10 +66,16 @@ class AkiKVCache:
         if need > self.t_cap:
             raise ValueError(f"KV cache capacity {self.t_cap} exceeded (need {need})")
 
+    def advance_host(self, t: int = 1) -> None:
+        """Host-side bookkeeping after a device-driven (graph-replayed) step appended t rows to every layer."""
+        self._check(self._len[0] + t)
+        self._len = [n + t for n in self._len]
+
     def reset(self) -> None:
         """Forget the contents (buffers are reused; nothing is freed)."""
         self._len = [0] * len(self.k)
         self.kv_len.zero_()
+        self.past_dev.zero_()
 
     def to_legacy_cache(self):
         return tuple(self[i] for i in range(len(self.k)))

@@ -57,9 +57,11 @@ __global__ void __launch_bounds__(192)
 rope_kv_write_kernel(const __nv_bfloat16* __restrict__ qkv, int64_t qkv_stride_b, int64_t qkv_stride_t,
                      const float* __restrict__ cos_t, const float* __restrict__ sin_t, int64_t rope_stride_b, int T,
                      int H, __nv_bfloat16* __restrict__ k_cache, __nv_bfloat16* __restrict__ v_cache,
-                     int64_t cache_stride_b, int64_t cache_stride_h, int past_len, __nv_bfloat16* __restrict__ q_rot) {
+                     int64_t cache_stride_b, int64_t cache_stride_h, int past_len_host,
+                     const int32_t* __restrict__ past_len_dev, __nv_bfloat16* __restrict__ q_rot) {
   constexpr int D = 96, HALF = 48;
   const int t = blockIdx.x, b = blockIdx.y;
+  const int past_len = past_len_dev ? past_len_dev[b] : past_len_host;   // device-resident length: CUDA-graph decode
   const float* cr = cos_t + (size_t)b * rope_stride_b + (size_t)t * HALF;
   const float* sr = sin_t + (size_t)b * rope_stride_b + (size_t)t * HALF;
   const __nv_bfloat16* row = qkv + (size_t)b * qkv_stride_b + (size_t)t * qkv_stride_t;
@@ -108,10 +110,10 @@ extern "C" int aki_mma_rope_table(const int64_t* position_ids, const float* inv_
   return check_launch();
 }
 
-extern "C" int aki_mma_rope_kv_write(const void* qkv, int64_t qkv_stride_b, int64_t qkv_stride_t, const float* cos,
-                                     const float* sin, int64_t rope_stride_b, int B, int T, int H, int D,
-                                     void* k_cache, void* v_cache, int64_t cache_stride_b, int64_t cache_stride_h,
-                                     int past_len, void* q_rot, aki_stream_t stream) {
+static int rope_kv_write_impl(const void* qkv, int64_t qkv_stride_b, int64_t qkv_stride_t, const float* cos,
+                              const float* sin, int64_t rope_stride_b, int B, int T, int H, int D, void* k_cache,
+                              void* v_cache, int64_t cache_stride_b, int64_t cache_stride_h, int past_len,
+                              const int32_t* past_len_dev, void* q_rot, aki_stream_t stream) {
   AKI_REQUIRE(qkv && cos && sin && k_cache, AKI_ERR_NULL);
   AKI_REQUIRE(B > 0 && T > 0 && H > 0 && past_len >= 0 && B <= 65535, AKI_ERR_BAD_SHAPE);
   AKI_REQUIRE(D == AKI_MMA_HEAD_DIM, AKI_ERR_UNSUPPORTED);
@@ -123,6 +125,23 @@ extern "C" int aki_mma_rope_kv_write(const void* qkv, int64_t qkv_stride_b, int6
   rope_kv_write_kernel<<<dim3(T, B), 192, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(qkv), qkv_stride_b, qkv_stride_t, cos, sin, rope_stride_b, T, H,
       static_cast<__nv_bfloat16*>(k_cache), static_cast<__nv_bfloat16*>(v_cache), cache_stride_b, cache_stride_h,
-      past_len, static_cast<__nv_bfloat16*>(q_rot));
+      past_len, past_len_dev, static_cast<__nv_bfloat16*>(q_rot));
   return check_launch();
+}
+
+extern "C" int aki_mma_rope_kv_write(const void* qkv, int64_t qkv_stride_b, int64_t qkv_stride_t, const float* cos,
+                                     const float* sin, int64_t rope_stride_b, int B, int T, int H, int D,
+                                     void* k_cache, void* v_cache, int64_t cache_stride_b, int64_t cache_stride_h,
+                                     int past_len, void* q_rot, aki_stream_t stream) {
+  return rope_kv_write_impl(qkv, qkv_stride_b, qkv_stride_t, cos, sin, rope_stride_b, B, T, H, D, k_cache, v_cache,
+                            cache_stride_b, cache_stride_h, past_len, nullptr, q_rot, stream);
+}
+
+extern "C" int aki_mma_rope_kv_write_dev(const void* qkv, int64_t qkv_stride_b, int64_t qkv_stride_t, const float* cos,
+                                         const float* sin, int64_t rope_stride_b, int B, int T, int H, int D,
+                                         void* k_cache, void* v_cache, int64_t cache_stride_b, int64_t cache_stride_h,
+                                         const int32_t* past_len_dev, void* q_rot, aki_stream_t stream) {
+  AKI_REQUIRE(past_len_dev, AKI_ERR_NULL);
+  return rope_kv_write_impl(qkv, qkv_stride_b, qkv_stride_t, cos, sin, rope_stride_b, B, T, H, D, k_cache, v_cache,
+                            cache_stride_b, cache_stride_h, 0, past_len_dev, q_rot, stream);
 }

@@ -75,6 +75,59 @@ class AkiPhi3Runner(nn.Module):
         h = self._run_layers(h, cos, sin, None, cache)
         return self.lm.lm_head(h)
 
+    # ---- CUDA-graph decode ("next" row f-4 of SURVEY 8): the whole 32-layer step is one graph launch -----------------
+    @torch.no_grad()
+    def _graph_body(self, cache: AkiKVCache):
+        st = self._g
+        cache.kv_len.copy_(cache.past_dev + 1)                       # keys visible to this step (incl. the new one)
+        st["pos"].copy_(cache.past_dev[:1].to(torch.int64).view(1, 1))   # position id = past length (aki_generation.py:72-84)
+        h = self.lm.model.embed_tokens(st["tok"])
+        inv = self.rope.inv_freq_long if st["long"] else self.rope.inv_freq_short
+        cos, sin = ops.rope_table(st["pos"], inv, self.rope.attention_factor)
+        h = self._run_layers(h, cos, sin, None, cache)
+        st["next"].copy_(self.lm.lm_head(h)[:, -1].argmax(-1, keepdim=True))
+        cache.past_dev.add_(1)
+
+    @torch.no_grad()
+    def decode_step_graphed(self, token_ids: torch.Tensor, cache: AkiKVCache) -> torch.Tensor:
+        """Greedy decode step replayed from a CUDA graph: returns the next token ids (B,1).  The graph is captured on
+        first use for this cache; the write row, the key count and the position id live in device memory
+        (cache.past_dev), so replays need no host-side arguments.  The longrope factor set (short / long) is fixed at
+        capture from the cache capacity (the reference re-selects it from the running maximum position)."""
+        past = cache.get_seq_length()
+        g = getattr(self, "_g", None)
+        if g is None or g["cache"] is not cache:
+            B = token_ids.shape[0]
+            dev = token_ids.device
+            self._g = g = {"cache": cache, "tok": token_ids.clone(), "next": torch.zeros(B, 1, dtype=torch.int64, device=dev),
+                           "pos": torch.zeros(1, 1, dtype=torch.int64, device=dev),
+                           "long": cache.t_cap > self.rope.original_max, "graph": None}
+            cache.device_driven = True
+            cache.past_dev.fill_(past)
+            keep = (cache.past_dev.clone(), [k[:, :, past:past + 3].clone() for k in cache.k],
+                    [v[:, :, past:past + 3].clone() for v in cache.v])
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):                                   # warm-up outside capture (lazy inits, autotune)
+                    self._graph_body(cache)
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                self._graph_body(cache)
+            g["graph"] = graph
+            # undo the side effects of warm-up + capture: three rows written past the end, counters advanced
+            cache.past_dev.copy_(keep[0])
+            for k, v, k0, v0 in zip(cache.k, cache.v, keep[1], keep[2]):
+                k[:, :, past:past + 3].copy_(k0); v[:, :, past:past + 3].copy_(v0)
+        else:
+            cache.device_driven = True
+        g["tok"].copy_(token_ids)
+        g["graph"].replay()
+        cache.advance_host(1)
+        cache.device_driven = False
+        return g["next"].clone()
+
     @torch.no_grad()
     def generate(self, inputs_embeds, segs, max_new_tokens: int, t_cap: Optional[int] = None):
         B, T, _ = inputs_embeds.shape

@@ -211,13 +211,22 @@ def rope_table(position_ids: torch.Tensor, inv_freq: torch.Tensor, attention_fac
 
 
 def rope_kv_write(qkv: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor, k_cache: torch.Tensor,
-                  v_cache: Optional[torch.Tensor], past_len: int, num_heads: int, q_rot: Optional[torch.Tensor] = None):
-    """qkv (B,T,3*H*D) bf16 -> K (post-RoPE) / V rows [past_len, past_len+T) of (B,H,t_cap,D) caches."""
-    _require_cuda(qkv, cos, sin, k_cache, v_cache, q_rot)
+                  v_cache: Optional[torch.Tensor], past_len: int, num_heads: int, q_rot: Optional[torch.Tensor] = None,
+                  past_len_dev: Optional[torch.Tensor] = None):
+    """qkv (B,T,3*H*D) bf16 -> K (post-RoPE) / V rows [past_len, past_len+T) of (B,H,t_cap,D) caches.
+    past_len_dev (B,) int32 on the device replaces the host integer (CUDA-graph decode)."""
+    _require_cuda(qkv, cos, sin, k_cache, v_cache, q_rot, past_len_dev)
     B, T, _ = qkv.shape
     if qkv.stride(2) != 1:
         qkv = qkv.contiguous()
     rope_sb = 0 if cos.shape[0] == 1 else cos.stride(0)
+    if past_len_dev is not None:
+        assert past_len_dev.dtype == torch.int32 and past_len_dev.numel() == B
+        check(lib.aki_mma_rope_kv_write_dev(_ptr(qkv), qkv.stride(0), qkv.stride(1), _ptr(cos), _ptr(sin), rope_sb, B, T,
+                                            num_heads, HEAD_DIM, _ptr(k_cache), _ptr(v_cache), k_cache.stride(0),
+                                            k_cache.stride(1), _ptr(past_len_dev), _ptr(q_rot), _stream()),
+              "aki_mma_rope_kv_write_dev")
+        return
     check(lib.aki_mma_rope_kv_write(_ptr(qkv), qkv.stride(0), qkv.stride(1), _ptr(cos), _ptr(sin), rope_sb, B, T,
                                     num_heads, HEAD_DIM, _ptr(k_cache), _ptr(v_cache), k_cache.stride(0),
                                     k_cache.stride(1), int(past_len), _ptr(q_rot), _stream()), "aki_mma_rope_kv_write")

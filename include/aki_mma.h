@@ -117,6 +117,13 @@ int aki_mma_rope_kv_write(const void* qkv, int64_t qkv_stride_b, int64_t qkv_str
                           const float* sin, int64_t rope_stride_b, int B, int T, int H, int D, void* k_cache,
                           void* v_cache, int64_t cache_stride_b, int64_t cache_stride_h, int past_len, void* q_rot,
                           aki_stream_t stream);
+/* Same, with the past length read from DEVICE memory (past_len_dev (B) int32, one per sequence): the decode step can
+ * then be captured in a CUDA graph and replayed while the cache grows (aki_generation.py:72-84 derives the position
+ * from past_key_values[0][0].shape[2] on the host every step). */
+int aki_mma_rope_kv_write_dev(const void* qkv, int64_t qkv_stride_b, int64_t qkv_stride_t, const float* cos,
+                              const float* sin, int64_t rope_stride_b, int B, int T, int H, int D, void* k_cache,
+                              void* v_cache, int64_t cache_stride_b, int64_t cache_stride_h,
+                              const int32_t* past_len_dev, void* q_rot, aki_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------
  * (4) Attention core -- replaces the eager path of Phi3Attention.forward: QK^T/sqrt(D) + additive mask,

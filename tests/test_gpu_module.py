@@ -246,3 +246,34 @@ def test_trainable_splice_gradient_matches_torch_cat_reference():
     (ref.float() * w.float()).sum().backward()
     assert torch.allclose(emb.grad.float(), emb_r.grad.float(), atol=1e-6)
     assert torch.allclose(vis.grad.float(), vis_r.grad.float(), atol=1e-6)
+
+
+@pytest.mark.gpu
+def test_cuda_graph_decode_equals_eager_decode():
+    """The graph-replayed decode step (device-resident write row / key count / position) must produce the same tokens
+    and the same cache contents as the host-driven step (aki_generation.py:72-84 semantics)."""
+    import aki_b200
+    from aki_b200.model import AkiPhi3Runner, phi35_mini_config
+    dev = torch.device("cuda", 0)
+    runner = AkiPhi3Runner(phi35_mini_config(num_layers=2), device=dev, seed=0)
+    B, T, n_new = 2, 70, 6
+    emb = (torch.randn(B, T, 3072, generator=torch.Generator().manual_seed(1)) * 0.05).to(torch.bfloat16).to(dev)
+    outs, caches = [], []
+    for graphed in (False, True):
+        cache = runner.new_cache(B, T + n_new + 4)
+        logits = runner.prefill(emb, None, cache)
+        tok = logits[:, -1].argmax(-1, keepdim=True)
+        toks = [tok]
+        for _ in range(n_new):
+            if graphed:
+                tok = runner.decode_step_graphed(tok, cache)
+            else:
+                tok = runner.decode_step(tok, cache)[:, -1].argmax(-1, keepdim=True)
+            toks.append(tok)
+        assert cache.get_seq_length() == T + n_new
+        outs.append(torch.cat(toks, 1).cpu()); caches.append(cache)
+    assert torch.equal(outs[0], outs[1])
+    n = T + n_new
+    for l in range(2):
+        assert torch.equal(caches[0].k[l][:, :, :n], caches[1].k[l][:, :, :n])
+        assert torch.equal(caches[0].v[l][:, :, :n], caches[1].v[l][:, :, :n])
