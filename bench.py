@@ -98,17 +98,28 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.samples.append(line.strip())
+            self.samples.append((time.time(), line.strip()))
+
+    def mark_begin(self):
+        """Start of the timed region: the sampler itself is started earlier (nvidia-smi needs up to a second to
+        produce its first line on an 8-GPU box); only samples that arrive inside the marked window are used."""
+        self.t0 = time.time()
 
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        t1 = time.time()
         time.sleep(0.12)
         self.proc.terminate()
         try:
             self.thread.join(timeout=2.0)
         except Exception:
             pass
+        t0 = getattr(self, "t0", 0.0)
+        window = [s for (ts, s) in self.samples if t0 <= ts <= t1 + 0.1]
+        if not window:                      # region shorter than one sampling period: take the nearest samples
+            window = [s for (ts, s) in self.samples][-3:]
+        self.samples = window
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for s in self.samples:
@@ -317,10 +328,11 @@ def sft_main(args, rank, world, local):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)
+    sampler.start()
     for i in range(args.warmup):
         step(i)
-    sampler = ClockSampler(local)
-    barrier(); sampler.start()
+    barrier(); sampler.mark_begin()
     a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
     for i in range(args.steps):
@@ -353,6 +365,9 @@ def sft_main(args, rank, world, local):
 
 # ------------------------------------------------------------------------------------------------ main
 def main():
+    # rank 0 prints exactly ONE line on stdout: keep NCCL's version banner (NCCL_DEBUG=VERSION on some boxes) off it
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO"):
+        os.environ["NCCL_DEBUG_FILE"] = os.environ.get("NCCL_DEBUG_FILE", "/dev/stderr")
     args = parse()
     rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
@@ -434,11 +449,12 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)
+    sampler.start()
     for _ in range(args.warmup):
         step(False)
-    sampler = ClockSampler(local)
     barrier()
-    sampler.start()
+    sampler.mark_begin()
     t_start, t_end = ev(), ev()
     t_start.record()
     for _ in range(args.steps):
