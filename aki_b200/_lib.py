@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libaki_mma.so")
+LIB_PATH = os.environ.get("AKI_MMA_LIB") or os.path.join(_HERE, "libaki_mma.so")   # AKI_MMA_LIB: A/B builds (tools only)
 
 AKI_OK = 0
 HEAD_DIM = 96
