@@ -84,6 +84,10 @@ struct BwdKernelParams {
   int trace_cta;
 };
 
+// -DKO_x (tools/build_bwd_ko.sh) are timing-only knockout builds: each removes one component -- an MMA group (KO_S KO_DP
+// KO_DV KO_DQ KO_DK), the ex2 (KO_EXP), the dS compute + store + proxy fence (KO_DS; KO_FENCE only the fence), the dQ
+// drain (KO_DRAIN; KO_RED only its reductions), the Q/dO loads after the first ring fill (KO_TMA).  Results are wrong by
+// construction; the shipped build defines none of them.
 #ifdef AKI_FWD_TRACE
 #define TRB(slot, j, k) do { if (tracing && (j) < 64) P.trace[((slot) * 64 + (j)) * 8 + (k)] = clock64(); } while (0)
 #else
@@ -215,6 +219,9 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
         const int i0 = (int)qlist[it] * BM;
         const int sq = it % Q_STAGES, sd = it % DO_STAGES;
         mbar_wait(BAR(Q_EMPTY + sq), ((it / Q_STAGES) & 1) ^ 1);
+#ifdef KO_TMA
+        if (it >= Q_STAGES) { mbar_arrive(BAR(Q_FULL + sq)); mbar_wait(BAR(DO_EMPTY + sd), ((it / DO_STAGES) & 1) ^ 1); mbar_arrive(BAR(DO_FULL + sd)); continue; }
+#endif
         mbar_arrive_expect_tx(BAR(Q_FULL + sq), TILE_BYTES + AUG_BYTES);
         for (int a = 0; a < 3; ++a)
           tma_load_4d(smem_base + SMEM_Q + sq * TILE_BYTES + a * ATOM_BYTES, &map_q, BAR(Q_FULL + sq), a * 32, i0, h, b);
@@ -264,9 +271,11 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
         auto issue_s = [&](int it) {
           const uint32_t sQ = smem_base + SMEM_Q + (it % Q_STAGES) * TILE_BYTES;
           const uint32_t sA = smem_base + SMEM_QAUG + (it % Q_STAGES) * AUG_BYTES;
+#ifndef KO_S
 #pragma unroll
           for (int k = 0; k < 6; ++k) umma_ss(tmem + TM_S, kmajor(sK, k), kmajor(sQ, k), IDESC_SS_KK, k > 0);
           umma_ss(tmem + TM_S, DESC_ONES, DESC_AUG | (uint64_t)((sA >> 4) & 0x3FFFu), IDESC_SS_KK, 1);
+#endif
           umma_commit(BAR(S_FULL));
           umma_commit(BAR(Q_EMPTY + it % Q_STAGES));   // this stream's half of the release (the other: dK on B)
         };
@@ -282,9 +291,11 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
           mbar_wait(BAR(P_READY), it & 1);
           tc_fence_after();
           TRB(2, it, 1);
+#ifndef KO_DV
 #pragma unroll
           for (int k = 0; k < 8; ++k)
             umma_ts(tmem + TM_DV, tmem + TM_P + 8 * k, mnmajor(sDO, k), IDESC_N96_BMN, (it > 0 || k > 0));
+#endif
           umma_commit(BAR(DO_EMPTY + it % DO_STAGES));
           TRB(2, it, 2);
           // S^T of the next query tile (the S region is free once P^T(it) has been written to its own columns)
@@ -302,9 +313,11 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
         auto issue_dp = [&](int it) {
           const uint32_t sDO = smem_base + SMEM_DO + (it % DO_STAGES) * TILE_BYTES;
           const uint32_t sA = smem_base + SMEM_QAUG + (it % Q_STAGES) * AUG_BYTES;   // row statistics travel with Q(it)
+#ifndef KO_DP
 #pragma unroll
           for (int k = 0; k < 6; ++k) umma_ss(tmem + TM_DP, kmajor(sV, k), kmajor(sDO, k), IDESC_SS_KK, k > 0);
           umma_ss(tmem + TM_DP, DESC_ONES_D, DESC_AUG | (uint64_t)((sA >> 4) & 0x3FFFu), IDESC_SS_KK, 1);
+#endif
           umma_commit(BAR(DP_FULL));
           umma_commit(BAR(DO_EMPTY + it % DO_STAGES));
         };
@@ -320,13 +333,17 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
           mbar_wait(BAR(DS_READY), it & 1);
           tc_fence_after();
           TRB(3, it, 1);
+#ifndef KO_DQ
 #pragma unroll
           for (int k = 0; k < 8; ++k)
             umma_ss(tmem + TM_DP, mnmajor(sDS, k), mnmajor(sK, k), IDESC_N96_AMN_BMN, k > 0);
+#endif
           umma_commit(BAR(DQ_FULL));
+#ifndef KO_DK
 #pragma unroll
           for (int k = 0; k < 8; ++k)
             umma_ss(tmem + TM_DK, kmajor(sDS, k), mnmajor(sQ, k), IDESC_N96_BMN, (it > 0 || k > 0));
+#endif
           umma_commit(BAR(Q_EMPTY + it % Q_STAGES));
           TRB(3, it, 2);
           // dP^T of the next query tile overwrites the dQ region: wait until it has been drained
@@ -406,8 +423,12 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
       for (int c = 0; c < 64; c += 2) {
         float x0, x1;
         f32x2_mul(x0, x1, __uint_as_float(sraw[c]), __uint_as_float(sraw[c + 1]), P.scale_log2, P.scale_log2);
+#ifdef KO_EXP
+        p[c] = x0; p[c + 1] = x1;
+#else
         p[c] = ex2_approx(x0);
         p[c + 1] = ex2_approx(x1);
+#endif
       }
       if (!full) {
         // c visible iff (c >= cmin, causal) or (row c of the tile is an image row whose interval holds key j)
@@ -468,10 +489,14 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
         }
         const int col = 64 * hq + 8 * c8;          // query column of this chunk
         const uint32_t addr = ds_base + (col >> 5) * ATOM_BYTES + sw64_offset(r, (col & 31) >> 3);
+#ifndef KO_DS
         asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(dsw[4 * c8]), "r"(dsw[4 * c8 + 1]),
                      "r"(dsw[4 * c8 + 2]), "r"(dsw[4 * c8 + 3]));
+#endif
       }
+#if !defined(KO_DS) && !defined(KO_FENCE)
       fence_proxy_async_smem();
+#endif
       tc_fence_before();
       mbar_arrive(BAR(DS_READY));
       TRB(slot, it, 6);
@@ -571,6 +596,10 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
       mbar_wait(BAR(DQ_FULL), it & 1);
       tc_fence_after();
       TRB(4, it, 1);
+#ifdef KO_DRAIN
+      mbar_arrive(BAR(DQ_DRAINED));
+      continue;
+#endif
       uint32_t dq[96];
       tmem_ld_x32(tmem + TM_DP + lane_base, dq);
       tmem_ld_x32(tmem + TM_DP + lane_base + 32, dq + 32);
@@ -594,10 +623,12 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
         }
         fence_proxy_async_smem();
         named_bar_sync(3, 128);
+#ifndef KO_RED
         if (r == 0) {
           tma_reduce_add_4d(&map_dq, abase, 32 * a, i0, h, b);
           tma_store_commit();
         }
+#endif
       }
     }
     TRB(4, n_q - 1, 3);
