@@ -157,7 +157,7 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
     tma_prefetch_desc(&map_dq); tma_prefetch_desc(&map_qaug);
   }
   if (warp == 3) {
-    // list of query tiles to visit, ascending
+    // list of query tiles to visit (first query row of each, ascending)
     const int n_live = (len + BM - 1) / BM;
     const int lane = tid & 31;
     int n = 0;
@@ -180,12 +180,63 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
           while (word) {
             const int bit = __ffs(word) - 1;
             word &= word - 1;
-            qlist[pos++] = (uint16_t)(w * 32 + bit);
+            qlist[pos++] = (uint16_t)((w * 32 + bit) * BM);
           }
           n += __shfl_sync(0xffffffffu, incl, 31);
         }
+        // Visits before the diagonal exist only for image rows (their interval reaches this key tile).  An image span
+        // that straddles two 128-row tiles would cost two visits per key tile; the query tile is only a TMA coordinate,
+        // so such a pair becomes ONE visit of the unaligned tile that starts at the span's first relevant row.
+        __syncwarp();
+        int n_pre = 0;
+        for (int e = lane; e < n; e += 32) n_pre += ((int)qlist[e] < j0) ? 1 : 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) n_pre += __shfl_xor_sync(0xffffffffu, n_pre, o);
+        if (n_pre >= 2 && P.mm.row_lo) {
+          auto relevant = [&](int i) {
+            if (i >= len) return false;
+            const int lo = __ldg(P.mm.row_lo + (size_t)b * P.mm.meta_pitch + i);
+            const int hi = __ldg(P.mm.row_hi + (size_t)b * P.mm.meta_pitch + i);
+            return hi > lo && lo < j0 + BN && hi > j0;
+          };
+          int out = 0, e = 0;
+          while (e < n_pre) {
+            const int a = (int)qlist[e];
+            int i0 = a, step = 1;
+            if (e + 1 < n_pre && (int)qlist[e + 1] == a + BM) {
+              int first = 1 << 30, last = -1;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const int row = 32 * k + lane;
+                if (relevant(a + row)) first = min(first, row);
+                if (relevant(a + BM + row)) last = max(last, row);
+              }
+#pragma unroll
+              for (int o = 16; o > 0; o >>= 1) {
+                first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
+                last = max(last, __shfl_xor_sync(0xffffffffu, last, o));
+              }
+              if (first > 0 && first < BM && last < first) { i0 = a + first; step = 2; }
+            }
+            __syncwarp();
+            if (lane == 0) qlist[out] = (uint16_t)i0;
+            ++out;
+            e += step;
+          }
+          const int shift = n_pre - out;
+          if (shift > 0) {
+            for (int base = n_pre; base < n; base += 32) {
+              const int idx = base + lane;
+              const uint16_t v = (idx < n) ? qlist[idx] : (uint16_t)0;
+              __syncwarp();
+              if (idx < n) qlist[idx - shift] = v;
+              __syncwarp();
+            }
+            n -= shift;
+          }
+        }
       } else {
-        for (int qt = kt + lane; qt < n_live; qt += 32) qlist[qt - kt] = (uint16_t)qt;
+        for (int qt = kt + lane; qt < n_live; qt += 32) qlist[qt - kt] = (uint16_t)(qt * BM);
         n = max(0, n_live - kt);
       }
     }
@@ -216,7 +267,7 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
         tma_load_4d(smem_base + SMEM_V + a * ATOM_BYTES, &map_v, BAR(KV_FULL), a * 32, j0, h, b);
       }
       for (int it = 0; it < n_q; ++it) {
-        const int i0 = (int)qlist[it] * BM;
+        const int i0 = (int)qlist[it];
         const int sq = it % Q_STAGES, sd = it % DO_STAGES;
         mbar_wait(BAR(Q_EMPTY + sq), ((it / Q_STAGES) & 1) ^ 1);
 #ifdef KO_TMA
@@ -368,7 +419,7 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
     for (int it = 0; it < n_q; ++it) {
       const int st = it & 1;
       mbar_wait(BAR(ST_EMPTY + st), ((it >> 1) & 1) ^ 1);
-      const int i0 = (int)qlist[it] * BM;
+      const int i0 = (int)qlist[it];
       int* dst = stats_gen + st * STATS_STAGE_INTS;
       bool rel = false;
 #pragma unroll
@@ -409,8 +460,8 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
 #endif
 
     auto phase_a = [&](int it) {
-      const int qt = (int)qlist[it];
-      const bool full = (qt > kt) && keys_all_valid;     // CTA-uniform
+      const int i0 = (int)qlist[it];
+      const bool full = (i0 >= j0 + BN) && keys_all_valid;     // every query row lies after every key; CTA-uniform
       TRB(slot, it, 0);
       mbar_wait(BAR(S_FULL), it & 1);
       tc_fence_after();
@@ -435,7 +486,7 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
         const int st = it & 1;
         mbar_wait(BAR(ST_FULL + st), (it >> 1) & 1);
         const int* sp = stats_gen + st * STATS_STAGE_INTS;
-        const int cmin = k_valid ? (j - qt * BM - 64 * hq) : (1 << 30);
+        const int cmin = k_valid ? (j - i0 - 64 * hq) : (1 << 30);
         if (sp[256] && k_mutual) {
           const int4* lo4 = reinterpret_cast<const int4*>(sp + 64 * hq);
           const int4* w4 = reinterpret_cast<const int4*>(sp + 128 + 64 * hq);
@@ -591,7 +642,7 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
     const bool tracing = P.trace && (int)blockIdx.x == P.trace_cta && r == 0;
 #endif
     for (int it = 0; it < n_q; ++it) {
-      const int i0 = (int)qlist[it] * BM;
+      const int i0 = (int)qlist[it];
       TRB(4, it, 0);
       mbar_wait(BAR(DQ_FULL), it & 1);
       tc_fence_after();
