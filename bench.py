@@ -47,7 +47,9 @@ def parse():
     ap.add_argument("--workload", default="attn", choices=["attn", "sft"],
                     help="attn: the headline line (+ AKI-4B prefill/decode section); sft: BASELINE config 4, DDP step")
     ap.add_argument("--sft-layers", type=int, default=32)
-    ap.add_argument("--sft-fp32-reduce", action="store_true", help="all-reduce gradients in fp32 instead of bf16")
+    ap.add_argument("--sft-bf16-reduce", action="store_true",
+                    help="all-reduce gradients in bf16 (DDP compress hook) instead of fp32; measured SLOWER on 2 B200s over "
+                         "NVLink (158.3 vs 145.4 ms per step: the casts cost more than the halved transfer saves)")
     ap.add_argument("--seq", type=int, default=8192)
     ap.add_argument("--batch", type=int, default=2)
     ap.add_argument("--images", type=int, default=4)
@@ -295,9 +297,9 @@ def sft_main(args, rank, world, local):
     model = AkiPhi3SFT(phi35_mini_config(num_layers=args.sft_layers), device=dev, seed=0)
     n_params = sum(p.numel() for p in model.parameters())
     net = DDP(model, device_ids=[local], gradient_as_bucket_view=True) if world > 1 else model
-    if world > 1 and not args.sft_fp32_reduce:
+    if world > 1 and args.sft_bf16_reduce:
         # gradients cross NVLink in bf16, as the reference's FSDP mixed-precision config reduces them
-        # (train/distributed.py:163-167); halves the 15.3 GB fp32 all-reduce
+        # (train/distributed.py:163-167); halves the 15.3 GB fp32 all-reduce but adds two cast passes per bucket
         from torch.distributed.algorithms.ddp_comm_hooks import default_hooks
         net.register_comm_hook(None, default_hooks.bf16_compress_hook)
     opt = torch.optim.AdamW(model.parameters(), lr=2e-5, weight_decay=1e-4, fused=True)
@@ -354,8 +356,8 @@ def sft_main(args, rank, world, local):
                                    f"init) B={Bp}/gpu L={L} 1 image x {N} -> T={T}, AdamW(fused), clip 1.0, host batches "
                                    "copied in and loss read back every step",
                        "parallelism": f"DDP x{world} (NCCL gradient all-reduce, "
-                                      f"{n_params * (4 if args.sft_fp32_reduce else 2) / 1e9:.1f} GB "
-                                      f"{'fp32' if args.sft_fp32_reduce else 'bf16'} per step)"},
+                                      f"{n_params * (2 if args.sft_bf16_reduce else 4) / 1e9:.1f} GB "
+                                      f"{'bf16' if args.sft_bf16_reduce else 'fp32'} per step)"},
             "loss": float(host_loss[0]), "clocks": clocks,
             "e2e": {"value": world * Bp * T / (ms * 1e-3), "unit": "tokens/s",
                     "h2d_bytes_per_step": int(Bp * L * 8 * 3 + Bp * N * 3072 * 2), "d2h_bytes_per_step": 4}}))
@@ -366,8 +368,8 @@ def sft_main(args, rank, world, local):
 # ------------------------------------------------------------------------------------------------ main
 def main():
     # rank 0 prints exactly ONE line on stdout: keep NCCL's version banner (NCCL_DEBUG=VERSION on some boxes) off it
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO"):
-        os.environ["NCCL_DEBUG_FILE"] = os.environ.get("NCCL_DEBUG_FILE", "/dev/stderr")
+    # (set unconditionally: the level can also come from /etc/nccl.conf, where the environment does not show it)
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     args = parse()
     rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
