@@ -1,6 +1,6 @@
 """bench.py -- headline benchmark of the MMA hot path (BASELINE.json: "MMA attn fwd+bwd TFLOP/s vs BF16 peak").
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload attn|prefill]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload attn|sft|longctx]
 
 Workload (config.workload): BASELINE config 3 at the north-star point -- T=8192 context, B=2 per GPU, 32 heads x 96,
 4 interleaved image spans of 128 vision tokens, <|assistant|> 64 tokens before the end, Phi-3 longrope on Q/K,
@@ -44,7 +44,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="attn", choices=["attn", "sft"],
+    ap.add_argument("--workload", default="attn", choices=["attn", "sft", "longctx"],
                     help="attn: the headline line (+ AKI-4B prefill/decode section); sft: BASELINE config 4, DDP step")
     ap.add_argument("--sft-layers", type=int, default=32)
     ap.add_argument("--sft-bf16-reduce", action="store_true",
@@ -174,28 +174,35 @@ def cpu_reference_run(T, B, n_img, steps, warmup, threads=None):
 
 
 # ------------------------------------------------------------------------------------------------ AKI-4B prefill
-def prefill_section(dev, rank, world, steps, warmup):
+def prefill_section(dev, rank, world, steps, warmup, longctx=None):
     """BASELINE config 2: random-init AKI-4B language model (Phi-3.5-mini geometry, 32 layers, bf16), batch 8 per
     GPU, 1 image (144 vision tokens, AKI default) + 511 text tokens -> T = 655; prefill writes the KV cache in place,
     then 32 greedy decode steps.  LM only: the vision tower is replaced by N(0,0.02) vision tokens.
-    e2e: host token ids + host vision tokens -> device -> segments + splice kernels -> prefill -> argmax -> host."""
+    e2e: host token ids + host vision tokens -> device -> segments + splice kernels -> prefill -> argmax -> host.
+    longctx=(B, T, n_img, n_dec): BASELINE config 5 instead -- n_img x 128 image tokens interleaved in a T-token
+    context (the prompt of the attention benchmark), then n_dec greedy decode steps against the long cache."""
     import aki_b200
     from aki_b200 import ops
     from aki_b200.model import AkiPhi3Runner, phi35_mini_config
     import torch.distributed as dist
-    B, L, N = parse().prefill_batch, 512, 144
-    g = np.random.default_rng(100 + rank)
-    lang = g.integers(3, 31000, size=(B, L)).astype(np.int64)
-    lang[:, 8] = MEDIA_ID; lang[:, L - 40] = ASST_ID
-    am = np.ones_like(lang)
-    T = L - 1 + N
+    if longctx:
+        B, T, n_img, n_dec = longctx
+        N = N_VIS
+        lang, am = make_prompt(B, T, n_img, seed=100 + rank)
+        L = lang.shape[1]
+    else:
+        B, L, N, n_img, n_dec = parse().prefill_batch, 512, 144, 1, 32
+        g = np.random.default_rng(100 + rank)
+        lang = g.integers(3, 31000, size=(B, L)).astype(np.int64)
+        lang[:, 8] = MEDIA_ID; lang[:, L - 40] = ASST_ID
+        am = np.ones_like(lang)
+        T = L - 1 + N
     runner = AkiPhi3Runner(phi35_mini_config(), device=dev, seed=0)
     host_ids = torch.from_numpy(lang).pin_memory(); host_am = torch.from_numpy(am).pin_memory()
-    host_vis = (torch.randn(B, 1, N, 3072) * 0.02).to(torch.bfloat16).pin_memory()
+    host_vis = (torch.randn(B, n_img, N, 3072) * 0.02).to(torch.bfloat16).pin_memory()
     host_out = torch.empty(B, dtype=torch.int64).pin_memory()
     me = type("M", (), {})()
     me.lang_model = runner.lm; me.media_token_id = MEDIA_ID; me.num_tokens_per_vis = N; me.pad_token_id = 32000
-    n_dec = 32
     cache = runner.new_cache(B, T + n_dec + 1)
     ev = lambda: torch.cuda.Event(enable_timing=True)
 
@@ -234,7 +241,7 @@ def prefill_section(dev, rank, world, steps, warmup):
         b_.record()
         barrier()
         res[name] = a.elapsed_time(b_) / n
-    # decode: 32 steps on top of the last prefill
+    # decode: n_dec steps on top of the last prefill
     logits = prefill_resident()
     tok = logits[:, -1].argmax(-1, keepdim=True)
     for _ in range(3):
@@ -248,7 +255,7 @@ def prefill_section(dev, rank, world, steps, warmup):
     b_.record()
     barrier()
     dec_eager_ms = a.elapsed_time(b_) / n_dec
-    # the same 32 steps replayed from a CUDA graph (device-resident write row / key count / position id)
+    # the same steps replayed from a CUDA graph (device-resident write row / key count / position id)
     cache.reset(); logits = prefill_resident()
     tok = logits[:, -1].argmax(-1, keepdim=True)
     tok = runner.decode_step_graphed(tok, cache)          # captures the graph
@@ -268,14 +275,16 @@ def prefill_section(dev, rank, world, steps, warmup):
     del runner, cache
     torch.cuda.empty_cache()
     return {"workload": f"AKI-4B LM (Phi-3.5-mini geometry, 32 layers, random init, bf16) prefill B={B}/gpu T={T} "
-                        f"(1 image x {N} + {L - 1} text), KV cache written in place, last-token logits",
+                        f"({n_img} image(s) x {N} + {L - n_img} text), KV cache written in place, last-token logits; "
+                        f"{n_dec} greedy decode steps",
             "prefill_tokens_per_s": world * B * T / (r_ms * 1e-3), "prefill_ms": r_ms,
             "prefill_e2e_tokens_per_s": world * B * T / (e_ms * 1e-3), "prefill_e2e_ms": e_ms,
             "e2e_h2d_bytes": int(host_ids.numel() * 8 * 2 + host_vis.numel() * 2), "e2e_d2h_bytes": B * 8,
             "decode_tokens_per_s": world * B / (d_ms * 1e-3), "decode_ms_per_step": d_ms,
             "decode_note": "greedy step for all 32 layers replayed from one CUDA graph",
             "decode_eager_ms_per_step": de_ms,
-            "decode_attn_kv_bytes_per_step": kv_bytes}
+            "decode_attn_kv_bytes_per_step": kv_bytes,
+            "decode_attn_kv_gbs_floor": kv_bytes / (d_ms * 1e-3) / 1e9}
 
 
 # ------------------------------------------------------------------------------------------------ SFT step (config 4)
@@ -365,6 +374,35 @@ def sft_main(args, rank, world, local):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------------ config 5
+def longctx_main(args, rank, world, local):
+    """BASELINE config 5: multi-image long-context prefill + decode of the AKI-4B language model, batch-sharded over
+    the GPUs (no data-path collective): 4 x 128 image tokens interleaved in a T = 8192 context, B = 2 per GPU, then
+    128 greedy decode steps from one CUDA graph.  One JSON line: prefill tokens/s (value), decode tokens/s, K/V bytes."""
+    import torch.distributed as dist
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+        sampler.mark_begin()
+    r = prefill_section(dev, rank, world, args.steps, args.warmup, longctx=(args.batch, args.seq, args.images, 128))
+    clocks = sampler.stop() if sampler else None
+    if rank == 0:
+        print(json.dumps({"metric": "prefill_tokens_per_s", "value": r["prefill_tokens_per_s"], "unit": "tokens/s",
+                          "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["prefill_ms"],
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+                          "data": "synthetic", "config": {"workload": r["workload"],
+                                                          "parallelism": f"batch-sharded x{world}, no collective"},
+                          "longctx": r, "clocks": clocks,
+                          "e2e": {"value": r["prefill_e2e_tokens_per_s"], "unit": "tokens/s",
+                                  "h2d_bytes_per_step": r["e2e_h2d_bytes"], "d2h_bytes_per_step": r["e2e_d2h_bytes"]}}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 # ------------------------------------------------------------------------------------------------ main
 def main():
     # rank 0 prints exactly ONE line on stdout: keep NCCL's version banner (NCCL_DEBUG=VERSION on some boxes) off it
@@ -380,6 +418,8 @@ def main():
 
     if args.workload == "sft" and args.impl != "reference":
         return sft_main(args, rank, world, local)
+    if args.workload == "longctx" and args.impl != "reference":
+        return longctx_main(args, rank, world, local)
     if args.impl == "reference":
         if rank != 0:
             return
