@@ -357,7 +357,7 @@ def sft_main(args, rank, world, local):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t[0])
     if rank == 0:
-        print(json.dumps({
+        emit(({
             "metric": "sft_tokens_per_s", "value": world * Bp * T / (ms * 1e-3), "unit": "tokens/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16 autocast, fp32 master weights", "data": "synthetic",
@@ -391,7 +391,7 @@ def longctx_main(args, rank, world, local):
     r = prefill_section(dev, rank, world, args.steps, args.warmup, longctx=(args.batch, args.seq, args.images, 128))
     clocks = sampler.stop() if sampler else None
     if rank == 0:
-        print(json.dumps({"metric": "prefill_tokens_per_s", "value": r["prefill_tokens_per_s"], "unit": "tokens/s",
+        emit(({"metric": "prefill_tokens_per_s", "value": r["prefill_tokens_per_s"], "unit": "tokens/s",
                           "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["prefill_ms"],
                           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
                           "data": "synthetic", "config": {"workload": r["workload"],
@@ -404,10 +404,25 @@ def longctx_main(args, rank, world, local):
 
 
 # ------------------------------------------------------------------------------------------------ main
+_REAL_STDOUT_FD = None
+
+
+def emit(obj):
+    """Print the ONE JSON line of this run on the real stdout (see main())."""
+    sys.stdout.flush()
+    if _REAL_STDOUT_FD is not None:
+        os.dup2(_REAL_STDOUT_FD, 1)
+    print(json.dumps(obj), flush=True)
+
+
 def main():
-    # rank 0 prints exactly ONE line on stdout: keep NCCL's version banner (NCCL_DEBUG=VERSION on some boxes) off it
-    # (set unconditionally: the level can also come from /etc/nccl.conf, where the environment does not show it)
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    # rank 0 prints exactly ONE line on stdout.  Native libraries also write there (NCCL's version banner when the box
+    # sets NCCL_DEBUG=VERSION in the environment or /etc/nccl.conf; NCCL_DEBUG_FILE=/dev/stderr did not move it under
+    # torchrun), so file descriptor 1 points at stderr for the whole run and is restored only for that line.
+    global _REAL_STDOUT_FD
+    sys.stdout.flush()
+    _REAL_STDOUT_FD = os.dup(1)
+    os.dup2(2, 1)
     args = parse()
     rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
@@ -426,7 +441,7 @@ def main():
         Ts, Bs = min(T, 2048), 1
         val, ms, threads, nnz = cpu_reference_run(Ts, Bs, min(n_img, 4), max(1, min(args.steps, 3)), min(args.warmup, 1))
         sample = f"T={Ts} B={Bs} H={H} images={min(n_img, 4)} fwd+bwd fp32 eager with materialised 4-D mask"
-        print(json.dumps({"impl": "reference", "metric": "mma_attn_fwd_bwd_tflops", "value": val, "unit": "TFLOP/s",
+        emit(({"impl": "reference", "metric": "mma_attn_fwd_bwd_tflops", "value": val, "unit": "TFLOP/s",
                           "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
                           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                           "data": "synthetic", "config": dict(cfg, reference_sample=sample),
@@ -649,7 +664,7 @@ def main():
         val, ms, threads, _ = cpu_reference_run(Ts, 1, min(n_img, 4), 2, 1)
         line["cpu_baseline"] = {"value": val, "unit": "TFLOP/s", "cores": threads, "kind": "port",
                                 "sample": f"T={Ts} B=1 H={H} images={min(n_img, 4)} fwd+bwd fp32 eager, {ms:.0f} ms/step"}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 

@@ -156,13 +156,22 @@ def _edge_prompt(kind):
         lang = g.integers(3, 31000, size=(1, L)).astype(np.int64); am = np.ones_like(lang)
         lang[0, 5] = M; lang[0, 100] = M; lang[0, 280] = A
         text_only = True
+    elif kind == "span-straddles-tiles":       # backward: a 128-row span over two query tiles = ONE unaligned visit per
+        L, N = 450, 128                        # later key tile (row 0: rows [70,198)); row 1: tile-aligned span [128,256)
+        lang = g.integers(3, 31000, size=(2, L)).astype(np.int64); am = np.ones_like(lang)
+        lang[0, 70] = M; lang[0, 440] = A
+        lang[1, 128] = M; lang[1, 300] = A; lang[1, 400:] = PAD; am[1, 400:] = 0
+    elif kind == "back-to-back-spans":         # two adjacent spans [10,138) [138,266): three flagged tiles, no merge allowed
+        L, N = 400, 128
+        lang = g.integers(3, 31000, size=(1, L)).astype(np.int64); am = np.ones_like(lang)
+        lang[0, 10] = M; lang[0, 11] = M; lang[0, 390] = A
     else:
         raise KeyError(kind)
     return lang, am, N, text_only
 
 
 @pytest.mark.parametrize("kind", ["left-pad-generate", "mixed-image-counts", "tile-edges", "assistant-before-image",
-                                  "no-assistant", "text-only-variant"])
+                                  "no-assistant", "text-only-variant", "span-straddles-tiles", "back-to-back-spans"])
 def test_edge_geometries_forward_and_backward(kind):
     """Padding inside a sample, ragged batches, 0..3 images, tile-edge lengths, degenerate <|assistant|> positions and
     the text-only multi-image variant: bit-exact mask expansion, forward and gradients within the bf16 tolerance."""
