@@ -94,11 +94,6 @@ struct BwdKernelParams {
 #define TRB(slot, j, k) do { } while (0)
 #endif
 
-__device__ __forceinline__ uint64_t f32x2_pack(float lo, float hi) {
-  uint64_t r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-  return r;
-}
 __device__ __forceinline__ void f32x2_mul(float& lo, float& hi, float a_lo, float a_hi, float b_lo, float b_hi) {
   uint64_t r;
   asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(f32x2_pack(a_lo, a_hi)), "l"(f32x2_pack(b_lo, b_hi)));

@@ -449,31 +449,41 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
       if (partial0) mask32(0, c0, vw0, mw0);
       if (partial1) mask32(32, c0 + BN, vw1, mw1);
       // ---- maximum of this thread's scores of the pass; the partner half's arrives through shared memory
-      float mx[4] = {s[0], s[1], s[2], s[3]};
+      // three-input maxima (FMNMX3): two scores per instruction, four independent chains
+      float mx[4] = {fmax3(s[0], s[1], s[2]), fmax3(s[3], s[4], s[5]), fmax3(s[6], s[7], s[8]), fmax3(s[9], s[10], s[11])};
 #pragma unroll
-      for (int c = 4; c < 32; c += 4) {
-        mx[0] = fmaxf(mx[0], s[c]); mx[1] = fmaxf(mx[1], s[c + 1]); mx[2] = fmaxf(mx[2], s[c + 2]); mx[3] = fmaxf(mx[3], s[c + 3]);
+      for (int c = 12; c < 28; c += 8) {
+        mx[0] = fmax3(mx[0], s[c], s[c + 1]); mx[1] = fmax3(mx[1], s[c + 2], s[c + 3]);
+        mx[2] = fmax3(mx[2], s[c + 4], s[c + 5]); mx[3] = fmax3(mx[3], s[c + 6], s[c + 7]);
       }
+      mx[0] = fmax3(mx[0], s[28], s[29]); mx[1] = fmax3(mx[1], s[30], s[31]);
       if (two) {
 #pragma unroll
-        for (int c = 32; c < 64; c += 4) {
-          mx[0] = fmaxf(mx[0], s[c]); mx[1] = fmaxf(mx[1], s[c + 1]); mx[2] = fmaxf(mx[2], s[c + 2]); mx[3] = fmaxf(mx[3], s[c + 3]);
+        for (int c = 32; c < 64; c += 8) {
+          mx[0] = fmax3(mx[0], s[c], s[c + 1]); mx[1] = fmax3(mx[1], s[c + 2], s[c + 3]);
+          mx[2] = fmax3(mx[2], s[c + 4], s[c + 5]); mx[3] = fmax3(mx[3], s[c + 6], s[c + 7]);
         }
       }
-      const float m_half = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+      const float m_half = fmaxf(fmax3(mx[0], mx[1], mx[2]), mx[3]);
       xch[xp][t][ch][r] = m_half;
       // exp2((S - m_used) * scale*log2e) of 32 scores starting at `off`, packed IN PLACE into s[off .. off+16)
       auto exps = [&](int off) {
         const float neg_m = (m_used == -INFINITY) ? 0.f : -m_used * P.scale_log2;
-        float sum0 = 0.f, sum1 = 0.f;
+        // packed FFMA2 / FADD2: one scale-and-shift and one row-sum instruction per PAIR of scores
+        const uint64_t sc2 = f32x2_pack(P.scale_log2, P.scale_log2), nm2 = f32x2_pack(neg_m, neg_m);
+        uint64_t sum_a = f32x2_pack(0.f, 0.f), sum_b = sum_a;
 #pragma unroll
         for (int x = 0; x < 16; ++x) {
-          const float p0 = ex2_approx(fmaf(s[off + 2 * x], P.scale_log2, neg_m));
-          const float p1 = ex2_approx(fmaf(s[off + 2 * x + 1], P.scale_log2, neg_m));
-          sum0 += p0; sum1 += p1;
+          float a0, a1;
+          f32x2_unpack(f32x2_fma(f32x2_pack(s[off + 2 * x], s[off + 2 * x + 1]), sc2, nm2), a0, a1);
+          const float p0 = ex2_approx(a0), p1 = ex2_approx(a1);
+          if (x & 1) sum_b = f32x2_add(sum_b, f32x2_pack(p0, p1));
+          else sum_a = f32x2_add(sum_a, f32x2_pack(p0, p1));
           s[off + x] = __uint_as_float(pack_bf16x2(p0, p1));
         }
-        return sum0 + sum1;
+        float t0, t1;
+        f32x2_unpack(f32x2_add(sum_a, sum_b), t0, t1);
+        return t0 + t1;
       };
       float sum_j;
       if (j == 0) {

@@ -240,4 +240,31 @@ __host__ __device__ __forceinline__ uint32_t sw64_offset(uint32_t r, uint32_t c)
   return r * 64u + ((c ^ ((r >> 1) & 3u)) << 4);
 }
 
+// ---------------------------------------------------------------------------------------------- packed fp32 math
+// Blackwell issues two fp32 lanes per FFMA2 / FADD2 / FMUL2 and a three-input FMNMX3: the element-wise softmax work is
+// issue-bound next to the MUFU, so pairs of scores share one instruction.
+__device__ __forceinline__ uint64_t f32x2_pack(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void f32x2_unpack(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t f32x2_fma(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ uint64_t f32x2_add(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+
 }  // namespace aki
