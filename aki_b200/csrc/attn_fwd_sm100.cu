@@ -393,7 +393,10 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
     // its first batch of exponentials, so that from then on one tile's exp2 phase covers the other tile's barrier
     // probes / TMEM round trips (clock64 trace: started together, the tiles stay in phase and the exp2 phase of
     // all four warps takes 1240 cycles while the pipe idles for the other 1100 of each key tile).
-    const bool stagger = (n_kv0 > 0 && n_kv1 > 0);
+#ifndef AKI_STAGGER_POINT
+#define AKI_STAGGER_POINT 1     // where tile 0 releases tile 1: 0 never staggered, 1 after its first exponentials (shipped),
+#endif                          // 2 after its first TMEM load, 3 at the end of its first pass  (A/B builds only)
+    const bool stagger = (AKI_STAGGER_POINT != 0) && (n_kv0 > 0 && n_kv1 > 0);
     if (stagger && t == 1) named_bar_sync(9, 512);
     // Two key tiles per pass: the fixed per-tile latencies (mbarrier probes, TMEM round trips, the max exchange of the
     // two column halves) cost ~1000 cycles against ~500 of exponentials, so they are paid once per PAIR of key tiles:
@@ -446,6 +449,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
       if (two) tmem_ld_x32(tm_s + 64 * ((j + 1) & 1), reinterpret_cast<uint32_t*>(s) + 32);
       tmem_wait_ld();
       TR(slot, j, 2);
+      if (AKI_STAGGER_POINT == 2 && stagger && t == 0 && j == 0) asm volatile("bar.arrive 9, 512;" ::: "memory");
       if (partial0) mask32(0, c0, vw0, mw0);
       if (partial1) mask32(32, c0 + BN, vw1, mw1);
       // ---- maximum of this thread's scores of the pass; the partner half's arrives through shared memory
@@ -511,7 +515,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
         }
       }
       l += sum_j;
-      if (stagger && t == 0 && j == 0) asm volatile("bar.arrive 9, 512;" ::: "memory");   // release tile 1
+      if (AKI_STAGGER_POINT == 1 && stagger && t == 0 && j == 0) asm volatile("bar.arrive 9, 512;" ::: "memory");   // release tile 1
       // ---- both S buffers go back to the MMA warp: QK^T(j+2), QK^T(j+3) run during the rest of this pass
       tc_fence_before();
       mbar_arrive(BAR(S_FREE + 2 * t + (j & 1)));
@@ -544,6 +548,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
         mbar_arrive(BAR(P_FULL + t));
       }
       TR(slot, j, 6);
+      if (AKI_STAGGER_POINT == 3 && stagger && t == 0 && j == 0) asm volatile("bar.arrive 9, 512;" ::: "memory");
     }
 
     // ---- epilogue: O / l -> bf16 -> global; LSE

@@ -132,6 +132,27 @@ def test_bench_prompt_geometry():
     assert O.count_allowed(S) == int(O.expand_segments_to_4d(S).sum())
 
 
+def test_bench_reference_arm_prints_exactly_one_json_line():
+    """Driver contract: `bench.py --impl reference` runs on the host cores only and prints ONE JSON line on stdout
+    (anything native libraries write to fd 1 is diverted to stderr); other ranks of a torchrun launch print nothing."""
+    import json, subprocess
+    env = dict(os.environ, NCCL_DEBUG="VERSION")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "0", "--seq", "512", "--batch", "1", "--images", "1"],
+                         capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, out.stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "mma_attn_fwd_bwd_tflops" and d["unit"] == "TFLOP/s"
+    assert d["value"] > 0 and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    quiet = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                            "--warmup", "0"], capture_output=True, text=True, timeout=600,
+                           env=dict(env, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1"), cwd=ROOT)
+    assert quiet.returncode == 0 and quiet.stdout.strip() == ""
+
+
 def _gloo_worker(rank, world, port, q):
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
