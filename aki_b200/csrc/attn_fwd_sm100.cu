@@ -42,11 +42,13 @@ namespace fwd {
 constexpr int BM = 128, BN = 64, HD = 96;
 constexpr int Q_ATOM = 128 * 64, Q_TILE = 3 * Q_ATOM;     // 24576
 constexpr int KV_ATOM = BN * 64, KV_TILE = 3 * KV_ATOM;   // 12288
-constexpr int STAGES = 4;
+constexpr int STAGES = 4;                                 // V ring: 64-key tiles
+constexpr int K_PAIR_ATOM = 2 * BN * 64, K_PAIR_TILE = 3 * K_PAIR_ATOM;   // K ring: 128-key tiles (one per pass), 24576
+constexpr int K_STAGES = 2;
 constexpr int THREADS = 640;
 constexpr int SMEM_Q = 0;
 constexpr int SMEM_K = SMEM_Q + 2 * Q_TILE;
-constexpr int SMEM_V = SMEM_K + STAGES * KV_TILE;
+constexpr int SMEM_V = SMEM_K + K_STAGES * K_PAIR_TILE;
 constexpr int SMEM_TOTAL = SMEM_V + STAGES * KV_TILE;     // 147456
 constexpr int SMEM_ALLOC = SMEM_TOTAL + 1024;             // slack for 1024-byte alignment
 constexpr uint32_t TM_S = 0, TM_O = 256, TM_P = 448;      // S: tile t buffer u at 128 t + 64 u; O: 96 t; P: 32 t
@@ -122,7 +124,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   // barrier indices
-  constexpr int Q_FULL = 0, Q_READY = 2, K_FULL = 4, K_EMPTY = K_FULL + STAGES, V_FULL = K_EMPTY + STAGES,
+  constexpr int Q_FULL = 0, Q_READY = 2, K_FULL = 4, K_EMPTY = K_FULL + K_STAGES, V_FULL = K_EMPTY + K_STAGES,
                 V_EMPTY = V_FULL + STAGES, S_FULL = V_EMPTY + STAGES /* [t][buf] */, S_FREE = S_FULL + 4,
                 P_FULL = S_FREE + 4, O_FULL = P_FULL + 2, N_BARS = O_FULL + 2;
   __shared__ __align__(8) uint64_t bars[N_BARS];
@@ -154,10 +156,8 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
 
   if (tid == 0) {
     for (int i = 0; i < 2; ++i) { mbar_init(BAR(Q_FULL + i), 1); mbar_init(BAR(Q_READY + i), 256); }
-    for (int i = 0; i < STAGES; ++i) {
-      mbar_init(BAR(K_FULL + i), 1); mbar_init(BAR(K_EMPTY + i), 2);   // one release per MMA warp (query tile)
-      mbar_init(BAR(V_FULL + i), 1); mbar_init(BAR(V_EMPTY + i), 2);
-    }
+    for (int i = 0; i < K_STAGES; ++i) { mbar_init(BAR(K_FULL + i), 1); mbar_init(BAR(K_EMPTY + i), 2); }
+    for (int i = 0; i < STAGES; ++i) { mbar_init(BAR(V_FULL + i), 1); mbar_init(BAR(V_EMPTY + i), 2); }   // one release per query tile
     for (int i = 0; i < 4; ++i) { mbar_init(BAR(S_FULL + i), 1); mbar_init(BAR(S_FREE + i), 256); }
     for (int i = 0; i < 2; ++i) { mbar_init(BAR(P_FULL + i), 256); mbar_init(BAR(O_FULL + i), 1); }
     fence_barrier_init();
@@ -199,12 +199,12 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
         for (int a = 0; a < 3; ++a)
           tma_load_4d(smem_base + SMEM_Q + t * Q_TILE + a * Q_ATOM, &map_q, BAR(Q_FULL + t), a * 32, (2 * qp + t) * BM, h, b);
       }
-      auto load_k = [&](int j) {
-        const int s = j % STAGES;
-        mbar_wait(BAR(K_EMPTY + s), ((j / STAGES) & 1) ^ 1);
-        mbar_arrive_expect_tx(BAR(K_FULL + s), KV_TILE);
+      auto load_k = [&](int j) {                 // the 128 keys of pass j/2 (rows beyond T are zero-filled)
+        const int pp = j >> 1, s = pp % K_STAGES;
+        mbar_wait(BAR(K_EMPTY + s), ((pp / K_STAGES) & 1) ^ 1);
+        mbar_arrive_expect_tx(BAR(K_FULL + s), K_PAIR_TILE);
         for (int a = 0; a < 3; ++a)
-          tma_load_4d(smem_base + SMEM_K + s * KV_TILE + a * KV_ATOM, &map_k, BAR(K_FULL + s), a * 32, j * BN, h, b);
+          tma_load_4d(smem_base + SMEM_K + s * K_PAIR_TILE + a * K_PAIR_ATOM, &map_k, BAR(K_FULL + s), a * 32, j * BN, h, b);
       };
       auto load_v = [&](int j) {
         const int s = j % STAGES;
@@ -213,12 +213,10 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
         for (int a = 0; a < 3; ++a)
           tma_load_4d(smem_base + SMEM_V + s * KV_TILE + a * KV_ATOM, &map_v, BAR(V_FULL + s), a * 32, j * BN, h, b);
       };
-      // consumption order of the MMA warps (two key tiles per pass): K0 K1 | K2 K3 V0 V1 | K4 K5 V2 V3 | ...
+      // consumption order of the MMA warps (two key tiles per pass): K01 | K23 V0 V1 | K45 V2 V3 | ...
       if (n_max > 0) load_k(0);
-      if (n_max > 1) load_k(1);
       for (int j = 0; j < n_max; j += 2) {
         if (j + 2 < n_max) load_k(j + 2);
-        if (j + 3 < n_max) load_k(j + 3);
         load_v(j);
         if (j + 1 < n_max) load_v(j + 1);
       }
@@ -237,44 +235,44 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
 #ifdef AKI_FWD_TRACE
     const bool tracing = P.trace && (int)blockIdx.x == P.trace_cta && leader;
 #endif
-    constexpr uint32_t IDESC_QK = umma_idesc_bf16(BM, BN, 0, 0);
+    // One N=128 MMA group per pass: S_t(j) | S_t(j+1) = Q_t [K_j ; K_j+1]^T lands in the tile's 128 score columns.  An
+    // M=128,K=16 MMA costs ~64-76 cycles whether N is 64 or 128, so two N=64 groups took twice the tensor-pipe time.
+    constexpr uint32_t IDESC_QK128 = umma_idesc_bf16(BM, 2 * BN, 0, 0), IDESC_QK64 = umma_idesc_bf16(BM, BN, 0, 0);
     const uint64_t DESC_KMAJ = umma_smem_desc(0, 16, 512, UMMA_SW64);
     const uint32_t HI = (uint32_t)(DESC_KMAJ >> 32), KMAJ_LO = (uint32_t)DESC_KMAJ;
     const uint32_t qa = KMAJ_LO + ((smem_base + SMEM_Q + t * Q_TILE) >> 4), k_lo = KMAJ_LO + ((smem_base + SMEM_K) >> 4);
     if (nk > 0) mbar_wait(BAR((ROPE ? Q_READY : Q_FULL) + t), 0);
-    auto issue_qk = [&](int j) {              // S_t[j&1] = Q_t K_j^T, then this tile's release of the K stage
-      const int s = j % STAGES;
+    // Pass p handles key tiles j = 2p, 2p+1.  The softmax frees both S buffers at the same moment; the chain
+    // S_FREE -> S(j+2), S(j+3) is the critical path of a pass.  Every K stage is released by one arrival per query
+    // tile: a commit behind the MMAs that read it, or a plain arrive when this tile does not visit these keys.
+    for (int j = 0; j < n_max; j += 2) {
+      const int pp = j >> 1, s = pp % K_STAGES;
+      // waited for even when this tile skips the keys: it keeps the tile from running a whole ring ahead and
+      // arriving twice in one K_EMPTY phase
+      mbar_wait(BAR(K_FULL + s), (pp / K_STAGES) & 1);
       if (j < nk) {
-        const uint32_t ka = k_lo + s * (KV_TILE >> 4);
-        const uint32_t d = tmem + TM_S + 128 * t + 64 * (j & 1);
+        const bool two = (j + 1 < nk);
+        if (j >= 2) {                           // the softmax holds S_t(j-2), S_t(j-1) in registers
+          mbar_wait(BAR(S_FREE + 2 * t + 0), ((j - 2) >> 1) & 1);
+          if (two) mbar_wait(BAR(S_FREE + 2 * t + 1), ((j - 1) >> 1) & 1);
+        }
+        tc_fence_after();
+        TR(4 + t, j, 0);
+        const uint32_t ka = k_lo + s * (K_PAIR_TILE >> 4);
+        const uint32_t d = tmem + TM_S + 128 * t;
         if (leader) {
 #pragma unroll
           for (int k = 0; k < 6; ++k)
-            umma_ss_lh(d, qa + (((k >> 1) * Q_ATOM + (k & 1) * 32) >> 4), ka + (((k >> 1) * KV_ATOM + (k & 1) * 32) >> 4), HI,
-                       IDESC_QK, k > 0);
-          umma_commit(BAR(S_FULL + 2 * t + (j & 1)));
+            umma_ss_lh(d, qa + (((k >> 1) * Q_ATOM + (k & 1) * 32) >> 4), ka + (((k >> 1) * K_PAIR_ATOM + (k & 1) * 32) >> 4), HI,
+                       two ? IDESC_QK128 : IDESC_QK64, k > 0);
+          umma_commit(BAR(S_FULL + 2 * t + 0));
+          if (two) umma_commit(BAR(S_FULL + 2 * t + 1));
           umma_commit(BAR(K_EMPTY + s));
         }
+        TR(4 + t, j, 1);
       } else if (leader) {
         mbar_arrive(BAR(K_EMPTY + s));
       }
-    };
-    // Pass p handles key tiles 2p, 2p+1.  The softmax frees both S buffers at the same moment, so everything else
-    // (K tiles landed) is waited for first and the two QK^T are then issued back to back: the chain S_FREE -> S(j+3)
-    // is the critical path of a pass (clock64 trace: 2100 cycles when each QK^T paid its own round of waits).
-    for (int j = 0; j < n_max; j += 2) {
-      const bool two = (j + 1 < n_max);
-      mbar_wait(BAR(K_FULL + j % STAGES), (j / STAGES) & 1);
-      if (two) mbar_wait(BAR(K_FULL + (j + 1) % STAGES), ((j + 1) / STAGES) & 1);
-      if (j >= 2) {                           // the softmax holds S_t(j-2), S_t(j-1) in registers
-        if (j < nk) mbar_wait(BAR(S_FREE + 2 * t + (j & 1)), ((j - 2) >> 1) & 1);
-        if (j + 1 < nk) mbar_wait(BAR(S_FREE + 2 * t + ((j + 1) & 1)), ((j - 1) >> 1) & 1);
-      }
-      tc_fence_after();
-      TR(4 + t, j, 0);
-      issue_qk(j);
-      if (two) issue_qk(j + 1);
-      TR(4 + t, j, 1);
       __syncwarp();
     }
   } else if (warp == 2) {
@@ -661,7 +659,7 @@ extern "C" int aki_mma_attn_fwd(const AkiMmaAttnParams* p, aki_stream_t stream) 
   if (rc) return rc;
   CUtensorMap mq, mk, mv;
   if ((rc = make_tile_map(&mq, p->q, p->B, p->H, p->T, fwd::BM))) return rc;
-  if ((rc = make_tile_map(&mk, p->k, p->B, p->H, p->T, fwd::BN))) return rc;
+  if ((rc = make_tile_map(&mk, p->k, p->B, p->H, p->T, 2 * fwd::BN))) return rc;   // K: 128-key tiles (one per pass)
   if ((rc = make_tile_map(&mv, p->v, p->B, p->H, p->T, fwd::BN))) return rc;
   FwdKernelParams kp;
   kp.q = view_of(p->q); kp.o = view_of(p->o);
