@@ -391,6 +391,9 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
     // its first batch of exponentials, so that from then on one tile's exp2 phase covers the other tile's barrier
     // probes / TMEM round trips (clock64 trace: started together, the tiles stay in phase and the exp2 phase of
     // all four warps takes 1240 cycles while the pipe idles for the other 1100 of each key tile).
+#ifndef AKI_ONE_EXP_PHASE
+#define AKI_ONE_EXP_PHASE 0     // 1: both key tiles of a pass are exponentiated in ONE phase before P(j) is published (A/B)
+#endif
 #ifndef AKI_STAGGER_POINT
 #define AKI_STAGGER_POINT 1     // where tile 0 releases tile 1: 0 never staggered, 1 after its first exponentials (shipped),
 #endif                          // 2 after its first TMEM load, 3 at the end of its first pass  (A/B builds only)
@@ -487,16 +490,23 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
         f32x2_unpack(f32x2_add(sum_a, sum_b), t0, t1);
         return t0 + t1;
       };
+      auto fetch1 = [&]() {                          // (re)load this half of S_t(j+1) and mask it
+        tmem_ld_x32(tm_s + 64 * ((j + 1) & 1), reinterpret_cast<uint32_t*>(s) + 32);
+        tmem_wait_ld();
+        if (partial1) mask32(32, c0 + BN, vw1, mw1);
+      };
       float sum_j;
       if (j == 0) {
         named_bar_sync(pair_bar, 64);
         m_used = fmaxf(m_half, xch[xp][t][ch ^ 1][r]);
         sum_j = exps(0);
+        if (AKI_ONE_EXP_PHASE && two) sum_j += exps(32);
       } else {
         // Optimistic: exponentiate tile j against the running max of the EARLIER passes while the maxima are being
         // exchanged; if the pass maximum exceeds the reference by more than the threshold (rare after the first
         // tiles) O and l are rescaled and tile j is redone -- published P values never exceed 2^threshold.
         sum_j = exps(0);
+        if (AKI_ONE_EXP_PHASE && two) sum_j += exps(32);
         named_bar_sync(pair_bar, 64);
         const float m_new = fmaxf(m_used, fmaxf(m_half, xch[xp][t][ch ^ 1][r]));
         TR(slot, j, 3);
@@ -510,6 +520,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
           rescale_o48(tm_o, alpha);
           fetch0();
           sum_j = exps(0);
+          if (AKI_ONE_EXP_PHASE && two) { fetch1(); sum_j += exps(32); }
         }
       }
       l += sum_j;
@@ -531,7 +542,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
       mbar_arrive(BAR(P_FULL + t));
       if (two) {
         // ---- tile j+1 while PV(j) runs, then P(j+1) into the same columns
-        l += exps(32);
+        if (!AKI_ONE_EXP_PHASE) l += exps(32);
         mbar_wait(BAR(O_FULL + t), j & 1);
         o_waited = j + 1;
         tc_fence_after();
