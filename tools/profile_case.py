@@ -1,0 +1,28 @@
+"""One forward + backward of the bench workload (T=8192, B=2, 4 image spans) for ncu:
+  ncu --set full --clock-control none --import-source on -k regex:'attn_fwd_sm100|attn_bwd_sm100|bwd_preprocess|dq_finalize' \
+      -c 4 -o gpurun_out/prof python tools/profile_case.py
+then tools/ncu_summary.py gpurun_out/prof.ncu-rep profiles/<name>.csv"""
+import os, sys
+import numpy as np, torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench
+import aki_b200
+from aki_b200 import ops
+dev = torch.device("cuda", 0)
+H, D, T, B = 32, 96, 8192, 2
+rope = aki_b200.LongRope(device=dev)
+lang, am = bench.make_prompt(B, T, 4)
+segs = ops.build_segments(torch.from_numpy(lang).to(dev), torch.from_numpy(am).to(dev), 128, bench.MEDIA_ID, t_cap=T, exact_shape=False)
+meta = ops.meta_tuple(segs)
+g = torch.Generator(device=dev).manual_seed(0)
+qkv = torch.randn(B, T, 3 * H * D, generator=g, device=dev).to(torch.bfloat16)
+d_o = torch.randn(B, T, H, D, generator=g, device=dev).to(torch.bfloat16)
+cos, sin = rope.tables(torch.arange(T, device=dev)[None], max_position=T - 1)
+q4 = qkv[..., :H * D].unflatten(-1, (H, D)); v4 = qkv[..., 2 * H * D:].unflatten(-1, (H, D))
+k_rot = torch.empty(B, H, T, D, dtype=torch.bfloat16, device=dev)
+dq = torch.empty_like(q4.contiguous()); dk = torch.empty_like(dq); dv = torch.empty_like(dq)
+ops.rope_kv_write(qkv, cos, sin, k_rot, None, 0, H)
+o, lse = ops.attn_fwd_raw(q4, k_rot.transpose(1, 2), v4, cos, sin, meta, D ** -0.5)
+ops.attn_bwd_raw(d_o, q4, k_rot.transpose(1, 2), v4, o, lse, cos, sin, meta, D ** -0.5, dq, dk, dv)
+torch.cuda.synchronize()
