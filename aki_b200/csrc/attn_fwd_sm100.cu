@@ -391,6 +391,10 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
     // its first batch of exponentials, so that from then on one tile's exp2 phase covers the other tile's barrier
     // probes / TMEM round trips (clock64 trace: started together, the tiles stay in phase and the exp2 phase of
     // all four warps takes 1240 cycles while the pipe idles for the other 1100 of each key tile).
+#ifndef AKI_PV_FIRST
+#define AKI_PV_FIRST 1          // 1: publish P(j) before handing the S buffers back, so that PV(j) queues ahead of the
+                                // next pass's QK^T in the tensor pipe (same-box A/B: 1.047 -> 1.038 ms causal); 0: the reverse
+#endif
 #ifndef AKI_ONE_EXP_PHASE
 #define AKI_ONE_EXP_PHASE 0     // 1: both key tiles of a pass are exponentiated in ONE phase before P(j) is published (A/B)
 #endif
@@ -526,9 +530,11 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
       l += sum_j;
       if (AKI_STAGGER_POINT == 1 && stagger && t == 0 && j == 0) asm volatile("bar.arrive 9, 512;" ::: "memory");   // release tile 1
       // ---- both S buffers go back to the MMA warp: QK^T(j+2), QK^T(j+3) run during the rest of this pass
-      tc_fence_before();
-      mbar_arrive(BAR(S_FREE + 2 * t + (j & 1)));
-      if (two) mbar_arrive(BAR(S_FREE + 2 * t + ((j + 1) & 1)));
+      if (!AKI_PV_FIRST) {
+        tc_fence_before();
+        mbar_arrive(BAR(S_FREE + 2 * t + (j & 1)));
+        if (two) mbar_arrive(BAR(S_FREE + 2 * t + ((j + 1) & 1)));
+      }
       TR(slot, j, 4);
       // ---- publish P(j): its own TMEM columns, single-buffered -- PV(j-1) has consumed P(j-1)
       if (o_waited < j) {
@@ -540,6 +546,10 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
       tmem_wait_st();
       tc_fence_before();
       mbar_arrive(BAR(P_FULL + t));
+      if (AKI_PV_FIRST) {            // PV(j) enters the tensor-pipe queue ahead of QK^T(j+2), QK^T(j+3)
+        mbar_arrive(BAR(S_FREE + 2 * t + (j & 1)));
+        if (two) mbar_arrive(BAR(S_FREE + 2 * t + ((j + 1) & 1)));
+      }
       if (two) {
         // ---- tile j+1 while PV(j) runs, then P(j+1) into the same columns
         if (!AKI_ONE_EXP_PHASE) l += exps(32);
