@@ -317,7 +317,10 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
         jt[t] = j + 1;
         progressed = true;
       }
-      if (!progressed) __nanosleep(32);
+#ifndef AKI_PV_SLEEP
+#define AKI_PV_SLEEP 32         // ns between polls of the PV issuer when neither tile is ready (A/B: 0 = busy poll)
+#endif
+      if (!progressed && AKI_PV_SLEEP > 0) __nanosleep(AKI_PV_SLEEP);
     }
   } else {
     // ------------------------------------------------------------------ softmax / correction / epilogue
