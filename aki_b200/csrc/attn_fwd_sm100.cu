@@ -8,27 +8,26 @@
 // is evaluated in registers on the few tiles that are not fully visible, and key tiles beyond
 // q_tile_kv_end[b][qt] are never visited.  RoPE is applied to Q in shared memory right after the TMA load.
 //
-// CTA = 2 query tiles x 128 rows of one (batch, head), key tiles of 64; 20 warps:
-//   warp 0      TMA producer (Q once, then K_j / V_j through two 4-deep rings of 12 KB tiles)
-//   warp 1 / 3  QK^T issuers of query tile 0 / 1: S_t[j&1] = Q_t K_j^T (SS, N=64)
+// CTA = 2 query tiles x 128 rows of one (batch, head); a PASS covers 128 keys = two 64-key softmax tiles; 20 warps:
+//   warp 0      TMA producer (Q once; K as 128-key tiles through a 2-deep ring, V as 64-key tiles through a 4-deep ring)
+//   warp 1 / 3  QK^T issuers of query tile 0 / 1: [S_t(j) | S_t(j+1)] = Q_t [K_j ; K_j+1]^T, ONE SS group of N=128 per pass
+//               (an M=128,K=16 MMA costs 64-76 cycles whether N is 64 or 128: tools/mma_mix_bench.cu)
 //   warp 2      TMEM allocator, then PV issuer of both tiles: O_t += P_t V_j (TS, P read from TMEM); polls both P_FULL
 //   (warp 3 first finds the first key tile that holds padding)
 //   warps 4-19  softmax: warp = (tile t, column half c, lane group g); thread <-> row 32g+lane <-> TMEM lane,
-//               32 of the 64 key columns.  FOUR softmax warps per SM sub-partition: ncu on the 2-warp layout showed
-//               the exp2 pipe 47% busy because one warp's fixed latencies (mbarrier probes, TMEM round trips, max
-//               chain) exceed its own exp2 time, so a second warp could not cover them.  The two column halves of a
-//               row agree on the tile maximum through shared memory and a 64-thread named barrier.
-// S is DOUBLE-BUFFERED per query tile (that is why the key tile is 64 wide: 4 x 64 S columns + 2 x 96 O + 2 x 32 P
-// = 512 TMEM columns exactly) and a buffer is handed back to the MMA warp (S_FREE) as soon as its scores sit in
-// registers, i.e. one whole key tile before they are used: QK^T(j+2) is in flight while the softmax still works on
-// tile j, S(j+1) has always landed when it is fetched, and a softmax warp never waits for the tensor pipe (ncu on
-// the previous layout, P written in place over S: 22% of the softmax time was spent waiting for S).  Per key tile
-// a softmax warp runs one straight-line chain: start the TMEM load of S(j+1) -> row max of S(j) (3-input max) ->
-// release the buffer -> exp2/sum/pack of S(j) -> P store -> arrive.  Tiles below the diagonal that hold no padding
-// (j < n_full, one comparison) skip the predicate.
-// The exp2 (MUFU) pipe is the real bound of this head_dim: 64 exp vs 384 tensor cycles per row per key tile.
-// TMEM columns: S0a S0b S1a S1b [0,256) | O0 [256,352) O1 [352,448) | P0 [448,480) P1 [480,512).
-// Shared memory: Q 2x24 KB; K ring 4x12 KB; V ring 4x12 KB.  Every tile is 3 SWIZZLE_64B atoms [rows][64 B]
+//               32 of the 64 key columns of each softmax tile.  FOUR softmax warps per SM sub-partition: ncu on the
+//               2-warp layout showed the exp2 pipe 47% busy because one warp's fixed latencies (mbarrier probes, TMEM
+//               round trips, max chain) exceed its own exp2 time.  The two column halves of a row agree on the pass
+//               maximum through shared memory and a 64-thread named barrier.
+// Per pass a softmax warp: waits for both score halves, loads its 64 scores (2 x tcgen05.ld.x32), masks the tiles that
+// are not fully visible (j >= n_full), reduces the maximum (FMNMX3), exponentiates tile j OPTIMISTICALLY against the
+// running maximum of the earlier passes while the maxima are exchanged (redo + rescale only when the new maximum exceeds
+// it by 2^8), publishes P(j) (PV(j) enters the tensor pipe), hands both S buffers back (QK^T of the next pass), then
+// exponentiates tile j+1 under PV(j) and publishes P(j+1).  Element-wise math is packed (FFMA2 / FADD2).
+// Neither the exp2 (MUFU, 49 %) nor the tensor pipe (36 %) is saturated: a pass is bound by this serial chain with the two
+// query tiles' exp2 phases coinciding (DESIGN.md 4.1 lists what was tried against that).
+// TMEM columns: S0 [0,128) S1 [128,256) (two 64-column halves each) | O0 [256,352) O1 [352,448) | P0 [448,480) P1 [480,512).
+// Shared memory: Q 2x24 KB; K ring 2x24 KB; V ring 4x12 KB.  Every tile is 3 SWIZZLE_64B atoms [rows][64 B]
 // (head_dim 96 = 3 x 32), the layout both the TMA boxes and the UMMA descriptors use (tools/umma_probe.cu).
 #include <math.h>
 #include <stdio.h>
