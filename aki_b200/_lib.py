@@ -12,6 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("AKI_MMA_LIB") or os.path.join(_HERE, "libaki_mma.so")   # AKI_MMA_LIB: A/B builds (tools only)
 
 AKI_OK = 0
+ABI_VERSION = 2
 HEAD_DIM = 96
 TILE = 128
 
@@ -35,6 +36,7 @@ class AttnParams(C.Structure):
         ("kv_valid_bits", C.c_void_p), ("kv_mutual_bits", C.c_void_p),
         ("q_tile_kv_end", C.c_void_p), ("kv_tile_q_mask", C.c_void_p),
         ("meta_pitch", C.c_int32), ("bits_pitch", C.c_int32),
+        ("fwd_plan", C.c_void_p), ("plan_pairs", C.c_int32), ("reserved0", C.c_int32),
     ]
 
 
@@ -56,6 +58,8 @@ _SIGNATURES = {
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "aki_mma_tile_bounds": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                       C.c_void_p, C.c_void_p]),
+    "aki_mma_fwd_plan": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                   C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "aki_mma_expand_mask": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                       C.c_int, C.c_void_p, C.c_void_p]),
     "aki_mma_splice": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
@@ -90,12 +94,15 @@ def _load():
             f"{LIB_PATH} is missing: the CUDA library is the product and there is no fallback. Build it with "
             f"`python -c 'import __graft_entry__ as g; g.build()'` or `make -C aki_b200/csrc`.")
     lib = C.CDLL(LIB_PATH)
+    compat = bool(os.environ.get("AKI_MMA_LIB_COMPAT"))   # tools only: time the FORWARD of an ABI-1 build (same-box A/B)
     for name, (res, args) in _SIGNATURES.items():
+        if compat and not hasattr(lib, name):
+            continue
         fn = getattr(lib, name)          # AttributeError if the ABI is incomplete
         fn.restype = res
         fn.argtypes = args
-    if lib.aki_mma_abi_version() != 1:
-        raise ImportError(f"{LIB_PATH}: ABI version {lib.aki_mma_abi_version()} != 1; rebuild")
+    if lib.aki_mma_abi_version() != ABI_VERSION and not compat:
+        raise ImportError(f"{LIB_PATH}: ABI version {lib.aki_mma_abi_version()} != {ABI_VERSION}; rebuild")
     return lib
 
 

@@ -1,58 +1,59 @@
 // Modality-mutual attention forward for sm_100a: QK^T, online softmax and PV on tcgen05 tensor cores with
-// TMEM accumulators, operands staged by TMA, mbarrier pipelines, warp-specialised roles.
+// TMEM accumulators, operands staged by TMA, mbarrier pipelines, warp-specialised roles, persistent CTAs fed by the
+// hardware work queue (cluster launch control).
 //
 // Replaces the eager core of Phi3Attention.forward (softmax_fp32(QK^T/sqrt(96) + mask) V; installed
 // equivalent transformers/models/phi3/modeling_phi3.py:153-175) fed by the reference's materialised
 // (B,1,T,T) mask (codes/open_flamingo/src/vlm.py:410-443).  No mask is read from HBM: the predicate
 //   allowed(i,j) = (j<=i & valid[j]) | (row_lo[i]<=j<row_hi[i] & mutual_ok[j])
-// is evaluated in registers on the few tiles that are not fully visible, and key tiles beyond
-// q_tile_kv_end[b][qt] are never visited.  RoPE is applied to Q in shared memory right after the TMA load.
+// is evaluated in registers on the few key tiles that are not fully visible, and key tiles beyond a query tile's
+// reach are never visited.  RoPE is applied to Q in shared memory right after the TMA load.
 //
-// CTA = 2 query tiles x 128 rows of one (batch, head); a PASS covers 128 keys = two 64-key softmax tiles; 20 warps:
-//   warp 0      TMA producer (Q once; K as 128-key tiles through a 2-deep ring, V as 64-key tiles through a 4-deep ring)
-//   warp 1 / 3  QK^T issuers of query tile 0 / 1: [S_t(j) | S_t(j+1)] = Q_t [K_j ; K_j+1]^T, ONE SS group of N=128 per pass
-//               (an M=128,K=16 MMA costs 64-76 cycles whether N is 64 or 128: tools/mma_mix_bench.cu)
-//   warp 2      TMEM allocator, then PV issuer of both tiles: O_t += P_t V_j (TS, P read from TMEM); polls both P_FULL
-//   (warp 3 first finds the first key tile that holds padding)
-//   warps 4-19  softmax: warp = (tile t, column half c, lane group g); thread <-> row 32g+lane <-> TMEM lane,
-//               32 of the 64 key columns of each softmax tile.  FOUR softmax warps per SM sub-partition: ncu on the
-//               2-warp layout showed the exp2 pipe 47% busy because one warp's fixed latencies (mbarrier probes, TMEM
-//               round trips, max chain) exceed its own exp2 time.  The two column halves of a row agree on the pass
-//               maximum through shared memory and a 64-thread named barrier.
-// Per pass a softmax warp: waits for both score halves, loads its 64 scores (2 x tcgen05.ld.x32), masks the tiles that
-// are not fully visible (j >= n_full), reduces the maximum (FMNMX3), exponentiates tile j OPTIMISTICALLY against the
-// running maximum of the earlier passes while the maxima are exchanged (redo + rescale only when the new maximum exceeds
-// it by 2^8), publishes P(j) (PV(j) enters the tensor pipe), hands both S buffers back (QK^T of the next pass), then
-// exponentiates tile j+1 under PV(j) and publishes P(j+1).  Element-wise math is packed (FFMA2 / FADD2).
-// Neither the exp2 (MUFU, 49 %) nor the tensor pipe (36 %) is saturated: a pass is bound by this serial chain with the two
-// query tiles' exp2 phases coinciding (DESIGN.md 4.1 lists what was tried against that).
-// TMEM columns: S0 [0,128) S1 [128,256) (two 64-column halves each) | O0 [256,352) O1 [352,448) | P0 [448,480) P1 [480,512).
-// Shared memory: Q 2x24 KB; K ring 2x24 KB; V ring 4x12 KB.  Every tile is 3 SWIZZLE_64B atoms [rows][64 B]
-// (head_dim 96 = 3 x 32), the layout both the TMA boxes and the UMMA descriptors use (tools/umma_probe.cu).
+// WORK ITEM = one (batch, head) x one PAIR of query tiles from the forward plan (meta.cu, aki_mma_fwd_plan): query
+// tiles of <= 128 rows that start at every image span, ranked by the number of 128-key tiles they visit and paired
+// (both tiles of a pair consume one stream of K/V tiles).  Items are numbered heaviest-first inside groups of 16
+// (batch, head) slices (K/V of a group stay in L2); a CTA keeps asking the hardware queue for the next item
+// (clusterlaunchcontrol.try_cancel) until the grid is exhausted.
+//
+// CTA = 16 warps:
+//   warp 0       TMA producer: Q of the NEXT item while the current one runs (2 Q buffers), K ring (2 x 128 keys),
+//                V ring (3 x 128 keys)
+//   warp 1       scheduler: next item id from the hardware queue -> plan entry -> item ring (4 slots) in shared memory
+//   warp 2 / 3   MMA issuer of query tile 0 / 1 (+ TMEM allocation): S_t = Q_t K_j^T (one N=128 group per 128 keys),
+//                O_t += P_t V_j as two TS groups of 64 keys (P read from TMEM)
+//   warps 4-7 / 8-11   softmax of tile 0 / 1: ONE THREAD PER SCORE ROW, 128 keys per pass -- no cross-warp exchange,
+//                no block barrier in the loop: tcgen05.ld of the whole row, S buffer handed back at once (the next
+//                QK^T runs under the exponentials), mask (only tiles that are not fully visible), row maximum, lazy
+//                rescale of O (only when the maximum grew by more than 2^8; done in place by the same thread),
+//                exp2 of keys 0-63 -> P -> PV, exp2 of keys 64-127 -> P -> PV.  Packed FFMA2 / FADD2 / FMNMX3.
+//   warps 12-15  RoPE of the next item's Q tiles in shared memory, then the epilogue of the current item
+//                (O / l -> bf16 -> global, LSE) while the softmax warps already run the next item
+// TMEM columns: S0 [0,128) S1 [128,256) | O0 [256,352) O1 [352,448) | P0 [448,480) P1 [480,512) (64 keys of bf16 pairs).
+// Shared memory: Q 2 buffers x 2 tiles x 24 KB; K ring 2 x 24 KB; V ring 3 x 24 KB.  Every tile is 3 SWIZZLE_64B atoms
+// [128 rows][64 B] (head_dim 96 = 3 x 32), the layout both the TMA boxes and the UMMA descriptors use.
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <mutex>
 #include "attn_aux.cuh"
 #include "sm100_ptx.cuh"
 
 namespace aki {
 
 namespace fwd {
-constexpr int BM = 128, BN = 64, HD = 96;
-constexpr int Q_ATOM = 128 * 64, Q_TILE = 3 * Q_ATOM;     // 24576
-constexpr int KV_ATOM = BN * 64, KV_TILE = 3 * KV_ATOM;   // 12288
-constexpr int STAGES = 4;                                 // V ring: 64-key tiles
-constexpr int K_PAIR_ATOM = 2 * BN * 64, K_PAIR_TILE = 3 * K_PAIR_ATOM;   // K ring: 128-key tiles (one per pass), 24576
-constexpr int K_STAGES = 2;
-constexpr int THREADS = 640;
-constexpr int SMEM_Q = 0;
-constexpr int SMEM_K = SMEM_Q + 2 * Q_TILE;
-constexpr int SMEM_V = SMEM_K + K_STAGES * K_PAIR_TILE;
-constexpr int SMEM_TOTAL = SMEM_V + STAGES * KV_TILE;     // 147456
-constexpr int SMEM_ALLOC = SMEM_TOTAL + 1024;             // slack for 1024-byte alignment
-constexpr uint32_t TM_S = 0, TM_O = 256, TM_P = 448;      // S: tile t buffer u at 128 t + 64 u; O: 96 t; P: 32 t
-constexpr int REGS_CTRL = 56, REGS_SOFTMAX = 104;         // CTA pool (640 x 96 = 61440): 128*56 + 512*104 = 60416
+constexpr int BM = 128, BN = 128, HD = 96;
+constexpr int ATOM = 128 * 64, TILE_BYTES = 3 * ATOM;     // 24576
+constexpr int K_STAGES = 2, V_STAGES = 3, SLOTS = 4;
+constexpr int THREADS = 512;
+constexpr int SMEM_Q = 0;                                  // [buffer][tile]
+constexpr int SMEM_K = SMEM_Q + 4 * TILE_BYTES;
+constexpr int SMEM_V = SMEM_K + K_STAGES * TILE_BYTES;
+constexpr int SMEM_TOTAL = SMEM_V + V_STAGES * TILE_BYTES; // 221184
+constexpr int SMEM_ALLOC = SMEM_TOTAL + 1024;              // slack for 1024-byte alignment
+constexpr uint32_t TM_S = 0, TM_O = 256, TM_P = 448;       // S: 128 t; O: 96 t; P: 32 t
+constexpr int REGS_CTRL = 56, REGS_SOFTMAX = 192, REGS_EPI = 72;   // 128*56 + 256*192 + 128*72 = 65536 = 512 x 128
 constexpr float RESCALE_THRESHOLD = 8.0f;  // log2 units: P may grow to 2^8 before O is rescaled
+constexpr int HEADS_PER_GROUP = 16;
 }  // namespace fwd
 
 struct FwdKernelParams {
@@ -62,17 +63,12 @@ struct FwdKernelParams {
   const float* rope_sin;
   int64_t rope_stride_b;
   MaskMeta mm;
-  int B, H, T, n_qt, n_qp;
+  const int4* plan;      // (B, 1 + plan_pairs) or nullptr
+  int plan_pairs;
+  int B, H, T;
+  int ranks, group, n_items, use_clc;   // items: ((g * ranks + r) * group + slice)
   float scale_log2, scale;
-  unsigned long long* trace;  // debug (AKI_MMA_FWD_TRACE=<cta>, tools/fwd_trace.py): clock64 stamps of one CTA
-  int trace_cta;
 };
-
-#ifdef AKI_FWD_TRACE
-#define TR(slot, j, k) do { if (tracing && (j) < 64) P.trace[((slot) * 64 + (j)) * 8 + (k)] = clock64(); } while (0)
-#else
-#define TR(slot, j, k) do { } while (0)
-#endif
 
 __device__ __forceinline__ uint32_t low_mask(int n) {  // n low bits set, n clamped to [0,32]
   return n <= 0 ? 0u : (n >= 32 ? 0xffffffffu : ((1u << n) - 1u));
@@ -98,20 +94,40 @@ __device__ __forceinline__ void umma_ts_lh(uint32_t d_tmem, uint32_t a_tmem, uin
       : "memory");
 }
 
-// Rare path of the online softmax: the running max grew by more than the threshold, this thread's 48 columns of O_t
-// are rescaled by alpha.  Kept out of line so that the per-tile loop stays compact.
-__device__ __noinline__ void rescale_o48(uint32_t tm_o, float alpha) {
-  uint32_t o[32];
-  tmem_ld_x32(tm_o, o);
-  tmem_wait_ld();
+// Cluster launch control: ask the hardware queue for the next not-yet-started CTA of this grid.
+__device__ __forceinline__ void clc_try_cancel(uint32_t resp_smem, uint32_t bar) {
+  asm volatile("clusterlaunchcontrol.try_cancel.async.shared::cta.mbarrier::complete_tx::bytes.b128 [%0], [%1];" ::"r"(
+                   resp_smem),
+               "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ bool clc_query(uint32_t resp_smem, uint32_t& cta_x) {
+  uint32_t valid = 0, x = 0;
+  asm volatile(
+      "{\n\t.reg .pred p1;\n\t.reg .b128 resp;\n\t"
+      "ld.shared.b128 resp, [%2];\n\t"
+      "clusterlaunchcontrol.query_cancel.is_canceled.pred.b128 p1, resp;\n\t"
+      "selp.u32 %1, 1, 0, p1;\n\t"
+      "@p1 clusterlaunchcontrol.query_cancel.get_first_ctaid::x.b32.b128 %0, resp;\n\t}\n"
+      : "=r"(x), "=r"(valid)
+      : "r"(resp_smem)
+      : "memory");
+  cta_x = x;
+  return valid != 0;
+}
+
+// Rare path of the online softmax: the running max grew by more than the threshold, this thread's row of O_t is
+// rescaled by alpha.  Kept out of line so that the per-pass loop stays compact.
+__device__ __noinline__ void rescale_o96(uint32_t tm_o, float alpha) {
+#pragma unroll 1
+  for (int c = 0; c < 6; ++c) {
+    uint32_t o[16];
+    tmem_ld_x16(tm_o + 16 * c, o);
+    tmem_wait_ld();
 #pragma unroll
-  for (int x = 0; x < 32; ++x) o[x] = __float_as_uint(__uint_as_float(o[x]) * alpha);
-  tmem_st_x32(tm_o, o);
-  tmem_ld_x16(tm_o + 32, o);
-  tmem_wait_ld();
-#pragma unroll
-  for (int x = 0; x < 16; ++x) o[x] = __float_as_uint(__uint_as_float(o[x]) * alpha);
-  tmem_st_x16(tm_o + 32, o);
+    for (int x = 0; x < 16; ++x) o[x] = __float_as_uint(__uint_as_float(o[x]) * alpha);
+    tmem_st_x16(tm_o + 16 * c, o);
+  }
   tmem_wait_st();
 }
 
@@ -123,491 +139,492 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   // barrier indices
-  constexpr int Q_FULL = 0, Q_READY = 2, K_FULL = 4, K_EMPTY = K_FULL + K_STAGES, V_FULL = K_EMPTY + K_STAGES,
-                V_EMPTY = V_FULL + STAGES, S_FULL = V_EMPTY + STAGES /* [t][buf] */, S_FREE = S_FULL + 4,
-                P_FULL = S_FREE + 4, O_FULL = P_FULL + 2, N_BARS = O_FULL + 2;
+  constexpr int Q_FULL = 0 /* [buf][tile] */, Q_READY = Q_FULL + 4 /* [buf] */, Q_EMPTY = Q_READY + 2 /* [buf] */,
+                K_FULL = Q_EMPTY + 2, K_EMPTY = K_FULL + K_STAGES, V_FULL = K_EMPTY + K_STAGES,
+                V_EMPTY = V_FULL + V_STAGES, S_FULL = V_EMPTY + V_STAGES /* [tile] */, S_FREE = S_FULL + 2,
+                P_FULL = S_FREE + 2, PV_DONE = P_FULL + 2, O_DONE = PV_DONE + 2, O_FREE = O_DONE + 2,
+                L_READY = O_FREE + 2, ITEM_FULL = L_READY + 2, ITEM_EMPTY = ITEM_FULL + SLOTS,
+                CLC_BAR = ITEM_EMPTY + SLOTS, N_BARS = CLC_BAR + 1;
   __shared__ __align__(8) uint64_t bars[N_BARS];
+  __shared__ __align__(16) int4 item_ring[SLOTS][3];   // {valid,b,h,len} {start0,start1,rows0,rows1} {nkv0,nkv1,nfull0,nfull1}
+  __shared__ __align__(16) uint4 clc_resp;
+  __shared__ float2 lm_s[2][128];                      // per tile, per row: (row sum, running max) of the finished item
   __shared__ uint32_t tmem_base_s;
-  __shared__ int first_bad_s;
-  __shared__ float xch[2][2][2][128];   // [key-tile parity][query tile][column half][row]: tile maxima, then row sums
   const uint32_t bar0 = smem_u32(bars);
   auto BAR = [&](int i) { return bar0 + 8u * i; };
 
-  const int tid = threadIdx.x, warp = tid >> 5;
-  // work decomposition: consecutive CTAs share (b,h) so K/V stay in L2; heaviest query tiles first
-  const int bh = blockIdx.x / P.n_qp;
-  const int qp = P.n_qp - 1 - (blockIdx.x % P.n_qp);
-  const int b = bh / P.H, h = bh % P.H;
-  const int n_kt = (P.T + BN - 1) / BN;            // 64-key tiles
-  int n_kv0, n_kv1;
-  {
-    int n[2];
-#pragma unroll
-    for (int t = 0; t < 2; ++t) {
-      const int qt = 2 * qp + t;
-      if (qt >= P.n_qt) n[t] = 0;
-      else if (P.mm.q_tile_kv_end) n[t] = min(2 * P.mm.q_tile_kv_end[(size_t)b * P.n_qt + qt], n_kt);  // 128 -> 64 units
-      else n[t] = min(2 * (qt + 1), n_kt);
-    }
-    n_kv0 = n[0]; n_kv1 = n[1];
-  }
-  const int n_max = max(n_kv0, n_kv1);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (tid == 0) {
-    for (int i = 0; i < 2; ++i) { mbar_init(BAR(Q_FULL + i), 1); mbar_init(BAR(Q_READY + i), 256); }
-    for (int i = 0; i < K_STAGES; ++i) { mbar_init(BAR(K_FULL + i), 1); mbar_init(BAR(K_EMPTY + i), 2); }
-    for (int i = 0; i < STAGES; ++i) { mbar_init(BAR(V_FULL + i), 1); mbar_init(BAR(V_EMPTY + i), 2); }   // one release per query tile
-    for (int i = 0; i < 4; ++i) { mbar_init(BAR(S_FULL + i), 1); mbar_init(BAR(S_FREE + i), 256); }
-    for (int i = 0; i < 2; ++i) { mbar_init(BAR(P_FULL + i), 256); mbar_init(BAR(O_FULL + i), 1); }
+    for (int i = 0; i < 4; ++i) mbar_init(BAR(Q_FULL + i), 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(BAR(Q_READY + i), 128); mbar_init(BAR(Q_EMPTY + i), 2); }
+    for (int i = 0; i < K_STAGES; ++i) { mbar_init(BAR(K_FULL + i), 1); mbar_init(BAR(K_EMPTY + i), 2); }   // one release per query tile
+    for (int i = 0; i < V_STAGES; ++i) { mbar_init(BAR(V_FULL + i), 1); mbar_init(BAR(V_EMPTY + i), 2); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(BAR(S_FULL + i), 1); mbar_init(BAR(S_FREE + i), 128);
+      mbar_init(BAR(P_FULL + i), 128); mbar_init(BAR(PV_DONE + i), 1);
+      mbar_init(BAR(O_DONE + i), 1); mbar_init(BAR(O_FREE + i), 128);
+      mbar_init(BAR(L_READY + i), 128);
+    }
+    for (int i = 0; i < SLOTS; ++i) { mbar_init(BAR(ITEM_FULL + i), 1); mbar_init(BAR(ITEM_EMPTY + i), 15); }
+    mbar_init(BAR(CLC_BAR), 1);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<512>(smem_u32(&tmem_base_s));
   if (warp == 0 && elect_one()) { tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_k); tma_prefetch_desc(&map_v); }
-  if (warp == 3) {
-    // first 64-key tile (among those this CTA visits) that is not entirely inside the sequence and causally valid
-    const int lane = tid & 31;
-    const int len = meta_len(P.mm, b, P.T);
-    int first = n_max;
-    for (int base = 0; base < n_max; base += 32) {
-      const int jt = base + lane;
-      bool bad = false;
-      if (jt < n_max) {
-        bad = (jt * BN + BN > len);
-        if (!bad && P.mm.vbits) {
-          const uint32_t* w = P.mm.vbits + (size_t)b * P.mm.bits_pitch + 2 * jt;
-          bad = (__ldg(w) != 0xffffffffu) || (__ldg(w + 1) != 0xffffffffu);
-        }
-      }
-      const uint32_t m = __ballot_sync(0xffffffffu, bad);
-      if (m) { first = base + __ffs(m) - 1; break; }
-    }
-    if (lane == 0) first_bad_s = first;
-  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
 
+  // every role walks the same sequence of items through the ring; n = running item count of the caller
+  auto item_wait = [&](uint32_t n, int4& v0, int4& v1, int4& v2) {
+    const int slot = n % SLOTS;
+    mbar_wait(BAR(ITEM_FULL + slot), (n / SLOTS) & 1);
+    v0 = item_ring[slot][0]; v1 = item_ring[slot][1]; v2 = item_ring[slot][2];
+  };
+
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     setmaxnreg_dec<REGS_CTRL>();
     if (elect_one()) {
-      for (int t = 0; t < 2; ++t) {
-        if ((t ? n_kv1 : n_kv0) == 0) continue;
-        mbar_arrive_expect_tx(BAR(Q_FULL + t), Q_TILE);
-        for (int a = 0; a < 3; ++a)
-          tma_load_4d(smem_base + SMEM_Q + t * Q_TILE + a * Q_ATOM, &map_q, BAR(Q_FULL + t), a * 32, (2 * qp + t) * BM, h, b);
-      }
-      auto load_k = [&](int j) {                 // the 128 keys of pass j/2 (rows beyond T are zero-filled)
-        const int pp = j >> 1, s = pp % K_STAGES;
-        mbar_wait(BAR(K_EMPTY + s), ((pp / K_STAGES) & 1) ^ 1);
-        mbar_arrive_expect_tx(BAR(K_FULL + s), K_PAIR_TILE);
-        for (int a = 0; a < 3; ++a)
-          tma_load_4d(smem_base + SMEM_K + s * K_PAIR_TILE + a * K_PAIR_ATOM, &map_k, BAR(K_FULL + s), a * 32, j * BN, h, b);
+      uint32_t n_it = 0, n_q = 0, kc = 0, vc = 0;
+      bool q_end = false;
+      auto issue_q = [&](uint32_t n, const int4& v0, const int4& v1, const int4& v2) {
+        const int buf = n & 1;
+        for (int t = 0; t < 2; ++t) {
+          const uint32_t bar = BAR(Q_FULL + 2 * buf + t);
+          if ((t ? v2.y : v2.x) > 0) {
+            mbar_arrive_expect_tx(bar, TILE_BYTES);
+            for (int a = 0; a < 3; ++a)
+              tma_load_4d(smem_base + SMEM_Q + (2 * buf + t) * TILE_BYTES + a * ATOM, &map_q, bar, a * 32, t ? v1.y : v1.x, v0.z, v0.y);
+          } else {
+            mbar_arrive(bar);
+          }
+        }
       };
-      auto load_v = [&](int j) {
-        const int s = j % STAGES;
-        mbar_wait(BAR(V_EMPTY + s), ((j / STAGES) & 1) ^ 1);
-        mbar_arrive_expect_tx(BAR(V_FULL + s), KV_TILE);
-        for (int a = 0; a < 3; ++a)
-          tma_load_4d(smem_base + SMEM_V + s * KV_TILE + a * KV_ATOM, &map_v, BAR(V_FULL + s), a * 32, j * BN, h, b);
-      };
-      // consumption order of the MMA warps (two key tiles per pass): K01 | K23 V0 V1 | K45 V2 V3 | ...
-      if (n_max > 0) load_k(0);
-      for (int j = 0; j < n_max; j += 2) {
-        if (j + 2 < n_max) load_k(j + 2);
-        load_v(j);
-        if (j + 1 < n_max) load_v(j + 1);
+      for (;;) {
+        int4 v0, v1, v2;
+        item_wait(n_it, v0, v1, v2);
+        if (!v0.x) break;
+        if (n_q == n_it) {
+          mbar_wait(BAR(Q_EMPTY + (n_q & 1)), ((n_q >> 1) & 1) ^ 1);
+          issue_q(n_q, v0, v1, v2);
+          ++n_q;
+        }
+        const int b = v0.y, h = v0.z, n_max = max(v2.x, v2.y);
+        // Q of the next item as soon as its descriptor and its buffer are there (never blocks the K/V stream)
+        auto try_next_q = [&]() {
+          if (q_end || n_q != n_it + 1) return;
+          const int slot = n_q % SLOTS;
+          if (!mbar_test(BAR(ITEM_FULL + slot), (n_q / SLOTS) & 1)) return;
+          const int4 w0 = item_ring[slot][0];
+          if (!w0.x) { q_end = true; return; }
+          if (!mbar_test(BAR(Q_EMPTY + (n_q & 1)), ((n_q >> 1) & 1) ^ 1)) return;
+          issue_q(n_q, w0, item_ring[slot][1], item_ring[slot][2]);
+          ++n_q;
+        };
+        auto load_k = [&](int j) {                 // 128 keys (rows beyond T are zero-filled)
+          const uint32_t c = kc + j, s = c % K_STAGES;
+          mbar_wait(BAR(K_EMPTY + s), ((c / K_STAGES) & 1) ^ 1);
+          mbar_arrive_expect_tx(BAR(K_FULL + s), TILE_BYTES);
+          for (int a = 0; a < 3; ++a)
+            tma_load_4d(smem_base + SMEM_K + s * TILE_BYTES + a * ATOM, &map_k, BAR(K_FULL + s), a * 32, j * BN, h, b);
+        };
+        auto load_v = [&](int j) {
+          const uint32_t c = vc + j, s = c % V_STAGES;
+          mbar_wait(BAR(V_EMPTY + s), ((c / V_STAGES) & 1) ^ 1);
+          mbar_arrive_expect_tx(BAR(V_FULL + s), TILE_BYTES);
+          for (int a = 0; a < 3; ++a)
+            tma_load_4d(smem_base + SMEM_V + s * TILE_BYTES + a * ATOM, &map_v, BAR(V_FULL + s), a * 32, j * BN, h, b);
+        };
+        // consumption order of the MMA warps: K0 | K1 V0 | K2 V1 | ...
+        if (n_max > 0) load_k(0);
+        for (int j = 0; j < n_max; ++j) {
+          try_next_q();
+          if (j + 1 < n_max) load_k(j + 1);
+          load_v(j);
+        }
+        kc += n_max; vc += n_max;
+        mbar_arrive(BAR(ITEM_EMPTY + n_it % SLOTS));
+        ++n_it;
       }
     }
-  } else if (warp == 1 || warp == 3) {
-    // ------------------------------------------------------------------ QK^T issuers: warp 1 -> query tile 0, warp 3 -> tile 1
-    // An issuing thread streams M=128,K=16 MMAs at ~64-80 cycles each whatever N is (tools/mma_mix_bench.cu), so the
-    // MMA work is spread over three warps: one QK^T issuer per query tile and one PV issuer (warp 2).  The whole warp
-    // runs the loop so that addresses / descriptors stay in uniform registers; one elected lane issues.  Every K / V
-    // stage is released by one arrival per query tile: a commit behind the MMA that read it, or a plain arrive when
-    // that tile does not visit the key tile.
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ scheduler
     setmaxnreg_dec<REGS_CTRL>();
-    const int t = (warp == 3) ? 1 : 0;
-    const int nk = t ? n_kv1 : n_kv0;
-    const bool leader = elect_one();
-#ifdef AKI_FWD_TRACE
-    const bool tracing = P.trace && (int)blockIdx.x == P.trace_cta && leader;
-#endif
-    // One N=128 MMA group per pass: S_t(j) | S_t(j+1) = Q_t [K_j ; K_j+1]^T lands in the tile's 128 score columns.  An
-    // M=128,K=16 MMA costs ~64-76 cycles whether N is 64 or 128, so two N=64 groups took twice the tensor-pipe time.
-    constexpr uint32_t IDESC_QK128 = umma_idesc_bf16(BM, 2 * BN, 0, 0), IDESC_QK64 = umma_idesc_bf16(BM, BN, 0, 0);
-    const uint64_t DESC_KMAJ = umma_smem_desc(0, 16, 512, UMMA_SW64);
-    const uint32_t HI = (uint32_t)(DESC_KMAJ >> 32), KMAJ_LO = (uint32_t)DESC_KMAJ;
-    const uint32_t qa = KMAJ_LO + ((smem_base + SMEM_Q + t * Q_TILE) >> 4), k_lo = KMAJ_LO + ((smem_base + SMEM_K) >> 4);
-    if (nk > 0) mbar_wait(BAR((ROPE ? Q_READY : Q_FULL) + t), 0);
-    // Pass p handles key tiles j = 2p, 2p+1.  The softmax frees both S buffers at the same moment; the chain
-    // S_FREE -> S(j+2), S(j+3) is the critical path of a pass.  Every K stage is released by one arrival per query
-    // tile: a commit behind the MMAs that read it, or a plain arrive when this tile does not visit these keys.
-    for (int j = 0; j < n_max; j += 2) {
-      const int pp = j >> 1, s = pp % K_STAGES;
-      // waited for even when this tile skips the keys: it keeps the tile from running a whole ring ahead and
-      // arriving twice in one K_EMPTY phase
-      mbar_wait(BAR(K_FULL + s), (pp / K_STAGES) & 1);
-      if (j < nk) {
-        const bool two = (j + 1 < nk);
-        if (j >= 2) {                           // the softmax holds S_t(j-2), S_t(j-1) in registers
-          mbar_wait(BAR(S_FREE + 2 * t + 0), ((j - 2) >> 1) & 1);
-          if (two) mbar_wait(BAR(S_FREE + 2 * t + 1), ((j - 1) >> 1) & 1);
+    if (lane == 0) {
+      uint32_t n_pub = 0, n_clc = 0;
+      long long id = blockIdx.x;
+      const int n_kt = (P.T + BN - 1) / BN;
+      auto publish = [&](const int4& v0, const int4& v1, const int4& v2) {
+        const int slot = n_pub % SLOTS;
+        mbar_wait(BAR(ITEM_EMPTY + slot), ((n_pub / SLOTS) & 1) ^ 1);
+        item_ring[slot][0] = v0; item_ring[slot][1] = v1; item_ring[slot][2] = v2;
+        mbar_arrive(BAR(ITEM_FULL + slot));
+        ++n_pub;
+      };
+      for (;;) {
+        // item id -> (group of slices, rank inside the plan, slice)
+        const int per_group = P.ranks * P.group;
+        const int g = (int)(id / per_group), rem = (int)(id % per_group);
+        const int r = rem / P.group, bh = g * P.group + rem % P.group;
+        if (bh < P.B * P.H) {
+          const int b = bh / P.H, h = bh % P.H;
+          const int len = meta_len(P.mm, b, P.T);
+          int4 e = make_int4(0, 0, 0, 0);
+          int first_bad = 0;
+          bool ok = false;
+          if (P.plan) {
+            const int4* row = P.plan + (size_t)b * (1 + P.plan_pairs);
+            const int4 hdr = __ldg(row);
+            if (r < hdr.x) { e = __ldg(row + 1 + r); first_bad = hdr.y; ok = true; }
+          } else {
+            // no plan: aligned tiles (2p, 2p+1), heaviest pair first
+            const int n_qt = (P.T + BM - 1) / BM, p = P.ranks - 1 - r;
+            if (p >= 0 && 2 * p < n_qt) {
+              ok = true;
+              for (int t = 0; t < 2; ++t) {
+                const int qt = 2 * p + t;
+                int nk = 0, rows = 0;
+                if (qt < n_qt) {
+                  rows = min(BM, P.T - qt * BM);
+                  nk = P.mm.q_tile_kv_end ? min(__ldg(P.mm.q_tile_kv_end + (size_t)b * n_qt + qt), n_kt) : min(qt + 1, n_kt);
+                }
+                if (t == 0) { e.x = qt * BM; e.z = nk | (rows << 16); }
+                else { e.y = (qt < n_qt) ? qt * BM : 0; e.w = nk | (rows << 16); }
+              }
+              // without a plan nobody scanned the key bit-vectors: every tile is evaluated against the predicate
+              first_bad = (P.mm.seq_len || P.mm.vbits) ? 0 : P.T / BN;
+            }
+          }
+          if (ok) {
+            const int nk0 = e.z & 0xffff, nk1 = e.w & 0xffff;
+            publish(make_int4(1, b, h, len), make_int4(e.x, e.y, e.z >> 16, e.w >> 16),
+                    make_int4(nk0, nk1, min(first_bad, (e.x + 1) / BN), min(first_bad, (e.y + 1) / BN)));
+          }
         }
-        tc_fence_after();
-        TR(4 + t, j, 0);
-        const uint32_t ka = k_lo + s * (K_PAIR_TILE >> 4);
-        const uint32_t d = tmem + TM_S + 128 * t;
-        if (leader) {
-#pragma unroll
-          for (int k = 0; k < 6; ++k)
-            umma_ss_lh(d, qa + (((k >> 1) * Q_ATOM + (k & 1) * 32) >> 4), ka + (((k >> 1) * K_PAIR_ATOM + (k & 1) * 32) >> 4), HI,
-                       two ? IDESC_QK128 : IDESC_QK64, k > 0);
-          umma_commit(BAR(S_FULL + 2 * t + 0));
-          if (two) umma_commit(BAR(S_FULL + 2 * t + 1));
-          umma_commit(BAR(K_EMPTY + s));
+        if (!P.use_clc) {
+          id += gridDim.x;
+          if (id >= P.n_items) break;
+          continue;
         }
-        TR(4 + t, j, 1);
-      } else if (leader) {
-        mbar_arrive(BAR(K_EMPTY + s));
+        mbar_arrive_expect_tx(BAR(CLC_BAR), 16);
+        clc_try_cancel(smem_u32(&clc_resp), BAR(CLC_BAR));
+        mbar_wait(BAR(CLC_BAR), n_clc & 1);
+        ++n_clc;
+        uint32_t next;
+        const bool got = clc_query(smem_u32(&clc_resp), next);
+        fence_proxy_async_smem();     // the response buffer is rewritten by the next (async-proxy) query
+        if (!got) break;
+        id = next;
       }
-      __syncwarp();
+      publish(make_int4(0, 0, 0, 0), make_int4(0, 0, 0, 0), make_int4(0, 0, 0, 0));
     }
-  } else if (warp == 2) {
-    // ------------------------------------------------------------------ PV issuer of both query tiles
-    // O_t += P_t V_j (TS, P read from TMEM).  Polls the two tiles' P_FULL barriers and serves whichever is ready, so
-    // neither tile waits behind the other; tiles that do not visit key tile j just release the V stage.
+  } else if (warp == 2 || warp == 3) {
+    // ------------------------------------------------------------------ MMA issuer of query tile t
+    // Per pass j of this tile: QK^T(j+1) as soon as the softmax has taken S(j) out of TMEM, then PV(j) in two halves
+    // as the softmax publishes them -- the program order of the softmax threads, so plain blocking waits suffice.
+    // K / V stages and the Q buffer are released by one arrival per query tile: a commit behind the MMAs that read
+    // them, or a plain arrive when this tile does not visit those keys.
     setmaxnreg_dec<REGS_CTRL>();
-    const bool leader = elect_one();
-#ifdef AKI_FWD_TRACE
-    const bool tracing = P.trace && (int)blockIdx.x == P.trace_cta && leader;
-#endif
-    constexpr uint32_t IDESC_PV = umma_idesc_bf16(BM, HD, 0, 1);
-    const uint64_t DESC_V = umma_smem_desc(0, KV_ATOM, 512, UMMA_SW64);     // MN-major: LBO = atom stride
-    const uint32_t HI = (uint32_t)(DESC_V >> 32), v_lo = (uint32_t)DESC_V + ((smem_base + SMEM_V) >> 4);
-    int jt[2] = {0, 0};
-    while (jt[0] < n_max || jt[1] < n_max) {
-      bool progressed = false;
+    const int t = warp - 2;
+    if (elect_one()) {
+      constexpr uint32_t IDESC_QK = umma_idesc_bf16(BM, BN, 0, 0), IDESC_PV = umma_idesc_bf16(BM, HD, 0, 1);
+      const uint64_t DESC_KMAJ = umma_smem_desc(0, 16, 512, UMMA_SW64);
+      const uint64_t DESC_V = umma_smem_desc(0, ATOM, 512, UMMA_SW64);     // MN-major: LBO = atom stride
+      const uint32_t HI_K = (uint32_t)(DESC_KMAJ >> 32), KMAJ_LO = (uint32_t)DESC_KMAJ;
+      const uint32_t HI_V = (uint32_t)(DESC_V >> 32), v_lo = (uint32_t)DESC_V + ((smem_base + SMEM_V) >> 4);
+      const uint32_t k_lo = KMAJ_LO + ((smem_base + SMEM_K) >> 4);
+      const uint32_t d_s = tmem + TM_S + 128 * t, d_o = tmem + TM_O + 96 * t, a_p = tmem + TM_P + 32 * t;
+      uint32_t n_it = 0, kc = 0, vc = 0, n_qk = 0, n_ph = 0;
+      for (;;) {
+        int4 v0, v1, v2;
+        item_wait(n_it, v0, v1, v2);
+        if (!v0.x) break;
+        const int nk = t ? v2.y : v2.x, n_max = max(v2.x, v2.y), buf = n_it & 1;
+        const uint32_t qa = KMAJ_LO + ((smem_base + SMEM_Q + (2 * buf + t) * TILE_BYTES) >> 4);
+        if (nk > 0) mbar_wait(ROPE ? BAR(Q_READY + buf) : BAR(Q_FULL + 2 * buf + t), (n_it >> 1) & 1);
+        else mbar_arrive(BAR(Q_EMPTY + buf));
+        auto handle_k = [&](int j) {
+          const uint32_t c = kc + j, s = c % K_STAGES;
+          // waited for even when this tile skips the keys: it keeps the tile from running a whole ring ahead and
+          // arriving twice in one K_EMPTY phase
+          mbar_wait(BAR(K_FULL + s), (c / K_STAGES) & 1);
+          if (j < nk) {
+            if (n_qk > 0) mbar_wait(BAR(S_FREE + t), (n_qk - 1) & 1);   // the softmax holds the previous S in registers
+            tc_fence_after();
+            const uint32_t ka = k_lo + s * (TILE_BYTES >> 4);
 #pragma unroll
-      for (int t = 0; t < 2; ++t) {
-        const int j = jt[t];
-        if (j >= n_max) continue;
-        const int nk = t ? n_kv1 : n_kv0;
-        const int s = j % STAGES;
-        if (!mbar_test(BAR(V_FULL + s), (j / STAGES) & 1)) continue;
-        if (j < nk) {
-          if (!mbar_test(BAR(P_FULL + t), j & 1)) continue;
-          tc_fence_after();
-          TR(4 + t, j, 3);
-          const uint32_t va = v_lo + s * (KV_TILE >> 4);
-          const uint32_t d_o = tmem + TM_O + 96 * t, a_p = tmem + TM_P + 32 * t;
-          if (leader) {
+            for (int k = 0; k < 6; ++k)
+              umma_ss_lh(d_s, qa + (((k >> 1) * ATOM + (k & 1) * 32) >> 4), ka + (((k >> 1) * ATOM + (k & 1) * 32) >> 4), HI_K,
+                         IDESC_QK, k > 0);
+            umma_commit(BAR(S_FULL + t));
+            umma_commit(BAR(K_EMPTY + s));
+            if (j == nk - 1) umma_commit(BAR(Q_EMPTY + buf));
+            ++n_qk;
+          } else {
+            mbar_arrive(BAR(K_EMPTY + s));
+          }
+        };
+        if (n_max > 0) handle_k(0);
+        for (int j = 0; j < n_max; ++j) {
+          if (j + 1 < n_max) handle_k(j + 1);
+          const uint32_t c = vc + j, s = c % V_STAGES;
+          mbar_wait(BAR(V_FULL + s), (c / V_STAGES) & 1);
+          if (j < nk) {
+            if (j == 0 && n_it > 0) mbar_wait(BAR(O_FREE + t), (n_it - 1) & 1);   // the epilogue has read the previous O_t
+            const uint32_t va = v_lo + s * (TILE_BYTES >> 4);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) umma_ts_lh(d_o, a_p + 8 * k, va + k * 64, HI, IDESC_PV, (j > 0 || k > 0));
-            umma_commit(BAR(O_FULL + t));
+            for (int half = 0; half < 2; ++half) {
+              mbar_wait(BAR(P_FULL + t), n_ph & 1);
+              ++n_ph;
+              tc_fence_after();
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_ts_lh(d_o, a_p + 8 * k, va + (4 * half + k) * 64, HI_V, IDESC_PV, (j > 0 || half > 0 || k > 0));
+              umma_commit(BAR(PV_DONE + t));
+            }
             umma_commit(BAR(V_EMPTY + s));
+            if (j == nk - 1) umma_commit(BAR(O_DONE + t));
+          } else {
+            mbar_arrive(BAR(V_EMPTY + s));
           }
-          TR(4 + t, j, 4);
-        } else if (leader) {
-          mbar_arrive(BAR(V_EMPTY + s));
         }
-        __syncwarp();
-        jt[t] = j + 1;
-        progressed = true;
+        kc += n_max; vc += n_max;
+        mbar_arrive(BAR(ITEM_EMPTY + n_it % SLOTS));
+        ++n_it;
       }
-#ifndef AKI_PV_SLEEP
-#define AKI_PV_SLEEP 32         // ns between polls of the PV issuer when neither tile is ready (A/B: 0 = busy poll)
-#endif
-      if (!progressed && AKI_PV_SLEEP > 0) __nanosleep(AKI_PV_SLEEP);
     }
-  } else {
-    // ------------------------------------------------------------------ softmax / correction / epilogue
+  } else if (warp < 12) {
+    // ------------------------------------------------------------------ softmax: one thread per score row
     setmaxnreg_inc<REGS_SOFTMAX>();
-    const int sw = warp - 4;
-    const int t = sw >> 3, ch = (sw >> 2) & 1, g = sw & 3;   // query tile, column half, lane group (== warp % 4)
-    const int r = 32 * g + (tid & 31);            // row within the tile == TMEM lane
-    const int qt = 2 * qp + t;
-    const int i = qt * BM + r;                    // query index in mask coordinates
-    const int len = meta_len(P.mm, b, P.T);
+    const int t = (warp - 4) >> 2, g = warp & 3;
+    const int r = 32 * g + lane;                  // row within the tile == TMEM lane
     const uint32_t lane_base = (uint32_t)(g * 32) << 16;
-    const uint32_t tm_s = tmem + TM_S + 128 * t + 32 * ch + lane_base;
-    const uint32_t tm_o = tmem + TM_O + 96 * t + 48 * ch + lane_base;
-    const uint32_t tm_p = tmem + TM_P + 32 * t + 16 * ch + lane_base;
-    const int pair_bar = 1 + 4 * t + g;           // named barrier of the two warps that share these rows
-    const int nk = t ? n_kv1 : n_kv0;
-    // key tiles j < n_full lie entirely below the diagonal of this query tile and hold no padding
-    const int n_full = min(first_bad_s, 2 * qt);
-
-    if (ROPE && nk > 0) {
-      mbar_wait(BAR(Q_FULL + t), 0);
-      if (i < P.T) {
-        const uint32_t qa = smem_base + SMEM_Q + t * Q_TILE;
-        const float* cr = P.rope_cos + (size_t)b * P.rope_stride_b + (size_t)i * 48;
-        const float* sr = P.rope_sin + (size_t)b * P.rope_stride_b + (size_t)i * 48;
+    const uint32_t tm_s = tmem + TM_S + 128 * t + lane_base;
+    const uint32_t tm_o = tmem + TM_O + 96 * t + lane_base;
+    const uint32_t tm_p = tmem + TM_P + 32 * t + lane_base;
+    uint32_t n_it = 0, n_s = 0, n_pvh = 0;
+    for (;;) {
+      int4 v0, v1, v2;
+      item_wait(n_it, v0, v1, v2);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(BAR(ITEM_EMPTY + n_it % SLOTS));
+      if (!v0.x) break;
+      const int b = v0.y, len = v0.w;
+      const int nk = t ? v2.y : v2.x, n_full = t ? v2.w : v2.z;
+      const int i = (t ? v1.y : v1.x) + r;        // query index in mask coordinates
+      const bool row_live = (i < len);
+      int row_lo = 0, row_hi = 0;
+      if (row_live && P.mm.row_lo && nk > 0) {
+        row_lo = __ldg(P.mm.row_lo + (size_t)b * P.mm.meta_pitch + i);
+        row_hi = __ldg(P.mm.row_hi + (size_t)b * P.mm.meta_pitch + i);
+      }
+      float m_used = -INFINITY;  // running max (raw score units) the accumulators are expressed against
+      float l = 0.f;             // row sum
+      for (int j = 0; j < nk; ++j) {
+        const bool partial = (j >= n_full);            // warp-uniform (CTA-uniform)
+        uint32_t vw[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+        uint32_t mw[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+        if (partial) {                                 // one 32-bit word of each bit-vector covers 32 keys
 #pragma unroll
-        for (int cc = 0; cc < 3; ++cc) {          // 16-byte chunk c pairs with chunk c+6 (d <-> d+48)
-          const int c = 3 * ch + cc;
-          const uint32_t a_lo = qa + (c >> 2) * Q_ATOM + sw64_offset(r, c & 3);
-          const uint32_t a_hi = qa + ((c + 6) >> 2) * Q_ATOM + sw64_offset(r, (c + 6) & 3);
-          uint4 lo, hi;
-          asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w) : "r"(a_lo));
-          asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w) : "r"(a_hi));
-          float cs[8], sn[8];
-          *reinterpret_cast<float4*>(cs) = __ldg(reinterpret_cast<const float4*>(cr + c * 8));
-          *reinterpret_cast<float4*>(cs + 4) = __ldg(reinterpret_cast<const float4*>(cr + c * 8 + 4));
-          *reinterpret_cast<float4*>(sn) = __ldg(reinterpret_cast<const float4*>(sr + c * 8));
-          *reinterpret_cast<float4*>(sn + 4) = __ldg(reinterpret_cast<const float4*>(sr + c * 8 + 4));
-          const __nv_bfloat162* l2 = reinterpret_cast<const __nv_bfloat162*>(&lo);
-          const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&hi);
-          uint32_t lo_w[4], hi_w[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float2 lf = __bfloat1622float2(l2[e]), hf2 = __bfloat1622float2(h2[e]);
-            lo_w[e] = pack_bf16x2(lf.x * cs[2 * e] - hf2.x * sn[2 * e], lf.y * cs[2 * e + 1] - hf2.y * sn[2 * e + 1]);
-            hi_w[e] = pack_bf16x2(hf2.x * cs[2 * e] + lf.x * sn[2 * e], hf2.y * cs[2 * e + 1] + lf.y * sn[2 * e + 1]);
+          for (int w = 0; w < 4; ++w) {
+            const int wi = 4 * j + w;
+            if (P.mm.vbits) vw[w] = (wi < P.mm.bits_pitch) ? __ldg(P.mm.vbits + (size_t)b * P.mm.bits_pitch + wi) : 0u;
+            if (P.mm.mbits) mw[w] = (wi < P.mm.bits_pitch) ? __ldg(P.mm.mbits + (size_t)b * P.mm.bits_pitch + wi) : 0u;
           }
-          asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a_lo), "r"(lo_w[0]), "r"(lo_w[1]), "r"(lo_w[2]), "r"(lo_w[3]) : "memory");
-          asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a_hi), "r"(hi_w[0]), "r"(hi_w[1]), "r"(hi_w[2]), "r"(hi_w[3]) : "memory");
         }
-      }
-      fence_proxy_async_smem();
-      mbar_arrive(BAR(Q_READY + t));
-    }
-
-    int row_lo = 0, row_hi = 0;
-    const bool row_live = (i < len);
-    if (row_live && P.mm.row_lo) {
-      row_lo = P.mm.row_lo[(size_t)b * P.mm.meta_pitch + i];
-      row_hi = P.mm.row_hi[(size_t)b * P.mm.meta_pitch + i];
-    }
-    float m_used = -INFINITY;  // running max (raw score units) the accumulators are expressed against
-    float l = 0.f;             // row sum over this warp's column halves
-    int o_waited = 0;          // number of O_FULL phases this thread has already observed
-
-#ifdef AKI_FWD_TRACE
-    const bool tracing = P.trace && (int)blockIdx.x == P.trace_cta && g == 0 && (tid & 31) == 0;
-    const int slot = 2 * t + ch;
-#endif
-    // All four softmax warps of an SM sub-partition share its 4 MUFU lanes.  Tile 1 starts when tile 0 has finished
-    // its first batch of exponentials, so that from then on one tile's exp2 phase covers the other tile's barrier
-    // probes / TMEM round trips (clock64 trace: started together, the tiles stay in phase and the exp2 phase of
-    // all four warps takes 1240 cycles while the pipe idles for the other 1100 of each key tile).
-#ifndef AKI_PV_FIRST
-#define AKI_PV_FIRST 1          // 1: publish P(j) before handing the S buffers back, so that PV(j) queues ahead of the
-                                // next pass's QK^T in the tensor pipe (same-box A/B: 1.047 -> 1.038 ms causal); 0: the reverse
-#endif
-#ifndef AKI_ONE_EXP_PHASE
-#define AKI_ONE_EXP_PHASE 0     // 1: both key tiles of a pass are exponentiated in ONE phase before P(j) is published (A/B)
-#endif
-#ifndef AKI_STAGGER_POINT
-#define AKI_STAGGER_POINT 1     // where tile 0 releases tile 1: 0 never staggered, 1 after its first exponentials (shipped),
-#endif                          // 2 after its first TMEM load, 3 at the end of its first pass  (A/B builds only)
-    const bool stagger = (AKI_STAGGER_POINT != 0) && (n_kv0 > 0 && n_kv1 > 0);
-    if (stagger && t == 1) named_bar_sync(9, 512);
-    // Two key tiles per pass: the fixed per-tile latencies (mbarrier probes, TMEM round trips, the max exchange of the
-    // two column halves) cost ~1000 cycles against ~500 of exponentials, so they are paid once per PAIR of key tiles:
-    // both S buffers are fetched together, one exchange covers both, P(j) is published and PV(j) runs while the
-    // exponentials of tile j+1 are computed, then P(j+1) follows.  Exponentials overwrite the scores in place (bf16
-    // pairs compacted into the low registers), so the 64 scores of a pass are the only large register array.
-    // (A lock that made the two tiles' exp2 phases alternate on the 4 MUFU lanes of a sub-partition was tried: the
-    // extra barrier + CAS round trips cost more than the idle MUFU time they removed, 1.38 -> 1.59 ms.)
-    bool s_ready0 = false, s_ready1 = false;        // early probes of S_FULL for the next pass
-    for (int j = 0; j < nk; j += 2) {
-      TR(slot, j, 0);
-      const bool two = (j + 1 < nk);                // warp-uniform
-      const int xp = (j >> 1) & 1;                  // exchange-buffer parity of this pass
-      const int c0 = j * BN + 32 * ch;              // first key column of this thread's half of tile j
-      const bool partial0 = (j >= n_full), partial1 = two && (j + 1 >= n_full);
-      uint32_t vw0 = 0xffffffffu, mw0 = 0xffffffffu, vw1 = 0xffffffffu, mw1 = 0xffffffffu;
-      if (partial0) {                               // one 32-bit word of each bit-vector covers a half tile
-        if (P.mm.vbits) vw0 = __ldg(P.mm.vbits + (size_t)b * P.mm.bits_pitch + (c0 >> 5));
-        if (P.mm.mbits) mw0 = __ldg(P.mm.mbits + (size_t)b * P.mm.bits_pitch + (c0 >> 5));
-      }
-      if (partial1) {
-        if (P.mm.vbits) vw1 = __ldg(P.mm.vbits + (size_t)b * P.mm.bits_pitch + ((c0 + BN) >> 5));
-        if (P.mm.mbits) mw1 = __ldg(P.mm.mbits + (size_t)b * P.mm.bits_pitch + ((c0 + BN) >> 5));
-      }
-      // probe "PV(j-1) has consumed P(j-1)" now, use the answer just before the P store
-      const bool o_known = (j == 0) || (o_waited >= j) || mbar_test(BAR(O_FULL + t), (j - 1) & 1);
-
-      float s[64];                                   // [0,32): this half of S_t(j); [32,64): this half of S_t(j+1)
-      auto mask32 = [&](int off, int col0, uint32_t vw, uint32_t mw) {
-        const int d = row_live ? (i - col0) : -1;             // causal: column c visible iff c <= d
-        const int a = row_lo - col0, e = row_hi - col0;       // mutual: a <= c < e
-        const uint32_t in_len = low_mask(len - col0);
-        const uint32_t causal = low_mask(d + 1) & vw & in_len;
-        const uint32_t mutual = row_live ? (low_mask(e) & ~low_mask(a) & mw & in_len) : 0u;
-        const uint32_t ok = causal | mutual;
-#pragma unroll
-        for (int c = 0; c < 32; ++c)
-          if (!((ok >> c) & 1u)) s[off + c] = -INFINITY;
-      };
-      auto fetch0 = [&]() {                          // (re)load this half of S_t(j) and mask it
-        tmem_ld_x32(tm_s + 64 * (j & 1), reinterpret_cast<uint32_t*>(s));
+        float s[128];
+        mbar_wait(BAR(S_FULL + t), n_s & 1);
+        ++n_s;
+        tc_fence_after();
+        tmem_ld_x32(tm_s, reinterpret_cast<uint32_t*>(s));
+        tmem_ld_x32(tm_s + 32, reinterpret_cast<uint32_t*>(s) + 32);
+        tmem_ld_x32(tm_s + 64, reinterpret_cast<uint32_t*>(s) + 64);
+        tmem_ld_x32(tm_s + 96, reinterpret_cast<uint32_t*>(s) + 96);
         tmem_wait_ld();
-        if (partial0) mask32(0, c0, vw0, mw0);
-      };
-      if (!s_ready0) mbar_wait(BAR(S_FULL + 2 * t + (j & 1)), (j >> 1) & 1);
-      if (two && !s_ready1) mbar_wait(BAR(S_FULL + 2 * t + ((j + 1) & 1)), ((j + 1) >> 1) & 1);
-      tc_fence_after();
-      TR(slot, j, 1);
-      tmem_ld_x32(tm_s + 64 * (j & 1), reinterpret_cast<uint32_t*>(s));
-      if (two) tmem_ld_x32(tm_s + 64 * ((j + 1) & 1), reinterpret_cast<uint32_t*>(s) + 32);
-      tmem_wait_ld();
-      TR(slot, j, 2);
-      if (AKI_STAGGER_POINT == 2 && stagger && t == 0 && j == 0) asm volatile("bar.arrive 9, 512;" ::: "memory");
-      if (partial0) mask32(0, c0, vw0, mw0);
-      if (partial1) mask32(32, c0 + BN, vw1, mw1);
-      // ---- maximum of this thread's scores of the pass; the partner half's arrives through shared memory
-      // three-input maxima (FMNMX3): two scores per instruction, four independent chains
-      float mx[4] = {fmax3(s[0], s[1], s[2]), fmax3(s[3], s[4], s[5]), fmax3(s[6], s[7], s[8]), fmax3(s[9], s[10], s[11])};
+        tc_fence_before();
+        mbar_arrive(BAR(S_FREE + t));                  // QK^T of the next pass runs under the exponentials
+        if (partial) {
 #pragma unroll
-      for (int c = 12; c < 28; c += 8) {
-        mx[0] = fmax3(mx[0], s[c], s[c + 1]); mx[1] = fmax3(mx[1], s[c + 2], s[c + 3]);
-        mx[2] = fmax3(mx[2], s[c + 4], s[c + 5]); mx[3] = fmax3(mx[3], s[c + 6], s[c + 7]);
-      }
-      mx[0] = fmax3(mx[0], s[28], s[29]); mx[1] = fmax3(mx[1], s[30], s[31]);
-      if (two) {
+          for (int w = 0; w < 4; ++w) {
+            const int col0 = j * BN + 32 * w;
+            const int d = row_live ? (i - col0) : -1;             // causal: column c visible iff c <= d
+            const int a = row_lo - col0, e = row_hi - col0;       // mutual: a <= c < e
+            const uint32_t in_len = low_mask(len - col0);
+            const uint32_t causal = low_mask(d + 1) & vw[w] & in_len;
+            const uint32_t mutual = row_live ? (low_mask(e) & ~low_mask(a) & mw[w] & in_len) : 0u;
+            const uint32_t ok = causal | mutual;
 #pragma unroll
-        for (int c = 32; c < 64; c += 8) {
+            for (int c = 0; c < 32; ++c)
+              if (!((ok >> c) & 1u)) s[32 * w + c] = -INFINITY;
+          }
+        }
+        // ---- row maximum: three-input maxima (FMNMX3), four independent chains
+        float mx[4] = {fmax3(s[0], s[1], s[2]), fmax3(s[3], s[4], s[5]), fmax3(s[6], s[7], s[8]), fmax3(s[9], s[10], s[11])};
+#pragma unroll
+        for (int c = 12; c < 124; c += 8) {
           mx[0] = fmax3(mx[0], s[c], s[c + 1]); mx[1] = fmax3(mx[1], s[c + 2], s[c + 3]);
           mx[2] = fmax3(mx[2], s[c + 4], s[c + 5]); mx[3] = fmax3(mx[3], s[c + 6], s[c + 7]);
         }
-      }
-      const float m_half = fmaxf(fmax3(mx[0], mx[1], mx[2]), mx[3]);
-      xch[xp][t][ch][r] = m_half;
-      // exp2((S - m_used) * scale*log2e) of 32 scores starting at `off`, packed IN PLACE into s[off .. off+16)
-      auto exps = [&](int off) {
-        const float neg_m = (m_used == -INFINITY) ? 0.f : -m_used * P.scale_log2;
-        // packed FFMA2 / FADD2: one scale-and-shift and one row-sum instruction per PAIR of scores
-        const uint64_t sc2 = f32x2_pack(P.scale_log2, P.scale_log2), nm2 = f32x2_pack(neg_m, neg_m);
-        uint64_t sum_a = f32x2_pack(0.f, 0.f), sum_b = sum_a;
-#pragma unroll
-        for (int x = 0; x < 16; ++x) {
-          float a0, a1;
-          f32x2_unpack(f32x2_fma(f32x2_pack(s[off + 2 * x], s[off + 2 * x + 1]), sc2, nm2), a0, a1);
-          const float p0 = ex2_approx(a0), p1 = ex2_approx(a1);
-          if (x & 1) sum_b = f32x2_add(sum_b, f32x2_pack(p0, p1));
-          else sum_a = f32x2_add(sum_a, f32x2_pack(p0, p1));
-          s[off + x] = __uint_as_float(pack_bf16x2(p0, p1));
-        }
-        float t0, t1;
-        f32x2_unpack(f32x2_add(sum_a, sum_b), t0, t1);
-        return t0 + t1;
-      };
-      auto fetch1 = [&]() {                          // (re)load this half of S_t(j+1) and mask it
-        tmem_ld_x32(tm_s + 64 * ((j + 1) & 1), reinterpret_cast<uint32_t*>(s) + 32);
-        tmem_wait_ld();
-        if (partial1) mask32(32, c0 + BN, vw1, mw1);
-      };
-      float sum_j;
-      if (j == 0) {
-        named_bar_sync(pair_bar, 64);
-        m_used = fmaxf(m_half, xch[xp][t][ch ^ 1][r]);
-        sum_j = exps(0);
-        if (AKI_ONE_EXP_PHASE && two) sum_j += exps(32);
-      } else {
-        // Optimistic: exponentiate tile j against the running max of the EARLIER passes while the maxima are being
-        // exchanged; if the pass maximum exceeds the reference by more than the threshold (rare after the first
-        // tiles) O and l are rescaled and tile j is redone -- published P values never exceed 2^threshold.
-        sum_j = exps(0);
-        if (AKI_ONE_EXP_PHASE && two) sum_j += exps(32);
-        named_bar_sync(pair_bar, 64);
-        const float m_new = fmaxf(m_used, fmaxf(m_half, xch[xp][t][ch ^ 1][r]));
-        TR(slot, j, 3);
+        mx[0] = fmax3(mx[0], s[124], s[125]); mx[1] = fmax3(mx[1], s[126], s[127]);
+        const float m_new = fmaxf(m_used, fmaxf(fmax3(mx[0], mx[1], mx[2]), mx[3]));
+        // ---- lazy rescale: O and l stay expressed against m_used until the maximum has grown by more than 2^8
         const bool need = (m_new - m_used) * P.scale_log2 > RESCALE_THRESHOLD || (m_used == -INFINITY && m_new > -INFINITY);
         if (__any_sync(0xffffffffu, need)) {
-          const float alpha = (m_used == -INFINITY) ? 0.f : ex2_approx((m_used - m_new) * P.scale_log2);
-          m_used = m_new;
-          l *= alpha;
-          if (o_waited < j) { mbar_wait(BAR(O_FULL + t), (j - 1) & 1); o_waited = j; }   // PV(j-1) has landed
-          tc_fence_after();
-          rescale_o48(tm_o, alpha);
-          fetch0();
-          sum_j = exps(0);
-          if (AKI_ONE_EXP_PHASE && two) { fetch1(); sum_j += exps(32); }
+          if (j > 0) {
+            const float alpha = need ? ((m_used == -INFINITY) ? 0.f : ex2_approx((m_used - m_new) * P.scale_log2)) : 1.f;
+            mbar_wait(BAR(PV_DONE + t), (n_pvh - 1) & 1);    // every PV of this tile issued so far has landed
+            tc_fence_after();
+            rescale_o96(tm_o, alpha);
+            l *= alpha;
+          }
+          if (need) m_used = m_new;
         }
-      }
-      l += sum_j;
-      if (AKI_STAGGER_POINT == 1 && stagger && t == 0 && j == 0) asm volatile("bar.arrive 9, 512;" ::: "memory");   // release tile 1
-      // ---- both S buffers go back to the MMA warp: QK^T(j+2), QK^T(j+3) run during the rest of this pass
-      if (!AKI_PV_FIRST) {
-        tc_fence_before();
-        mbar_arrive(BAR(S_FREE + 2 * t + (j & 1)));
-        if (two) mbar_arrive(BAR(S_FREE + 2 * t + ((j + 1) & 1)));
-      }
-      TR(slot, j, 4);
-      // ---- publish P(j): its own TMEM columns, single-buffered -- PV(j-1) has consumed P(j-1)
-      if (o_waited < j) {
-        if (!o_known) mbar_wait(BAR(O_FULL + t), (j - 1) & 1);
-        o_waited = j;
-      }
-      TR(slot, j, 5);
-      tmem_st_x16(tm_p, reinterpret_cast<const uint32_t*>(s));
-      tmem_wait_st();
-      tc_fence_before();
-      mbar_arrive(BAR(P_FULL + t));
-      if (AKI_PV_FIRST) {            // PV(j) enters the tensor-pipe queue ahead of QK^T(j+2), QK^T(j+3)
-        mbar_arrive(BAR(S_FREE + 2 * t + (j & 1)));
-        if (two) mbar_arrive(BAR(S_FREE + 2 * t + ((j + 1) & 1)));
-      }
-      if (two) {
-        // ---- tile j+1 while PV(j) runs, then P(j+1) into the same columns
-        if (!AKI_ONE_EXP_PHASE) l += exps(32);
-        mbar_wait(BAR(O_FULL + t), j & 1);
-        o_waited = j + 1;
+        const float neg_m = (m_used == -INFINITY) ? 0.f : -m_used * P.scale_log2;
+        const uint64_t sc2 = f32x2_pack(P.scale_log2, P.scale_log2), nm2 = f32x2_pack(neg_m, neg_m);
+        // exp2((S - m_used) * scale*log2e) of 64 scores starting at `off`, packed IN PLACE into s[off .. off+32)
+        auto exps = [&](int off) {
+          uint64_t sum_a = f32x2_pack(0.f, 0.f), sum_b = sum_a;
+#pragma unroll
+          for (int x = 0; x < 32; ++x) {
+            float a0, a1;
+            f32x2_unpack(f32x2_fma(f32x2_pack(s[off + 2 * x], s[off + 2 * x + 1]), sc2, nm2), a0, a1);
+            const float p0 = ex2_approx(a0), p1 = ex2_approx(a1);
+            if (x & 1) sum_b = f32x2_add(sum_b, f32x2_pack(p0, p1));
+            else sum_a = f32x2_add(sum_a, f32x2_pack(p0, p1));
+            s[off + x] = __uint_as_float(pack_bf16x2(p0, p1));
+          }
+          float t0, t1;
+          f32x2_unpack(f32x2_add(sum_a, sum_b), t0, t1);
+          return t0 + t1;
+        };
+        // ---- keys 0-63 -> P -> PV(j, first half)
+        l += exps(0);
+        if (n_pvh > 0) mbar_wait(BAR(PV_DONE + t), (n_pvh - 1) & 1);   // the previous PV half has consumed P
         tc_fence_after();
-        tmem_st_x16(tm_p, reinterpret_cast<const uint32_t*>(s) + 32);
-      }
-      // probe S_FULL of the next pass while the P store drains
-      s_ready0 = (j + 2 < nk) && mbar_test(BAR(S_FULL + 2 * t + (j & 1)), ((j + 2) >> 1) & 1);
-      s_ready1 = (j + 3 < nk) && mbar_test(BAR(S_FULL + 2 * t + ((j + 1) & 1)), ((j + 3) >> 1) & 1);
-      if (two) {
+        tmem_st_x32(tm_p, reinterpret_cast<const uint32_t*>(s));
         tmem_wait_st();
         tc_fence_before();
         mbar_arrive(BAR(P_FULL + t));
-      }
-      TR(slot, j, 6);
-      if (AKI_STAGGER_POINT == 3 && stagger && t == 0 && j == 0) asm volatile("bar.arrive 9, 512;" ::: "memory");
-    }
-
-    // ---- epilogue: O / l -> bf16 -> global; LSE
-    if (qt < P.n_qt) {
-      float inv_l = 0.f;
-      if (nk > 0) {
-        // total row sum = sum of the two halves (the exchange buffer the last pass did not use)
-        const int xe = (((nk - 1) >> 1) + 1) & 1;
-        xch[xe][t][ch][r] = l;
-        named_bar_sync(pair_bar, 64);
-        l += xch[xe][t][ch ^ 1][r];
-        mbar_wait(BAR(O_FULL + t), (nk - 1) & 1);
+        ++n_pvh;
+        // ---- keys 64-127 while PV(first half) runs
+        l += exps(64);
+        mbar_wait(BAR(PV_DONE + t), (n_pvh - 1) & 1);
         tc_fence_after();
-        inv_l = (row_live && l > 0.f) ? 1.f / l : 0.f;  // batch-padding rows: zeros
+        tmem_st_x32(tm_p, reinterpret_cast<const uint32_t*>(s) + 64);
+        tmem_wait_st();
+        tc_fence_before();
+        mbar_arrive(BAR(P_FULL + t));
+        ++n_pvh;
       }
-      // tcgen05.ld is warp-collective (.sync.aligned): load unconditionally, predicate only the global stores
-      const bool store_row = (i < P.T);
-      __nv_bfloat16* orow = P.o.row(b, store_row ? i : 0, h) + 48 * ch;
-      uint32_t o[48];
-      if (nk > 0) {
-        tmem_ld_x32(tm_o, o);
-        tmem_ld_x16(tm_o + 32, o + 32);
-        tmem_wait_ld();
-      }
-#pragma unroll
-      for (int x = 0; x < 6; ++x) {
-        uint4 u;
-        uint32_t* w = reinterpret_cast<uint32_t*>(&u);
-#pragma unroll
-        for (int e = 0; e < 4; ++e)
-          w[e] = (inv_l > 0.f) ? pack_bf16x2(__uint_as_float(o[8 * x + 2 * e]) * inv_l,
-                                               __uint_as_float(o[8 * x + 2 * e + 1]) * inv_l)
-                               : 0u;
-        if (store_row) *reinterpret_cast<uint4*>(orow + 8 * x) = u;
-      }
-      if (P.lse && store_row && ch == 0)
-        P.lse[((size_t)b * P.H + h) * P.T + i] = (inv_l > 0.f) ? (m_used * P.scale + __logf(l)) : INFINITY;
+      // ---- hand the row statistics to the epilogue warps and move on to the next item
+      if (n_it > 0) mbar_wait(BAR(O_FREE + t), (n_it - 1) & 1);   // they have read the previous item's statistics
+      lm_s[t][r] = make_float2(row_live ? l : 0.f, m_used);
+      mbar_arrive(BAR(L_READY + t));
+      ++n_it;
     }
+  } else {
+    // ------------------------------------------------------------------ RoPE of the next item's Q, epilogue of this one
+    setmaxnreg_dec<REGS_EPI>();
+    const int g = warp & 3;
+    const int r = 32 * g + lane;
+    const uint32_t lane_base = (uint32_t)(g * 32) << 16;
+    auto rope_item = [&](uint32_t n, const int4& v0, const int4& v1, const int4& v2) {
+      const int buf = n & 1, b = v0.y;
+#pragma unroll 1
+      for (int t = 0; t < 2; ++t) {
+        mbar_wait(BAR(Q_FULL + 2 * buf + t), (n >> 1) & 1);
+        const int i = (t ? v1.y : v1.x) + r;
+        if ((t ? v2.y : v2.x) > 0 && i < P.T) {
+          const uint32_t qa = smem_base + SMEM_Q + (2 * buf + t) * TILE_BYTES;
+          const float* cr = P.rope_cos + (size_t)b * P.rope_stride_b + (size_t)i * 48;
+          const float* sr = P.rope_sin + (size_t)b * P.rope_stride_b + (size_t)i * 48;
+#pragma unroll 2
+          for (int c = 0; c < 6; ++c) {          // 16-byte chunk c pairs with chunk c+6 (d <-> d+48)
+            const uint32_t a_lo = qa + (c >> 2) * ATOM + sw64_offset(r, c & 3);
+            const uint32_t a_hi = qa + ((c + 6) >> 2) * ATOM + sw64_offset(r, (c + 6) & 3);
+            uint4 lo, hi;
+            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w) : "r"(a_lo));
+            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w) : "r"(a_hi));
+            float cs[8], sn[8];
+            *reinterpret_cast<float4*>(cs) = __ldg(reinterpret_cast<const float4*>(cr + c * 8));
+            *reinterpret_cast<float4*>(cs + 4) = __ldg(reinterpret_cast<const float4*>(cr + c * 8 + 4));
+            *reinterpret_cast<float4*>(sn) = __ldg(reinterpret_cast<const float4*>(sr + c * 8));
+            *reinterpret_cast<float4*>(sn + 4) = __ldg(reinterpret_cast<const float4*>(sr + c * 8 + 4));
+            const __nv_bfloat162* l2 = reinterpret_cast<const __nv_bfloat162*>(&lo);
+            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&hi);
+            uint32_t lo_w[4], hi_w[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 lf = __bfloat1622float2(l2[e]), hf2 = __bfloat1622float2(h2[e]);
+              lo_w[e] = pack_bf16x2(lf.x * cs[2 * e] - hf2.x * sn[2 * e], lf.y * cs[2 * e + 1] - hf2.y * sn[2 * e + 1]);
+              hi_w[e] = pack_bf16x2(hf2.x * cs[2 * e] + lf.x * sn[2 * e], hf2.y * cs[2 * e + 1] + lf.y * sn[2 * e + 1]);
+            }
+            asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a_lo), "r"(lo_w[0]), "r"(lo_w[1]), "r"(lo_w[2]), "r"(lo_w[3]) : "memory");
+            asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a_hi), "r"(hi_w[0]), "r"(hi_w[1]), "r"(hi_w[2]), "r"(hi_w[3]) : "memory");
+          }
+        }
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(BAR(Q_READY + buf));
+    };
+    uint32_t n_it = 0, n_od[2] = {0, 0};
+    int4 v0, v1, v2;
+    item_wait(0, v0, v1, v2);
+    if (ROPE && v0.x) rope_item(0, v0, v1, v2);
+    while (v0.x) {
+      int4 w0, w1, w2;
+      item_wait(n_it + 1, w0, w1, w2);
+      if (ROPE && w0.x) rope_item(n_it + 1, w0, w1, w2);
+      const int b = v0.y, h = v0.z, len = v0.w;
+#pragma unroll 1
+      for (int t = 0; t < 2; ++t) {
+        const int nk = t ? v2.y : v2.x, rows = t ? v1.w : v1.z;
+        const int i = (t ? v1.y : v1.x) + r;
+        mbar_wait(BAR(L_READY + t), n_it & 1);
+        const float2 lm = lm_s[t][r];
+        if (nk > 0) {
+          mbar_wait(BAR(O_DONE + t), n_od[t] & 1);
+          ++n_od[t];
+          tc_fence_after();
+        }
+        const float inv_l = (nk > 0 && i < len && lm.x > 0.f) ? 1.f / lm.x : 0.f;   // batch-padding rows: zeros
+        const bool store_row = (r < rows) && (i < P.T);
+        __nv_bfloat16* orow = P.o.row(b, store_row ? i : 0, h);
+        // tcgen05.ld is warp-collective (.sync.aligned): load unconditionally, predicate only the global stores
+#pragma unroll 1
+        for (int c = 0; c < 3; ++c) {
+          uint32_t o[32];
+          if (nk > 0) {
+            tmem_ld_x32(tmem + TM_O + 96 * t + lane_base + 32 * c, o);
+            tmem_wait_ld();
+          }
+#pragma unroll
+          for (int x = 0; x < 4; ++x) {
+            uint4 u;
+            uint32_t* w = reinterpret_cast<uint32_t*>(&u);
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              w[e] = (inv_l > 0.f) ? pack_bf16x2(__uint_as_float(o[8 * x + 2 * e]) * inv_l,
+                                                   __uint_as_float(o[8 * x + 2 * e + 1]) * inv_l)
+                                   : 0u;
+            if (store_row) *reinterpret_cast<uint4*>(orow + 32 * c + 8 * x) = u;
+          }
+        }
+        if (P.lse && store_row)
+          P.lse[((size_t)b * P.H + h) * P.T + i] = (inv_l > 0.f) ? (lm.y * P.scale + __logf(lm.x)) : INFINITY;
+        tc_fence_before();
+        mbar_arrive(BAR(O_FREE + t));
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(BAR(ITEM_EMPTY + n_it % SLOTS));
+      v0 = w0; v1 = w1; v2 = w2;
+      ++n_it;
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(BAR(ITEM_EMPTY + n_it % SLOTS));   // the terminator's slot
   }
   tc_fence_before();
   __syncthreads();
@@ -672,6 +689,29 @@ int make_row_stats_map(CUtensorMap* m, void* base, int B, int H, int t_pad) {
   return AKI_OK;
 }
 
+// Per-device one-time setup (kernel attribute, SM count): the library may drive several GPUs from one process.
+struct FwdDeviceState {
+  std::once_flag once;
+  int sm_count = 0;
+  cudaError_t err = cudaSuccess;
+};
+static FwdDeviceState g_fwd_dev[64];
+
+static int fwd_device_setup(int* sm_count) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) { set_last_cuda_error("cudaGetDevice failed"); return AKI_ERR_CUDA; }
+  FwdDeviceState& s = g_fwd_dev[dev];
+  std::call_once(s.once, [&]() {
+    s.err = cudaFuncSetAttribute(attn_fwd_sm100_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd::SMEM_ALLOC);
+    if (s.err == cudaSuccess)
+      s.err = cudaFuncSetAttribute(attn_fwd_sm100_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd::SMEM_ALLOC);
+    if (s.err == cudaSuccess) s.err = cudaDeviceGetAttribute(&s.sm_count, cudaDevAttrMultiProcessorCount, dev);
+  });
+  if (s.err != cudaSuccess) { set_last_cuda_error(cudaGetErrorString(s.err)); return AKI_ERR_CUDA; }
+  *sm_count = s.sm_count;
+  return AKI_OK;
+}
+
 }  // namespace aki
 
 using namespace aki;
@@ -680,65 +720,40 @@ extern "C" int aki_mma_attn_fwd(const AkiMmaAttnParams* p, aki_stream_t stream) 
   AKI_REQUIRE(p, AKI_ERR_NULL);
   int rc = check_attn_params(*p);
   if (rc) return rc;
+  AKI_REQUIRE(!p->fwd_plan || p->plan_pairs >= ((p->T + fwd::BM - 1) / fwd::BM + 1) / 2, AKI_ERR_BAD_SHAPE);
   CUtensorMap mq, mk, mv;
   if ((rc = make_tile_map(&mq, p->q, p->B, p->H, p->T, fwd::BM))) return rc;
-  if ((rc = make_tile_map(&mk, p->k, p->B, p->H, p->T, 2 * fwd::BN))) return rc;   // K: 128-key tiles (one per pass)
+  if ((rc = make_tile_map(&mk, p->k, p->B, p->H, p->T, fwd::BN))) return rc;
   if ((rc = make_tile_map(&mv, p->v, p->B, p->H, p->T, fwd::BN))) return rc;
   FwdKernelParams kp;
   kp.q = view_of(p->q); kp.o = view_of(p->o);
   kp.lse = p->lse; kp.rope_cos = p->rope_cos; kp.rope_sin = p->rope_sin; kp.rope_stride_b = p->rope_stride_b;
   kp.mm = mask_meta_from(*p);
+  kp.plan = reinterpret_cast<const int4*>(p->fwd_plan);
+  kp.plan_pairs = p->plan_pairs;
   kp.B = p->B; kp.H = p->H; kp.T = p->T;
-  kp.n_qt = (p->T + fwd::BM - 1) / fwd::BM;
-  kp.n_qp = (kp.n_qt + 1) / 2;
+  const int n_qt = (p->T + fwd::BM - 1) / fwd::BM;
+  kp.ranks = p->fwd_plan ? p->plan_pairs : (n_qt + 1) / 2;
+  const long long slices = (long long)p->B * p->H;
+  kp.group = (int)(slices < fwd::HEADS_PER_GROUP ? slices : fwd::HEADS_PER_GROUP);
+  const long long n_groups = (slices + kp.group - 1) / kp.group;
+  const long long n_items = n_groups * kp.ranks * kp.group;
+  AKI_REQUIRE(n_items > 0 && n_items < (1ll << 31), AKI_ERR_BAD_SHAPE);
+  kp.n_items = (int)n_items;
   kp.scale = p->scale;
   kp.scale_log2 = p->scale * 1.4426950408889634f;
-  kp.trace = nullptr; kp.trace_cta = -1;
-#ifdef AKI_FWD_TRACE
-  // Debug build only (make TRACE=1; tools/fwd_trace.py): dumps clock64 stamps of one CTA and SYNCHRONISES.
-  const char* trace_env = getenv("AKI_MMA_FWD_TRACE");
-  const size_t trace_bytes = 6 * 64 * 8 * sizeof(unsigned long long);
-  if (trace_env) {
-    kp.trace_cta = atoi(trace_env);
-    cudaMalloc(&kp.trace, trace_bytes);
-    cudaMemset(kp.trace, 0, trace_bytes);
-  }
-#endif
-  const long long grid = (long long)kp.n_qp * p->H * p->B;
-  AKI_REQUIRE(grid > 0 && grid < (1ll << 31), AKI_ERR_BAD_SHAPE);
+  int sm_count = 0;
+  if ((rc = fwd_device_setup(&sm_count))) return rc;
+  // AKI_MMA_FWD_SCHED=static: persistent CTAs walk the items with a fixed stride instead of the hardware queue (A/B only)
+  static const bool use_static = []() { const char* e = getenv("AKI_MMA_FWD_SCHED"); return e && e[0] == 's'; }();
+  kp.use_clc = use_static ? 0 : 1;
+  const unsigned grid = kp.use_clc ? (unsigned)n_items : (unsigned)(n_items < sm_count ? n_items : sm_count);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  static bool attr_done = false;
-  if (!attr_done) {
-    if (cudaFuncSetAttribute(attn_fwd_sm100_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd::SMEM_ALLOC) != cudaSuccess ||
-        cudaFuncSetAttribute(attn_fwd_sm100_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd::SMEM_ALLOC) != cudaSuccess) {
-      set_last_cuda_error(cudaGetErrorString(cudaGetLastError()));
-      return AKI_ERR_CUDA;
-    }
-    attr_done = true;
-  }
   timing_hook_begin(st);
   if (p->rope_cos)
-    attn_fwd_sm100_kernel<true><<<(unsigned)grid, fwd::THREADS, fwd::SMEM_ALLOC, st>>>(mq, mk, mv, kp);
+    attn_fwd_sm100_kernel<true><<<grid, fwd::THREADS, fwd::SMEM_ALLOC, st>>>(mq, mk, mv, kp);
   else
-    attn_fwd_sm100_kernel<false><<<(unsigned)grid, fwd::THREADS, fwd::SMEM_ALLOC, st>>>(mq, mk, mv, kp);
+    attn_fwd_sm100_kernel<false><<<grid, fwd::THREADS, fwd::SMEM_ALLOC, st>>>(mq, mk, mv, kp);
   timing_hook_end(st);
-#ifdef AKI_FWD_TRACE
-  if (trace_env) {
-    cudaDeviceSynchronize();
-    static unsigned long long host[6 * 64 * 8];
-    cudaMemcpy(host, kp.trace, trace_bytes, cudaMemcpyDeviceToHost);
-    cudaFree(kp.trace);
-    unsigned long long t0 = ~0ull;
-    for (size_t i = 0; i < 6 * 64 * 8; ++i) if (host[i] && host[i] < t0) t0 = host[i];
-    const char* names[6] = {"sm_t0c0", "sm_t0c1", "sm_t1c0", "sm_t1c1", "mma_t0", "mma_t1"};
-    for (int slot = 0; slot < 6; ++slot)
-      for (int j = 0; j < 64; ++j) {
-        if (!host[(slot * 64 + j) * 8]) continue;
-        fprintf(stderr, "TRACE %s j=%d:", names[slot], j);
-        for (int k = 0; k < 7; ++k) fprintf(stderr, " %llu", host[(slot * 64 + j) * 8 + k] ? host[(slot * 64 + j) * 8 + k] - t0 : 0ull);
-        fprintf(stderr, "\n");
-      }
-  }
-#endif
   return check_launch();
 }

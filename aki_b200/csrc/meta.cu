@@ -175,6 +175,139 @@ tile_bounds_kernel(const int32_t* __restrict__ seq_len, const int32_t* __restric
     for (int w = tid; w < n_words; w += 128) kv_tile_q_mask[((size_t)b * n_tiles + tile) * n_words + w] = s_mask[w];
 }
 
+// Forward work plan (include/aki_mma.h, aki_mma_fwd_plan): one block per sample.  Query rows are cut into tiles of
+// <= 128 rows that start at every image span (rows whose mutual interval [row_lo,row_hi) is non-empty and differs
+// from the previous row's), each tile gets the number of 128-key tiles its rows can see, tiles are ranked by that
+// count and paired.  O(T) integer work per sample; the result is shared by all heads and all layers.
+constexpr int PLAN_THREADS = 256;
+constexpr int PLAN_MAX_TILES = 1280;   // T <= 65536: 512 aligned tiles + span cuts
+constexpr int PLAN_MAX_CUTS = 256;
+
+__global__ void __launch_bounds__(PLAN_THREADS)
+fwd_plan_kernel(const int32_t* __restrict__ seq_len, const int32_t* __restrict__ row_lo,
+                const int32_t* __restrict__ row_hi, const uint32_t* __restrict__ vbits, int T, int meta_pitch,
+                int bits_pitch, int max_pairs, int flags, int4* __restrict__ plan) {
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int len = seq_len ? min(seq_len[b], T) : T;
+  const int32_t* lo = row_lo ? row_lo + (size_t)b * meta_pitch : nullptr;
+  const int32_t* hi = row_hi ? row_hi + (size_t)b * meta_pitch : nullptr;
+  __shared__ int s_first_bad, s_ncut, s_ntiles;
+  __shared__ int s_cut[PLAN_MAX_CUTS + 2];
+  __shared__ int s_cut_sorted[PLAN_MAX_CUTS + 2];
+  __shared__ int s_seg_tile0[PLAN_MAX_CUTS + 2];
+  __shared__ int s_start[PLAN_MAX_TILES], s_rows[PLAN_MAX_TILES], s_nkv[PLAN_MAX_TILES];
+  __shared__ uint16_t s_order[PLAN_MAX_TILES];
+  const int n_kt = (T + AKI_MMA_TILE - 1) / AKI_MMA_TILE;
+  if (tid == 0) { s_first_bad = n_kt; s_ncut = 0; }
+  __syncthreads();
+  // first 128-key tile that is not entirely inside the sequence and causally valid
+  for (int kt = tid; kt < n_kt; kt += PLAN_THREADS) {
+    bool bad = (kt * AKI_MMA_TILE + AKI_MMA_TILE > len);
+    if (!bad && vbits) {
+      const uint32_t* w = vbits + (size_t)b * bits_pitch + 4 * kt;
+      bad = (w[0] & w[1] & w[2] & w[3]) != 0xffffffffu;
+    }
+    if (bad) atomicMin(&s_first_bad, kt);
+  }
+  // span starts (cuts), as many as the pair budget allows
+  const int n_aligned = n_kt;
+  const int budget = min(max(2 * max_pairs - n_aligned - 1, 0), PLAN_MAX_CUTS);
+  if ((flags & 1) && lo && budget > 0) {
+    for (int i = 1 + tid; i < len; i += PLAN_THREADS) {
+      const int a = lo[i], e = hi[i];
+      if (e > a) {
+        const int a0 = lo[i - 1], e0 = hi[i - 1];
+        if (!(e0 > a0) || a0 != a) {
+          const int k = atomicAdd(&s_ncut, 1);
+          if (k < PLAN_MAX_CUTS) s_cut[k] = i;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  const int ncut_all = min(s_ncut, PLAN_MAX_CUTS);
+  // rank sort of the cuts (ascending), keep the first `budget`
+  for (int k = tid; k < ncut_all; k += PLAN_THREADS) {
+    const int v = s_cut[k];
+    int rank = 0;
+    for (int m = 0; m < ncut_all; ++m) rank += (s_cut[m] < v) ? 1 : 0;
+    s_cut_sorted[1 + rank] = v;
+  }
+  __syncthreads();
+  const int ncut = min(ncut_all, budget);
+  if (tid == 0) {
+    s_cut_sorted[0] = 0;
+    s_cut_sorted[1 + ncut] = T;
+    int n = 0;
+    for (int k = 0; k <= ncut; ++k) {
+      s_seg_tile0[k] = n;
+      n += (s_cut_sorted[k + 1] - s_cut_sorted[k] + AKI_MMA_TILE - 1) / AKI_MMA_TILE;
+    }
+    s_seg_tile0[ncut + 1] = n;
+    s_ntiles = n;
+  }
+  __syncthreads();
+  const int n_tiles = s_ntiles;   // <= n_aligned + ncut <= 2 * max_pairs - 1
+  // tiles of each segment
+  for (int k = warp; k <= ncut; k += PLAN_THREADS / 32) {
+    const int t0 = s_seg_tile0[k], cnt = s_seg_tile0[k + 1] - t0, r0 = s_cut_sorted[k], r1 = s_cut_sorted[k + 1];
+    for (int x = lane; x < cnt; x += 32) {
+      s_start[t0 + x] = r0 + x * AKI_MMA_TILE;
+      s_rows[t0 + x] = min(AKI_MMA_TILE, r1 - (r0 + x * AKI_MMA_TILE));
+    }
+  }
+  __syncthreads();
+  // key tiles each query tile must visit: its rows look right up to max(i + 1, row_hi[i]) (clipped to the sequence)
+  for (int x = warp; x < n_tiles; x += PLAN_THREADS / 32) {
+    const int r0 = s_start[x], nr = s_rows[x];
+    int need = 0;
+    for (int r = lane; r < nr; r += 32) {
+      const int i = r0 + r;
+      if (i < len) {
+        need = max(need, i + 1);
+        if (lo) {
+          const int a = lo[i], e = hi[i];
+          if (e > a) need = max(need, min(e, len));
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) need = max(need, __shfl_xor_sync(0xffffffffu, need, o));
+    if (lane == 0) s_nkv[x] = (need + AKI_MMA_TILE - 1) / AKI_MMA_TILE;
+  }
+  __syncthreads();
+  // rank by key-tile count (descending; ties by start) -- or plain descending start (the causal order) without bit 1
+  for (int x = tid; x < n_tiles; x += PLAN_THREADS) {
+    int rank = 0;
+    if (flags & 2) {
+      const int nk = s_nkv[x], st = s_start[x];
+      for (int y = 0; y < n_tiles; ++y) {
+        const int nky = s_nkv[y];
+        rank += (nky > nk || (nky == nk && s_start[y] < st)) ? 1 : 0;
+      }
+    } else {
+      rank = n_tiles - 1 - x;
+    }
+    s_order[rank] = (uint16_t)x;
+  }
+  __syncthreads();
+  const int n_pairs = (n_tiles + 1) / 2;
+  int4* out = plan + (size_t)b * (1 + max_pairs);
+  if (tid == 0) out[0] = make_int4(n_pairs, s_first_bad, n_tiles, 0);
+  for (int p = tid; p < max_pairs; p += PLAN_THREADS) {
+    int4 e = make_int4(0, 0, 0, 0);
+    if (p < n_pairs) {
+      const int x0 = s_order[2 * p];
+      e.x = s_start[x0]; e.z = s_nkv[x0] | (s_rows[x0] << 16);
+      if (2 * p + 1 < n_tiles) {
+        const int x1 = s_order[2 * p + 1];
+        e.y = s_start[x1]; e.w = s_nkv[x1] | (s_rows[x1] << 16);
+      }
+    }
+    out[1 + p] = e;
+  }
+}
+
 __global__ void __launch_bounds__(256)
 expand_mask_kernel(const int32_t* __restrict__ seq_len, const int32_t* __restrict__ row_lo,
                    const int32_t* __restrict__ row_hi, const uint32_t* __restrict__ vbits,
@@ -245,6 +378,23 @@ extern "C" int aki_mma_tile_bounds(const int32_t* seq_len, const int32_t* row_lo
   AKI_REQUIRE(n_words <= 64, AKI_ERR_UNSUPPORTED);
   tile_bounds_kernel<<<dim3(n_tiles, B), 128, 0, static_cast<cudaStream_t>(stream)>>>(
       seq_len, row_lo, row_hi, T, t_cap, n_tiles, n_words, q_tile_kv_end, kv_tile_q_mask);
+  return check_launch();
+}
+
+extern "C" int aki_mma_fwd_plan(const int32_t* seq_len, const int32_t* row_lo, const int32_t* row_hi,
+                                const uint32_t* kv_valid_bits, int B, int T, int meta_pitch, int bits_pitch,
+                                int max_pairs, int flags, int32_t* plan, aki_stream_t stream) {
+  AKI_REQUIRE(plan, AKI_ERR_NULL);
+  AKI_REQUIRE((row_lo == nullptr) == (row_hi == nullptr), AKI_ERR_NULL);
+  AKI_REQUIRE(B > 0 && T > 0, AKI_ERR_BAD_SHAPE);
+  const int n_aligned = (T + AKI_MMA_TILE - 1) / AKI_MMA_TILE;
+  AKI_REQUIRE(max_pairs >= (n_aligned + 1) / 2, AKI_ERR_BAD_SHAPE);
+  AKI_REQUIRE(2 * max_pairs <= PLAN_MAX_TILES, AKI_ERR_UNSUPPORTED);
+  AKI_REQUIRE(!row_lo || meta_pitch >= T, AKI_ERR_BAD_SHAPE);
+  AKI_REQUIRE(!kv_valid_bits || bits_pitch >= (T + 31) / 32, AKI_ERR_BAD_SHAPE);
+  AKI_REQUIRE(aligned16(plan), AKI_ERR_MISALIGNED);
+  fwd_plan_kernel<<<B, PLAN_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
+      seq_len, row_lo, row_hi, kv_valid_bits, T, meta_pitch, bits_pitch, max_pairs, flags, reinterpret_cast<int4*>(plan));
   return check_launch();
 }
 

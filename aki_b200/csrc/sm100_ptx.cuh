@@ -56,15 +56,22 @@ __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Spin on try_wait (a hardware-suspended wait with a time limit).  A protocol bug would otherwise hang the GPU
-// until the watchdog of the box kills the job; trap after ~seconds instead so it surfaces as a CUDA error.
+// Spin on try_wait (a hardware-suspended wait with a time limit).  Release builds never trap: a kernel that is merely
+// slowed down (profiler replay, compute-sanitizer, MPS time slicing, a debugger) keeps waiting and backs off with
+// nanosleep once the wait is clearly long.  Bring-up builds (make TRAP=1 -> -DAKI_MBAR_TRAP) turn a protocol bug into
+// a CUDA error after AKI_MBAR_SPIN_LIMIT probes instead of hanging the box.
 #ifndef AKI_MBAR_SPIN_LIMIT
-#define AKI_MBAR_SPIN_LIMIT (1u << 24)
+#define AKI_MBAR_SPIN_LIMIT (1u << 22)
 #endif
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > AKI_MBAR_SPIN_LIMIT) __trap();
+    ++spins;
+#ifdef AKI_MBAR_TRAP
+    if (spins > AKI_MBAR_SPIN_LIMIT) __trap();
+#else
+    if (spins > 64u) __nanosleep(spins > 4096u ? 256u : 32u);
+#endif
   }
 }
 

@@ -11,6 +11,7 @@ Ops (torch.library, namespace ``aki_mma``):
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass
 from typing import Optional, Tuple
 
@@ -54,6 +55,8 @@ class MMASegments:
     q_tile_kv_end: torch.Tensor    # (B,ceil(T/128)) int32
     kv_tile_q_mask: torch.Tensor   # (B,ceil(T/128),ceil(ceil(T/128)/32)) int32 (bit pattern of uint32)
     T: int
+    fwd_plan: Optional[torch.Tensor] = None   # (B, 1 + pairs, 4) int32: forward work plan (aki_mma_fwd_plan)
+    max_spans: int = 8                        # image spans per sample that may start a query tile of their own
 
     @property
     def B(self) -> int:
@@ -80,7 +83,7 @@ class MMASegments:
             self.seq_len, self.q_end, self.seg[:, :T].contiguous(), self.row_lo[:, :T].contiguous(),
             self.row_hi[:, :T].contiguous(), self.src[:, :T].contiguous(),
             self.kv_valid_bits[:, :(T + 31) // 32].contiguous(), self.kv_mutual_bits[:, :(T + 31) // 32].contiguous(),
-            self.q_tile_kv_end, self.kv_tile_q_mask, T))
+            self.q_tile_kv_end, self.kv_tile_q_mask, T, None, self.max_spans))
 
 
 def rebuild_tile_bounds(s: MMASegments) -> MMASegments:
@@ -90,12 +93,30 @@ def rebuild_tile_bounds(s: MMASegments) -> MMASegments:
     s.kv_tile_q_mask = torch.empty(s.B, nt, (nt + 31) // 32, dtype=torch.int32, device=dev)
     check(lib.aki_mma_tile_bounds(_ptr(s.seq_len), _ptr(s.row_lo), _ptr(s.row_hi), s.B, s.T, s.T,
                                   _ptr(s.q_tile_kv_end), _ptr(s.kv_tile_q_mask), _stream()), "aki_mma_tile_bounds")
+    s.fwd_plan = build_fwd_plan(s.seq_len, s.row_lo, s.row_hi, s.kv_valid_bits, s.T, s.max_spans)
     return s
+
+
+PLAN_FLAGS = int(os.environ.get("AKI_MMA_PLAN_FLAGS", "3"))   # tools only: bit 0 cut at span starts, bit 1 rank + pair
+
+
+def build_fwd_plan(seq_len, row_lo, row_hi, vbits, T: int, max_spans: int = 8, flags: Optional[int] = None) -> torch.Tensor:
+    """Forward work plan (include/aki_mma.h, aki_mma_fwd_plan): (B, 1 + pairs, 4) int32."""
+    if not hasattr(lib, "aki_mma_fwd_plan"):      # AKI_MMA_LIB_COMPAT (tools): an ABI-1 build has no plan
+        return None
+    B = seq_len.shape[0]
+    nt = (T + TILE - 1) // TILE
+    pairs = (nt + max_spans + 2) // 2
+    plan = torch.empty(B, 1 + pairs, 4, dtype=torch.int32, device=seq_len.device)
+    check(lib.aki_mma_fwd_plan(_ptr(seq_len), _ptr(row_lo), _ptr(row_hi), _ptr(vbits), B, T,
+                               row_lo.shape[1] if row_lo is not None else 0, vbits.shape[1] if vbits is not None else 0,
+                               pairs, PLAN_FLAGS if flags is None else flags, _ptr(plan), _stream()), "aki_mma_fwd_plan")
+    return plan
 
 
 def build_segments(lang_x: torch.Tensor, attention_mask: torch.Tensor, num_tokens_per_vis: int, media_token_id: int,
                    assistant_token_id: int = 32001, t_cap: Optional[int] = None, text_only: bool = False,
-                   exact_shape: bool = True) -> MMASegments:
+                   exact_shape: bool = True, max_spans: int = 8) -> MMASegments:
     """Device replacement of the mask half of _prepare_inputs_for_forward (vlm.py:486-577).
 
     t_cap: row pitch / upper bound of the spliced length; default L + (#<image> in the widest row)*(N-1) needs one
@@ -125,7 +146,7 @@ def build_segments(lang_x: torch.Tensor, attention_mask: torch.Tensor, num_token
     check(lib.aki_mma_segments(_ptr(lang_x), _ptr(attention_mask), B, L, N, media_token_id, assistant_token_id, T,
                                int(text_only), _ptr(seq_len), _ptr(q_end), _ptr(seg), _ptr(row_lo), _ptr(row_hi),
                                _ptr(src), _ptr(vbits), _ptr(mbits), _ptr(status), _stream()), "aki_mma_segments")
-    s = MMASegments(seq_len, q_end, seg, row_lo, row_hi, src, vbits, mbits, None, None, T)
+    s = MMASegments(seq_len, q_end, seg, row_lo, row_hi, src, vbits, mbits, None, None, T, None, int(max_spans))
     if exact_shape:
         t_max = int(seq_len.max().item())
         if t_max > T:
@@ -253,7 +274,11 @@ def _fill_params(p: AttnParams, q, k, v, o, lse, cos, sin, meta, scale):
         p.rope_cos, p.rope_sin = cos.data_ptr(), sin.data_ptr()
         p.rope_stride_b = 0 if cos.shape[0] == 1 else cos.stride(0)
     if meta is not None:
-        seq_len, row_lo, row_hi, vbits, mbits, qkv_end, kvq_start = meta
+        seq_len, row_lo, row_hi, vbits, mbits, qkv_end, kvq_start, *rest = meta
+        plan = rest[0] if rest else None
+        if plan is not None:
+            assert plan.dtype == torch.int32 and plan.is_contiguous() and plan.shape[0] == B and plan.shape[2] == 4
+            p.fwd_plan, p.plan_pairs = plan.data_ptr(), plan.shape[1] - 1
         p.seq_len, p.row_lo, p.row_hi = _ptr(seq_len), _ptr(row_lo), _ptr(row_hi)
         p.kv_valid_bits, p.kv_mutual_bits = _ptr(vbits), _ptr(mbits)
         p.q_tile_kv_end, p.kv_tile_q_mask = _ptr(qkv_end), _ptr(kvq_start)
@@ -269,7 +294,7 @@ def meta_tuple(segs: Optional[MMASegments]):
     if segs is None:
         return None
     return (segs.seq_len, segs.row_lo, segs.row_hi, segs.kv_valid_bits, segs.kv_mutual_bits, segs.q_tile_kv_end,
-            segs.kv_tile_q_mask)
+            segs.kv_tile_q_mask, segs.fwd_plan)
 
 
 def attn_fwd_raw(q, k, v, cos, sin, meta, scale, need_lse=True, simt=False):
@@ -307,15 +332,15 @@ _OT = Optional[torch.Tensor]
 @torch.library.custom_op("aki_mma::attn", mutates_args=())
 def attn_op(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, scale: float, seq_len: _OT = None, row_lo: _OT = None,
             row_hi: _OT = None, vbits: _OT = None, mbits: _OT = None, q_tile_kv_end: _OT = None,
-            kv_tile_q_mask: _OT = None) -> Tuple[torch.Tensor, torch.Tensor]:
+            kv_tile_q_mask: _OT = None, fwd_plan: _OT = None) -> Tuple[torch.Tensor, torch.Tensor]:
     """q,k,v (B,T,H,D) logical, already rotated.  Returns o (B,T,H,D), lse (B,H,T)."""
-    meta = None if seq_len is None else (seq_len, row_lo, row_hi, vbits, mbits, q_tile_kv_end, kv_tile_q_mask)
+    meta = None if seq_len is None else (seq_len, row_lo, row_hi, vbits, mbits, q_tile_kv_end, kv_tile_q_mask, fwd_plan)
     return attn_fwd_raw(q, k, v, None, None, meta, scale)
 
 
 @attn_op.register_fake
 def _(q, k, v, scale, seq_len=None, row_lo=None, row_hi=None, vbits=None, mbits=None, q_tile_kv_end=None,
-      kv_tile_q_mask=None):
+      kv_tile_q_mask=None, fwd_plan=None):
     B, T, H, D = q.shape
     return q.new_empty(B, T, H, D), q.new_empty(B, H, T, dtype=torch.float32)
 
@@ -334,7 +359,7 @@ def _attn_backward(ctx, d_o, d_lse):
     B, T, H, D = q.shape
     dqkv = torch.empty(3, B, T, H, D, dtype=torch.bfloat16, device=q.device)
     attn_bwd_raw(d_o, q, k, v, o, lse, None, None, meta, ctx.scale, dqkv[0], dqkv[1], dqkv[2])
-    return (dqkv[0], dqkv[1], dqkv[2], None) + (None,) * 7
+    return (dqkv[0], dqkv[1], dqkv[2], None) + (None,) * 8
 
 
 attn_op.register_autograd(_attn_backward, setup_context=_attn_setup)
@@ -343,7 +368,7 @@ attn_op.register_autograd(_attn_backward, setup_context=_attn_setup)
 @torch.library.custom_op("aki_mma::attn_packed", mutates_args=())
 def attn_packed_op(qkv: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor, num_heads: int, scale: float,
                    seq_len: _OT = None, row_lo: _OT = None, row_hi: _OT = None, vbits: _OT = None, mbits: _OT = None,
-                   q_tile_kv_end: _OT = None, kv_tile_q_mask: _OT = None
+                   q_tile_kv_end: _OT = None, kv_tile_q_mask: _OT = None, fwd_plan: _OT = None
                    ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
     """qkv (B,T,3*H*D) bf16 straight from qkv_proj; cos/sin (B|1,T,D/2) fp32.
     Returns o (B,T,H*D), lse (B,H,T), k_rot (B,H,T,D) (post-RoPE keys, kept for backward)."""
@@ -353,14 +378,14 @@ def attn_packed_op(qkv: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor, num_
     rope_kv_write(qkv, cos, sin, k_rot, None, 0, H)
     q4 = qkv[..., : H * D].unflatten(-1, (H, D))
     v4 = qkv[..., 2 * H * D:].unflatten(-1, (H, D))
-    meta = None if seq_len is None else (seq_len, row_lo, row_hi, vbits, mbits, q_tile_kv_end, kv_tile_q_mask)
+    meta = None if seq_len is None else (seq_len, row_lo, row_hi, vbits, mbits, q_tile_kv_end, kv_tile_q_mask, fwd_plan)
     o, lse = attn_fwd_raw(q4, k_rot.transpose(1, 2), v4, cos, sin, meta, scale)
     return o.view(B, T, H * D), lse, k_rot
 
 
 @attn_packed_op.register_fake
 def _(qkv, cos, sin, num_heads, scale, seq_len=None, row_lo=None, row_hi=None, vbits=None, mbits=None,
-      q_tile_kv_end=None, kv_tile_q_mask=None):
+      q_tile_kv_end=None, kv_tile_q_mask=None, fwd_plan=None):
     B, T, _ = qkv.shape
     return (qkv.new_empty(B, T, num_heads * HEAD_DIM), qkv.new_empty(B, num_heads, T, dtype=torch.float32),
             qkv.new_empty(B, num_heads, T, HEAD_DIM))
@@ -384,7 +409,7 @@ def _packed_backward(ctx, d_o, d_lse, d_krot):
     views = [d_qkv[..., i * H * D:(i + 1) * H * D].unflatten(-1, (H, D)) for i in range(3)]
     attn_bwd_raw(d_o.reshape(B, T, H, D), q4, k_rot.transpose(1, 2), v4, o.view(B, T, H, D), lse, cos, sin, meta,
                  ctx.scale, views[0], views[1], views[2])
-    return (d_qkv, None, None, None, None) + (None,) * 7
+    return (d_qkv, None, None, None, None) + (None,) * 8
 
 
 attn_packed_op.register_autograd(_packed_backward, setup_context=_packed_setup)

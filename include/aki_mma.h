@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define AKI_MMA_ABI_VERSION 1
+#define AKI_MMA_ABI_VERSION 2
 #define AKI_MMA_HEAD_DIM 96
 #define AKI_MMA_TILE 128 /* query / key tile edge used by the attention kernels and by tile_bounds */
 
@@ -82,6 +82,21 @@ int aki_mma_segments(const int64_t* lang_x, const int64_t* attention_mask, int B
  *                                tiles before the diagonal plus everything from the diagonal on) */
 int aki_mma_tile_bounds(const int32_t* seq_len, const int32_t* row_lo, const int32_t* row_hi, int B, int T,
                         int t_cap, int32_t* q_tile_kv_end, uint32_t* kv_tile_q_mask, aki_stream_t stream);
+
+/* Forward work plan (ABI 2): the query rows of every sample cut into tiles of <= 128 rows that START at each image span
+ * (so that a span of <= 128 vision tokens is ONE query tile instead of straddling two aligned ones -- with the
+ * reference's 128/144-token spans an aligned tiling makes two tiles per span walk all keys up to <|assistant|>), each
+ * with the number of 128-key tiles it must visit; tiles are ranked by that count and paired (two query tiles share
+ * one stream of K/V tiles in the forward kernel), heaviest pair first -- the order the persistent forward CTAs consume.
+ *   plan (B, 1 + max_pairs, 4) int32: row 0 = {n_pairs, first key tile that holds a padded / invalid key, n_tiles, 0};
+ *   row 1+p = {start0, start1, n_kv0 | rows0 << 16, n_kv1 | rows1 << 16}.
+ *   max_pairs >= ceil(ceil(T/128) / 2); every pair above that minimum lets two more spans start a tile of their own
+ *   (spans beyond the budget keep the aligned cut: same results, more masked work).
+ *   flags: bit 0 = cut at span starts, bit 1 = rank and pair by key-tile count (0: index order).  Default 3.
+ * No reference counterpart: the reference materialises the (B,1,T,T) mask instead (vlm.py:410-443). */
+int aki_mma_fwd_plan(const int32_t* seq_len, const int32_t* row_lo, const int32_t* row_hi,
+                     const uint32_t* kv_valid_bits, int B, int T, int meta_pitch, int bits_pitch, int max_pairs,
+                     int flags, int32_t* plan, aki_stream_t stream);
 
 /* Debug / parity helper: expand the compact description to the reference's (B,1,T,T) int64 0/1 tensor
  * (what _prepare_inputs_for_forward returns under "attention_mask", vlm.py:589-603). */
@@ -157,6 +172,12 @@ typedef struct AkiMmaAttnParams {
   const int32_t* q_tile_kv_end;    /* (B, ceil(T/128)) */
   const uint32_t* kv_tile_q_mask;  /* (B, ceil(T/128), ceil(ceil(T/128)/32)); backward only */
   int32_t meta_pitch, bits_pitch;
+  /* ABI 2: forward work plan from aki_mma_fwd_plan ((B, 1 + plan_pairs) x 4 int32), or NULL: aligned 128-row query
+   * tiles in index order (and, when seq_len / kv_valid_bits are given without a plan, every key tile is evaluated
+   * against the predicate -- correct, slower). */
+  const int32_t* fwd_plan;
+  int32_t plan_pairs;
+  int32_t reserved0;
 } AkiMmaAttnParams;
 
 int aki_mma_attn_fwd(const AkiMmaAttnParams* p, aki_stream_t stream);

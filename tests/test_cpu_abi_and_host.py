@@ -31,7 +31,7 @@ def test_header_symbols_exported(lib):
 
 
 def test_abi_version_and_strerror(lib):
-    assert lib.lib.aki_mma_abi_version() == 1
+    assert lib.lib.aki_mma_abi_version() == 2
     assert lib.lib.aki_mma_strerror(0) == b"ok"
     for code in range(-6, 0):
         assert len(lib.lib.aki_mma_strerror(code)) > 3
