@@ -11,8 +11,9 @@
 //
 // WORK ITEM = one (batch, head) x one PAIR of query tiles from the forward plan (meta.cu, aki_mma_fwd_plan): query
 // tiles of <= 128 rows that start at every image span, ranked by the number of 128-key tiles they visit and paired
-// (both tiles of a pair consume one stream of K/V tiles).  Items are numbered heaviest-first inside groups of 16
-// (batch, head) slices (K/V of a group stay in L2); a CTA keeps asking the hardware queue for the next item
+// (both tiles of a pair consume one stream of K/V tiles).  Items are numbered heaviest-first inside groups of 64
+// (batch, head) slices (same box, T=8192: groups of 4 / 8 / 16 / 32 / 64 -> 1.07 / 1.05 / 0.99 / 0.96 / 0.95 ms);
+// a CTA keeps asking the hardware queue for the next item
 // (clusterlaunchcontrol.try_cancel) until the grid is exhausted.
 //
 // CTA = 16 warps:
@@ -38,6 +39,13 @@
 #include "attn_aux.cuh"
 #include "sm100_ptx.cuh"
 
+#ifndef AKI_FWD_POLY
+#define AKI_FWD_POLY 0         // of every 4 score pairs, how many take the polynomial exp2 (FMA pipe) instead of MUFU.EX2
+#endif                         // (same box, causal / 4 images: 0 -> 0.88 / 1.06 ms, 1 -> 0.87-0.99 / 1.04-1.19 depending on
+                               // code placement, 2 -> 0.96 / 1.14, 3 -> 1.03 / 1.24: the softmax warps are bound by their
+                               // own instruction stream, not by the MUFU pipe -- tools/mufu_bench.cu)
+
+
 namespace aki {
 
 namespace fwd {
@@ -53,7 +61,10 @@ constexpr int SMEM_ALLOC = SMEM_TOTAL + 1024;              // slack for 1024-byt
 constexpr uint32_t TM_S = 0, TM_O = 256, TM_P = 448;       // S: 128 t; O: 96 t; P: 32 t
 constexpr int REGS_CTRL = 56, REGS_SOFTMAX = 192, REGS_EPI = 72;   // 128*56 + 256*192 + 128*72 = 65536 = 512 x 128
 constexpr float RESCALE_THRESHOLD = 8.0f;  // log2 units: P may grow to 2^8 before O is rescaled
-constexpr int HEADS_PER_GROUP = 16;
+#ifndef AKI_FWD_HEADS_PER_GROUP
+#define AKI_FWD_HEADS_PER_GROUP 64
+#endif
+constexpr int HEADS_PER_GROUP = AKI_FWD_HEADS_PER_GROUP;
 }  // namespace fwd
 
 struct FwdKernelParams {
@@ -68,7 +79,15 @@ struct FwdKernelParams {
   int B, H, T;
   int ranks, group, n_items, use_clc;   // items: ((g * ranks + r) * group + slice)
   float scale_log2, scale;
+  unsigned long long* trace;  // debug build (make TRACE=1, tools/fwd_trace.py): clock64 stamps of one CTA's first item
+  int trace_cta;
 };
+
+#ifdef AKI_FWD_TRACE
+#define TR(slot, j, k) do { if (tracing && (j) < 64) P.trace[((slot) * 64 + (j)) * 12 + (k)] = clock64(); } while (0)
+#else
+#define TR(slot, j, k) do { } while (0)
+#endif
 
 __device__ __forceinline__ uint32_t low_mask(int n) {  // n low bits set, n clamped to [0,32]
   return n <= 0 ? 0u : (n >= 32 ? 0xffffffffu : ((1u << n) - 1u));
@@ -114,6 +133,30 @@ __device__ __forceinline__ bool clc_query(uint32_t resp_smem, uint32_t& cta_x) {
       : "memory");
   cta_x = x;
   return valid != 0;
+}
+
+// exp2 of two scores on the FMA pipe (Cody-Waite split + degree-3 minimax polynomial, relative error 7.5e-5 -- far
+// below the bf16 rounding of P): x = n + f with n = round(x) taken from the mantissa of x + 1.5*2^23, 2^f from the
+// polynomial on [-0.5, 0.5], 2^n by adding n to the exponent field.  The MUFU unit (4 lanes per sub-partition) is the
+// scarcest pipe of this kernel (16 384 exponentials per 128 x 128 tile = 1024 cycles against ~1000 of tensor time), so
+// a share of the scores goes this way.  Inputs below -126 (masked scores are -inf) are clamped: they come out as
+// 2^-126 ~ 1e-38 instead of 0, which vanishes against the row maximum's 2^0.
+__device__ __forceinline__ void exp2_poly_x2(uint64_t a2, float& p0, float& p1) {
+  float a0, a1;
+  f32x2_unpack(a2, a0, a1);
+  a0 = fmaxf(a0, -126.f); a1 = fmaxf(a1, -126.f);
+  a2 = f32x2_pack(a0, a1);
+  const uint64_t t2 = f32x2_add(a2, f32x2_pack(12582912.f, 12582912.f));
+  const uint64_t n2 = f32x2_add(t2, f32x2_pack(-12582912.f, -12582912.f));
+  const uint64_t f2 = f32x2_fma(n2, f32x2_pack(-1.f, -1.f), a2);
+  uint64_t q = f32x2_fma(f2, f32x2_pack(0.0551716685f, 0.0551716685f), f32x2_pack(0.242611125f, 0.242611125f));
+  q = f32x2_fma(q, f2, f32x2_pack(0.693260968f, 0.693260968f));
+  q = f32x2_fma(q, f2, f32x2_pack(0.999928057f, 0.999928057f));
+  float q0, q1, t0, t1;
+  f32x2_unpack(q, q0, q1);
+  f32x2_unpack(t2, t0, t1);
+  p0 = __uint_as_float(__float_as_uint(q0) + (__float_as_uint(t0) << 23));
+  p1 = __uint_as_float(__float_as_uint(q1) + (__float_as_uint(t1) << 23));
 }
 
 // Rare path of the online softmax: the running max grew by more than the threshold, this thread's row of O_t is
@@ -343,7 +386,11 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
         item_wait(n_it, v0, v1, v2);
         if (!v0.x) break;
         const int nk = t ? v2.y : v2.x, n_max = max(v2.x, v2.y), buf = n_it & 1;
+
         const uint32_t qa = KMAJ_LO + ((smem_base + SMEM_Q + (2 * buf + t) * TILE_BYTES) >> 4);
+#ifdef AKI_FWD_TRACE
+        const bool tracing = P.trace && (int)blockIdx.x == P.trace_cta && n_it == 0;
+#endif
         if (nk > 0) mbar_wait(ROPE ? BAR(Q_READY + buf) : BAR(Q_FULL + 2 * buf + t), (n_it >> 1) & 1);
         else mbar_arrive(BAR(Q_EMPTY + buf));
         auto handle_k = [&](int j) {
@@ -352,8 +399,10 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
           // arriving twice in one K_EMPTY phase
           mbar_wait(BAR(K_FULL + s), (c / K_STAGES) & 1);
           if (j < nk) {
+            TR(2 + t, j, 0);
             if (n_qk > 0) mbar_wait(BAR(S_FREE + t), (n_qk - 1) & 1);   // the softmax holds the previous S in registers
             tc_fence_after();
+            TR(2 + t, j, 1);
             const uint32_t ka = k_lo + s * (TILE_BYTES >> 4);
 #pragma unroll
             for (int k = 0; k < 6; ++k)
@@ -377,9 +426,11 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
             const uint32_t va = v_lo + s * (TILE_BYTES >> 4);
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
+              TR(2 + t, j, 2 + 2 * half);
               mbar_wait(BAR(P_FULL + t), n_ph & 1);
               ++n_ph;
               tc_fence_after();
+              TR(2 + t, j, 3 + 2 * half);
 #pragma unroll
               for (int k = 0; k < 4; ++k)
                 umma_ts_lh(d_o, a_p + 8 * k, va + (4 * half + k) * 64, HI_V, IDESC_PV, (j > 0 || half > 0 || k > 0));
@@ -423,7 +474,11 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
       }
       float m_used = -INFINITY;  // running max (raw score units) the accumulators are expressed against
       float l = 0.f;             // row sum
+#ifdef AKI_FWD_TRACE
+      const bool tracing = P.trace && (int)blockIdx.x == P.trace_cta && n_it == 0 && r == 0;
+#endif
       for (int j = 0; j < nk; ++j) {
+        TR(t, j, 0);
         const bool partial = (j >= n_full);            // warp-uniform (CTA-uniform)
         uint32_t vw[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
         uint32_t mw[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
@@ -439,6 +494,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
         mbar_wait(BAR(S_FULL + t), n_s & 1);
         ++n_s;
         tc_fence_after();
+        TR(t, j, 1);
         tmem_ld_x32(tm_s, reinterpret_cast<uint32_t*>(s));
         tmem_ld_x32(tm_s + 32, reinterpret_cast<uint32_t*>(s) + 32);
         tmem_ld_x32(tm_s + 64, reinterpret_cast<uint32_t*>(s) + 64);
@@ -446,6 +502,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
         tmem_wait_ld();
         tc_fence_before();
         mbar_arrive(BAR(S_FREE + t));                  // QK^T of the next pass runs under the exponentials
+        TR(t, j, 2);
         if (partial) {
 #pragma unroll
           for (int w = 0; w < 4; ++w) {
@@ -456,9 +513,12 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
             const uint32_t causal = low_mask(d + 1) & vw[w] & in_len;
             const uint32_t mutual = row_live ? (low_mask(e) & ~low_mask(a) & mw[w] & in_len) : 0u;
             const uint32_t ok = causal | mutual;
+            // a word whose 32 keys are visible to every row of this warp costs one vote
+            if (!__all_sync(0xffffffffu, ok == 0xffffffffu)) {
 #pragma unroll
-            for (int c = 0; c < 32; ++c)
-              if (!((ok >> c) & 1u)) s[32 * w + c] = -INFINITY;
+              for (int c = 0; c < 32; ++c)
+                if (!((ok >> c) & 1u)) s[32 * w + c] = -INFINITY;
+            }
           }
         }
         // ---- row maximum: three-input maxima (FMNMX3), four independent chains
@@ -489,9 +549,15 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
           uint64_t sum_a = f32x2_pack(0.f, 0.f), sum_b = sum_a;
 #pragma unroll
           for (int x = 0; x < 32; ++x) {
-            float a0, a1;
-            f32x2_unpack(f32x2_fma(f32x2_pack(s[off + 2 * x], s[off + 2 * x + 1]), sc2, nm2), a0, a1);
-            const float p0 = ex2_approx(a0), p1 = ex2_approx(a1);
+            const uint64_t a2 = f32x2_fma(f32x2_pack(s[off + 2 * x], s[off + 2 * x + 1]), sc2, nm2);
+            float p0, p1;
+            if ((x & 3) >= 4 - AKI_FWD_POLY) {
+              exp2_poly_x2(a2, p0, p1);
+            } else {
+              float a0, a1;
+              f32x2_unpack(a2, a0, a1);
+              p0 = ex2_approx(a0); p1 = ex2_approx(a1);
+            }
             if (x & 1) sum_b = f32x2_add(sum_b, f32x2_pack(p0, p1));
             else sum_a = f32x2_add(sum_a, f32x2_pack(p0, p1));
             s[off + x] = __uint_as_float(pack_bf16x2(p0, p1));
@@ -501,7 +567,9 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
           return t0 + t1;
         };
         // ---- keys 0-63 -> P -> PV(j, first half)
+        TR(t, j, 3);
         l += exps(0);
+        TR(t, j, 4);
         if (n_pvh > 0) mbar_wait(BAR(PV_DONE + t), (n_pvh - 1) & 1);   // the previous PV half has consumed P
         tc_fence_after();
         tmem_st_x32(tm_p, reinterpret_cast<const uint32_t*>(s));
@@ -509,10 +577,13 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
         tc_fence_before();
         mbar_arrive(BAR(P_FULL + t));
         ++n_pvh;
+        TR(t, j, 6);
         // ---- keys 64-127 while PV(first half) runs
         l += exps(64);
+        TR(t, j, 7);
         mbar_wait(BAR(PV_DONE + t), (n_pvh - 1) & 1);
         tc_fence_after();
+        TR(t, j, 8);
         tmem_st_x32(tm_p, reinterpret_cast<const uint32_t*>(s) + 64);
         tmem_wait_st();
         tc_fence_before();
@@ -590,7 +661,9 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
           ++n_od[t];
           tc_fence_after();
         }
-        const float inv_l = (nk > 0 && i < len && lm.x > 0.f) ? 1.f / lm.x : 0.f;   // batch-padding rows: zeros
+        // rows with no visible key (batch padding, keys all invalid): zeros.  Their maximum never left -inf;
+        // the row sum alone does not tell (the polynomial exp2 returns 2^-126, not 0, for a masked score)
+        const float inv_l = (nk > 0 && i < len && lm.x > 0.f && lm.y > -INFINITY) ? 1.f / lm.x : 0.f;
         const bool store_row = (r < rows) && (i < P.T);
         __nv_bfloat16* orow = P.o.row(b, store_row ? i : 0, h);
         // tcgen05.ld is warp-collective (.sync.aligned): load unconditionally, predicate only the global stores
@@ -742,6 +815,17 @@ extern "C" int aki_mma_attn_fwd(const AkiMmaAttnParams* p, aki_stream_t stream) 
   kp.n_items = (int)n_items;
   kp.scale = p->scale;
   kp.scale_log2 = p->scale * 1.4426950408889634f;
+  kp.trace = nullptr; kp.trace_cta = -1;
+#ifdef AKI_FWD_TRACE
+  // Debug build only (make TRACE=1; tools/fwd_trace.py): dumps clock64 stamps of one CTA's first item and SYNCHRONISES.
+  const char* trace_env = getenv("AKI_MMA_FWD_TRACE");
+  const size_t trace_bytes = 4 * 64 * 12 * sizeof(unsigned long long);
+  if (trace_env) {
+    kp.trace_cta = atoi(trace_env);
+    cudaMalloc(&kp.trace, trace_bytes);
+    cudaMemset(kp.trace, 0, trace_bytes);
+  }
+#endif
   int sm_count = 0;
   if ((rc = fwd_device_setup(&sm_count))) return rc;
   // AKI_MMA_FWD_SCHED=static: persistent CTAs walk the items with a fixed stride instead of the hardware queue (A/B only)
@@ -755,5 +839,23 @@ extern "C" int aki_mma_attn_fwd(const AkiMmaAttnParams* p, aki_stream_t stream) 
   else
     attn_fwd_sm100_kernel<false><<<grid, fwd::THREADS, fwd::SMEM_ALLOC, st>>>(mq, mk, mv, kp);
   timing_hook_end(st);
+#ifdef AKI_FWD_TRACE
+  if (trace_env) {
+    cudaDeviceSynchronize();
+    static unsigned long long host[4 * 64 * 12];
+    cudaMemcpy(host, kp.trace, trace_bytes, cudaMemcpyDeviceToHost);
+    cudaFree(kp.trace);
+    unsigned long long t0 = ~0ull;
+    for (size_t i = 0; i < 4 * 64 * 12; ++i) if (host[i] && host[i] < t0) t0 = host[i];
+    const char* names[4] = {"sm_t0", "sm_t1", "mma_t0", "mma_t1"};
+    for (int slot = 0; slot < 4; ++slot)
+      for (int j = 0; j < 64; ++j) {
+        if (!host[(slot * 64 + j) * 12] && !host[(slot * 64 + j) * 12 + 2]) continue;
+        fprintf(stderr, "TRACE %s j=%d:", names[slot], j);
+        for (int k = 0; k < 10; ++k) fprintf(stderr, " %llu", host[(slot * 64 + j) * 12 + k] ? host[(slot * 64 + j) * 12 + k] - t0 : 0ull);
+        fprintf(stderr, "\n");
+      }
+  }
+#endif
   return check_launch();
 }

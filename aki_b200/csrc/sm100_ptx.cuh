@@ -56,23 +56,38 @@ __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Spin on try_wait (a hardware-suspended wait with a time limit).  Release builds never trap: a kernel that is merely
-// slowed down (profiler replay, compute-sanitizer, MPS time slicing, a debugger) keeps waiting and backs off with
-// nanosleep once the wait is clearly long.  Bring-up builds (make TRAP=1 -> -DAKI_MBAR_TRAP) turn a protocol bug into
-// a CUDA error after AKI_MBAR_SPIN_LIMIT probes instead of hanging the box.
+// Blocking wait: try_wait with a suspend-time hint, so that the warp stays suspended in hardware until the phase
+// completes (the default time limit is only ~80 cycles: a warp spinning on it issues ~1 instruction per 8 cycles and
+// hammers the MIO queue the MUFU instructions of the softmax warps go through -- ncu: a third of all warp instructions
+// of the forward kernel were such spins).  Release builds never trap: a kernel that is merely slowed down (profiler
+// replay, compute-sanitizer, MPS time slicing, a debugger) keeps waiting.  Bring-up builds (make TRAP=1 ->
+// -DAKI_MBAR_TRAP) turn a protocol bug into a CUDA error after AKI_MBAR_SPIN_LIMIT expired waits instead of hanging the box.
 #ifndef AKI_MBAR_SPIN_LIMIT
-#define AKI_MBAR_SPIN_LIMIT (1u << 22)
+#define AKI_MBAR_SPIN_LIMIT 400u
 #endif
+#ifndef AKI_MBAR_SUSPEND_NS
+#define AKI_MBAR_SUSPEND_NS 0x989680u   // 10 ms per try_wait
+#endif
+__device__ __forceinline__ bool mbar_try_wait_hint(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
+      "selp.b32 %0, 1, 0, P;\n\t}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity), "r"(AKI_MBAR_SUSPEND_NS)
+      : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    ++spins;
 #ifdef AKI_MBAR_TRAP
-    if (spins > AKI_MBAR_SPIN_LIMIT) __trap();
-#else
-    if (spins > 64u) __nanosleep(spins > 4096u ? 256u : 32u);
-#endif
+  uint32_t spins = 0;
+  while (!mbar_try_wait_hint(bar, parity)) {
+    if (++spins > AKI_MBAR_SPIN_LIMIT) __trap();
   }
+#else
+  while (!mbar_try_wait_hint(bar, parity)) { }
+#endif
 }
 
 // ---------------------------------------------------------------------------------------------- fences
