@@ -113,28 +113,6 @@ __device__ __forceinline__ void umma_ts_lh(uint32_t d_tmem, uint32_t a_tmem, uin
       : "memory");
 }
 
-// Cluster launch control: ask the hardware queue for the next not-yet-started CTA of this grid.
-__device__ __forceinline__ void clc_try_cancel(uint32_t resp_smem, uint32_t bar) {
-  asm volatile("clusterlaunchcontrol.try_cancel.async.shared::cta.mbarrier::complete_tx::bytes.b128 [%0], [%1];" ::"r"(
-                   resp_smem),
-               "r"(bar)
-               : "memory");
-}
-__device__ __forceinline__ bool clc_query(uint32_t resp_smem, uint32_t& cta_x) {
-  uint32_t valid = 0, x = 0;
-  asm volatile(
-      "{\n\t.reg .pred p1;\n\t.reg .b128 resp;\n\t"
-      "ld.shared.b128 resp, [%2];\n\t"
-      "clusterlaunchcontrol.query_cancel.is_canceled.pred.b128 p1, resp;\n\t"
-      "selp.u32 %1, 1, 0, p1;\n\t"
-      "@p1 clusterlaunchcontrol.query_cancel.get_first_ctaid::x.b32.b128 %0, resp;\n\t}\n"
-      : "=r"(x), "=r"(valid)
-      : "r"(resp_smem)
-      : "memory");
-  cta_x = x;
-  return valid != 0;
-}
-
 // exp2 of two scores on the FMA pipe (Cody-Waite split + degree-3 minimax polynomial, relative error 7.5e-5 -- far
 // below the bf16 rounding of P): x = n + f with n = round(x) taken from the mantissa of x + 1.5*2^23, 2^f from the
 // polynomial on [-0.5, 0.5], 2^n by adding n to the exponent field.  The MUFU unit (4 lanes per sub-partition) is the

@@ -90,6 +90,29 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 #endif
 }
 
+// ---------------------------------------------------------------------------------------------- work queue
+// Cluster launch control: ask the hardware queue for the next not-yet-started CTA of this grid.
+__device__ __forceinline__ void clc_try_cancel(uint32_t resp_smem, uint32_t bar) {
+  asm volatile("clusterlaunchcontrol.try_cancel.async.shared::cta.mbarrier::complete_tx::bytes.b128 [%0], [%1];" ::"r"(
+                   resp_smem),
+               "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ bool clc_query(uint32_t resp_smem, uint32_t& cta_x) {
+  uint32_t valid = 0, x = 0;
+  asm volatile(
+      "{\n\t.reg .pred p1;\n\t.reg .b128 resp;\n\t"
+      "ld.shared.b128 resp, [%2];\n\t"
+      "clusterlaunchcontrol.query_cancel.is_canceled.pred.b128 p1, resp;\n\t"
+      "selp.u32 %1, 1, 0, p1;\n\t"
+      "@p1 clusterlaunchcontrol.query_cancel.get_first_ctaid::x.b32.b128 %0, resp;\n\t}\n"
+      : "=r"(x), "=r"(valid)
+      : "r"(resp_smem)
+      : "memory");
+  cta_x = x;
+  return valid != 0;
+}
+
 // ---------------------------------------------------------------------------------------------- fences
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
