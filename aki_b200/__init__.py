@@ -2,13 +2,13 @@
 
 Importing the package loads aki_b200/libaki_mma.so (C ABI: include/aki_mma.h); there is no fallback."""
 from . import ops                                                    # noqa: F401  (loads the library)
-from .attention import (AkiMMAAttention, aki_mma_attention, register_attention_interface,   # noqa: F401
+from .attention import (AkiMMAAttention, aki_mma_attention, mma_context, register_attention_interface,   # noqa: F401
                         replace_phi3_attention)
 from .cache import AkiKVCache                                        # noqa: F401
 from .inputs import prepare_inputs_for_forward                       # noqa: F401
 from .ops import MMASegments, build_segments                         # noqa: F401
 from .rope import LongRope, longrope_attention_factor               # noqa: F401
 
-__all__ = ["AkiMMAAttention", "aki_mma_attention", "register_attention_interface", "replace_phi3_attention",
+__all__ = ["AkiMMAAttention", "aki_mma_attention", "mma_context", "register_attention_interface", "replace_phi3_attention",
            "AkiKVCache", "prepare_inputs_for_forward", "MMASegments", "build_segments", "LongRope",
            "longrope_attention_factor", "ops"]

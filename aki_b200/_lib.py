@@ -69,16 +69,16 @@ _SIGNATURES = {
                                      C.c_void_p, C.c_void_p]),
     "aki_mma_rope_kv_write": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_int,
                                         C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64,
-                                        C.c_int, C.c_void_p, C.c_void_p]),
+                                        C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "aki_mma_rope_kv_write_dev": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_int,
                                             C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64,
-                                            C.c_void_p, C.c_void_p, C.c_void_p]),
+                                            C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "aki_mma_attn_fwd": (C.c_int, [C.POINTER(AttnParams), C.c_void_p]),
     "aki_mma_attn_bwd": (C.c_int, [C.POINTER(AttnBwdParams), C.c_void_p]),
     "aki_mma_attn_bwd_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "aki_mma_decode_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
-    "aki_mma_decode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int,
-                                 C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_size_t,
+    "aki_mma_decode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
+                                 C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_size_t,
                                  C.c_void_p]),
     "aki_mma_set_timing_events": (C.c_int, [C.c_void_p, C.c_void_p]),
     "aki_mma_attn_fwd_simt": (C.c_int, [C.POINTER(AttnParams), C.c_void_p]),

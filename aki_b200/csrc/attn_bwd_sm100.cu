@@ -887,6 +887,7 @@ extern "C" int aki_mma_attn_bwd(const AkiMmaAttnBwdParams* p, aki_stream_t strea
       (rc = check_tensor(p->d_v)))
     return rc;
   AKI_REQUIRE(f.lse && p->workspace, AKI_ERR_NULL);
+  AKI_REQUIRE(p->deterministic == 0, AKI_ERR_UNSUPPORTED);
   AKI_REQUIRE(p->workspace_bytes >= aki_mma_attn_bwd_workspace_bytes(f.B, f.H, f.T, f.D), AKI_ERR_BAD_SHAPE);
   AKI_REQUIRE((reinterpret_cast<uintptr_t>(p->workspace) & 255u) == 0, AKI_ERR_MISALIGNED);
   cudaStream_t st = static_cast<cudaStream_t>(stream);

@@ -34,12 +34,15 @@ __device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
 __global__ void __launch_bounds__(DEC_THREADS)
 decode_partial_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k_cache,
                       const __nv_bfloat16* __restrict__ v_cache, int64_t cache_stride_b, int64_t cache_stride_h,
-                      const int32_t* __restrict__ kv_len, int H, float scale_log2, int n_splits,
+                      const int32_t* __restrict__ kv_len, const int32_t* __restrict__ kv_start, int H, float scale_log2,
+                      int n_splits,
                       float* __restrict__ ws_m, float* __restrict__ ws_l, float* __restrict__ ws_acc) {
   const int split = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, s = lane & 3;
   const int len = kv_len[b];
-  const int j0 = split * DEC_CHUNK, j1 = min(j0 + DEC_CHUNK, len);
+  // keys [kv_start[b], kv_len[b]) are visible: left-padded prompts (padding_side="left" in AKI.generate) keep their pad
+  // rows at the front of the cache
+  const int j0 = max(split * DEC_CHUNK, kv_start ? kv_start[b] : 0), j1 = min(split * DEC_CHUNK + DEC_CHUNK, len);
   const size_t part = ((size_t)b * H + h) * n_splits + split;
 
   float qf[24];
@@ -168,8 +171,9 @@ extern "C" size_t aki_mma_decode_workspace_bytes(int B, int H, int D, int max_kv
 }
 
 extern "C" int aki_mma_decode(const void* q, const void* k_cache, const void* v_cache, int64_t cache_stride_b,
-                              int64_t cache_stride_h, const int32_t* kv_len, int max_kv_len, int B, int H, int D,
-                              float scale, void* out, void* workspace, size_t workspace_bytes, aki_stream_t stream) {
+                              int64_t cache_stride_h, const int32_t* kv_len, const int32_t* kv_start, int max_kv_len,
+                              int B, int H, int D, float scale, void* out, void* workspace, size_t workspace_bytes,
+                              aki_stream_t stream) {
   AKI_REQUIRE(q && k_cache && v_cache && kv_len && out && workspace, AKI_ERR_NULL);
   AKI_REQUIRE(B > 0 && H > 0 && max_kv_len > 0 && B <= 65535 && H <= 65535, AKI_ERR_BAD_SHAPE);
   AKI_REQUIRE(D == DEC_D, AKI_ERR_UNSUPPORTED);
@@ -184,8 +188,8 @@ extern "C" int aki_mma_decode(const void* q, const void* k_cache, const void* v_
   const float scale_log2 = scale * 1.4426950408889634f;
   decode_partial_kernel<<<dim3(n_splits, H, B), DEC_THREADS, 0, st>>>(
       static_cast<const __nv_bfloat16*>(q), static_cast<const __nv_bfloat16*>(k_cache),
-      static_cast<const __nv_bfloat16*>(v_cache), cache_stride_b, cache_stride_h, kv_len, H, scale_log2, n_splits, ws_m,
-      ws_l, ws_acc);
+      static_cast<const __nv_bfloat16*>(v_cache), cache_stride_b, cache_stride_h, kv_len, kv_start, H, scale_log2, n_splits,
+      ws_m, ws_l, ws_acc);
   int rc = check_launch();
   if (rc != AKI_OK) return rc;
   decode_combine_kernel<<<dim3(H, B), DEC_D, 0, st>>>(ws_m, ws_l, ws_acc, H, n_splits, static_cast<__nv_bfloat16*>(out));

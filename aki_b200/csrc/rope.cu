@@ -58,7 +58,7 @@ rope_kv_write_kernel(const __nv_bfloat16* __restrict__ qkv, int64_t qkv_stride_b
                      const float* __restrict__ cos_t, const float* __restrict__ sin_t, int64_t rope_stride_b, int T,
                      int H, __nv_bfloat16* __restrict__ k_cache, __nv_bfloat16* __restrict__ v_cache,
                      int64_t cache_stride_b, int64_t cache_stride_h, int past_len_host,
-                     const int32_t* __restrict__ past_len_dev, __nv_bfloat16* __restrict__ q_rot) {
+                     const int32_t* __restrict__ past_len_dev, int t_cap, __nv_bfloat16* __restrict__ q_rot) {
   constexpr int D = 96, HALF = 48;
   const int t = blockIdx.x, b = blockIdx.y;
   const int past_len = past_len_dev ? past_len_dev[b] : past_len_host;   // device-resident length: CUDA-graph decode
@@ -73,14 +73,15 @@ rope_kv_write_kernel(const __nv_bfloat16* __restrict__ qkv, int64_t qkv_stride_b
     *reinterpret_cast<float4*>(sn) = *reinterpret_cast<const float4*>(sr + c * 8);
     *reinterpret_cast<float4*>(sn + 4) = *reinterpret_cast<const float4*>(sr + c * 8 + 4);
     const size_t dst = (size_t)b * cache_stride_b + (size_t)h * cache_stride_h + (size_t)(past_len + t) * D;
-    {
+    const bool in_cache = (past_len + t) < t_cap;     // a row past the capacity is dropped, never written next door
+    if (in_cache) {
       const __nv_bfloat16* kp = row + (size_t)H * D + h * D + c * 8;
       uint4 lo = *reinterpret_cast<const uint4*>(kp), hi = *reinterpret_cast<const uint4*>(kp + HALF), lo2, hi2;
       rotate8(lo, hi, cs, sn, lo2, hi2);
       *reinterpret_cast<uint4*>(k_cache + dst + c * 8) = lo2;
       *reinterpret_cast<uint4*>(k_cache + dst + HALF + c * 8) = hi2;
     }
-    if (v_cache) {
+    if (v_cache && in_cache) {
       const __nv_bfloat16* vp = row + (size_t)2 * H * D + h * D + c * 8;
       *reinterpret_cast<uint4*>(v_cache + dst + c * 8) = *reinterpret_cast<const uint4*>(vp);
       *reinterpret_cast<uint4*>(v_cache + dst + HALF + c * 8) = *reinterpret_cast<const uint4*>(vp + HALF);
@@ -113,9 +114,10 @@ extern "C" int aki_mma_rope_table(const int64_t* position_ids, const float* inv_
 static int rope_kv_write_impl(const void* qkv, int64_t qkv_stride_b, int64_t qkv_stride_t, const float* cos,
                               const float* sin, int64_t rope_stride_b, int B, int T, int H, int D, void* k_cache,
                               void* v_cache, int64_t cache_stride_b, int64_t cache_stride_h, int past_len,
-                              const int32_t* past_len_dev, void* q_rot, aki_stream_t stream) {
+                              const int32_t* past_len_dev, int t_cap, void* q_rot, aki_stream_t stream) {
   AKI_REQUIRE(qkv && cos && sin && k_cache, AKI_ERR_NULL);
-  AKI_REQUIRE(B > 0 && T > 0 && H > 0 && past_len >= 0 && B <= 65535, AKI_ERR_BAD_SHAPE);
+  AKI_REQUIRE(B > 0 && T > 0 && H > 0 && past_len >= 0 && B <= 65535 && t_cap > 0, AKI_ERR_BAD_SHAPE);
+  AKI_REQUIRE(past_len_dev || past_len + T <= t_cap, AKI_ERR_BAD_SHAPE);
   AKI_REQUIRE(D == AKI_MMA_HEAD_DIM, AKI_ERR_UNSUPPORTED);
   AKI_REQUIRE(qkv_stride_b % 8 == 0 && qkv_stride_t % 8 == 0 && cache_stride_b % 8 == 0 && cache_stride_h % 8 == 0,
               AKI_ERR_UNSUPPORTED);
@@ -125,23 +127,23 @@ static int rope_kv_write_impl(const void* qkv, int64_t qkv_stride_b, int64_t qkv
   rope_kv_write_kernel<<<dim3(T, B), 192, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(qkv), qkv_stride_b, qkv_stride_t, cos, sin, rope_stride_b, T, H,
       static_cast<__nv_bfloat16*>(k_cache), static_cast<__nv_bfloat16*>(v_cache), cache_stride_b, cache_stride_h,
-      past_len, past_len_dev, static_cast<__nv_bfloat16*>(q_rot));
+      past_len, past_len_dev, t_cap, static_cast<__nv_bfloat16*>(q_rot));
   return check_launch();
 }
 
 extern "C" int aki_mma_rope_kv_write(const void* qkv, int64_t qkv_stride_b, int64_t qkv_stride_t, const float* cos,
                                      const float* sin, int64_t rope_stride_b, int B, int T, int H, int D,
                                      void* k_cache, void* v_cache, int64_t cache_stride_b, int64_t cache_stride_h,
-                                     int past_len, void* q_rot, aki_stream_t stream) {
+                                     int past_len, int t_cap, void* q_rot, aki_stream_t stream) {
   return rope_kv_write_impl(qkv, qkv_stride_b, qkv_stride_t, cos, sin, rope_stride_b, B, T, H, D, k_cache, v_cache,
-                            cache_stride_b, cache_stride_h, past_len, nullptr, q_rot, stream);
+                            cache_stride_b, cache_stride_h, past_len, nullptr, t_cap, q_rot, stream);
 }
 
 extern "C" int aki_mma_rope_kv_write_dev(const void* qkv, int64_t qkv_stride_b, int64_t qkv_stride_t, const float* cos,
                                          const float* sin, int64_t rope_stride_b, int B, int T, int H, int D,
                                          void* k_cache, void* v_cache, int64_t cache_stride_b, int64_t cache_stride_h,
-                                         const int32_t* past_len_dev, void* q_rot, aki_stream_t stream) {
+                                         const int32_t* past_len_dev, int t_cap, void* q_rot, aki_stream_t stream) {
   AKI_REQUIRE(past_len_dev, AKI_ERR_NULL);
   return rope_kv_write_impl(qkv, qkv_stride_b, qkv_stride_t, cos, sin, rope_stride_b, B, T, H, D, k_cache, v_cache,
-                            cache_stride_b, cache_stride_h, 0, past_len_dev, q_rot, stream);
+                            cache_stride_b, cache_stride_h, 0, past_len_dev, t_cap, q_rot, stream);
 }

@@ -82,7 +82,7 @@ class AkiPhi3Runner(nn.Module):
         cache.kv_len.copy_(cache.past_dev + 1)                       # keys visible to this step (incl. the new one)
         st["pos"].copy_(cache.past_dev[:1].to(torch.int64).view(1, 1))   # position id = past length (aki_generation.py:72-84)
         h = self.lm.model.embed_tokens(st["tok"])
-        inv = self.rope.inv_freq_long if st["long"] else self.rope.inv_freq_short
+        inv = self.rope.inv_freq_long if st["capturing_long"] else self.rope.inv_freq_short
         cos, sin = ops.rope_table(st["pos"], inv, self.rope.attention_factor)
         h = self._run_layers(h, cos, sin, None, cache)
         st["next"].copy_(self.lm.lm_head(h)[:, -1].argmax(-1, keepdim=True))
@@ -90,22 +90,31 @@ class AkiPhi3Runner(nn.Module):
 
     @torch.no_grad()
     def decode_step_graphed(self, token_ids: torch.Tensor, cache: AkiKVCache) -> torch.Tensor:
-        """Greedy decode step replayed from a CUDA graph: returns the next token ids (B,1).  The graph is captured on
-        first use for this cache; the write row, the key count and the position id live in device memory
-        (cache.past_dev), so replays need no host-side arguments.  The longrope factor set (short / long) is fixed at
-        capture from the cache capacity (the reference re-selects it from the running maximum position)."""
+        """Greedy decode step replayed from a CUDA graph: returns the next token ids (B,1).  A graph is captured on first
+        use for this cache and for each longrope factor set; the write row, the key count and the position id live in
+        device memory (cache.past_dev), so replays need no host-side arguments.  The factor set follows the running
+        maximum position exactly as the eager step and the reference do (modeling_rope_utils.py:47-80): short factors
+        while past + 1 <= original_max, long factors afterwards -- the step switches graphs when the boundary is crossed."""
         past = cache.get_seq_length()
+        cache._check(past + 1)                                       # BEFORE anything is enqueued: the row must exist
         g = getattr(self, "_g", None)
         if g is None or g["cache"] is not cache:
             B = token_ids.shape[0]
             dev = token_ids.device
             self._g = g = {"cache": cache, "tok": token_ids.clone(), "next": torch.zeros(B, 1, dtype=torch.int64, device=dev),
-                           "pos": torch.zeros(1, 1, dtype=torch.int64, device=dev),
-                           "long": cache.t_cap > self.rope.original_max, "graph": None}
+                           "pos": torch.zeros(1, 1, dtype=torch.int64, device=dev), "capturing_long": False, "graphs": {}}
+        use_long = (past + 1) > self.rope.original_max
+        if use_long not in g["graphs"]:
+            # warm-up (2 steps) + capture (1 step) write rows past .. past+2: they must exist, and they are restored below
+            if past + 3 > cache.t_cap:
+                raise ValueError(f"capturing the decode graph needs 3 free cache rows (have {cache.t_cap - past}): "
+                                 f"allocate the cache with t_cap >= prompt + new tokens + 2")
+            g["capturing_long"] = use_long
             cache.device_driven = True
             cache.past_dev.fill_(past)
             keep = (cache.past_dev.clone(), [k[:, :, past:past + 3].clone() for k in cache.k],
                     [v[:, :, past:past + 3].clone() for v in cache.v])
+            dev = token_ids.device
             side = torch.cuda.Stream(device=dev)
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
@@ -115,15 +124,17 @@ class AkiPhi3Runner(nn.Module):
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
                 self._graph_body(cache)
-            g["graph"] = graph
+            g["graphs"][use_long] = graph
             # undo the side effects of warm-up + capture: three rows written past the end, counters advanced
             cache.past_dev.copy_(keep[0])
             for k, v, k0, v0 in zip(cache.k, cache.v, keep[1], keep[2]):
                 k[:, :, past:past + 3].copy_(k0); v[:, :, past:past + 3].copy_(v0)
-        else:
-            cache.device_driven = True
+        cache.device_driven = True
+        if g.get("expected_past") != past:                           # eager steps (or a reset) happened in between
+            cache.past_dev.fill_(past)
         g["tok"].copy_(token_ids)
-        g["graph"].replay()
+        g["graphs"][use_long].replay()
+        g["expected_past"] = past + 1
         cache.advance_host(1)
         cache.device_driven = False
         return g["next"].clone()

@@ -57,6 +57,14 @@ class MMASegments:
     T: int
     fwd_plan: Optional[torch.Tensor] = None   # (B, 1 + pairs, 4) int32: forward work plan (aki_mma_fwd_plan)
     max_spans: int = 8                        # image spans per sample that may start a query tile of their own
+    status: Optional[torch.Tensor] = None     # (1,) int32 device flag of aki_mma_segments: 1 = some sample exceeded t_cap
+
+    def check(self) -> "MMASegments":
+        """Raises if a sample was longer than t_cap.  build_segments(t_cap=..., exact_shape=False) does no host read
+        (nothing on the prefill path synchronises); call this where a read is affordable."""
+        if self.status is not None and int(self.status.item()):
+            raise _lib.AkiMmaError(f"t_cap={self.T} is smaller than the longest spliced sample ({int(self.seq_len.max())})")
+        return self
 
     @property
     def B(self) -> int:
@@ -147,9 +155,10 @@ def build_segments(lang_x: torch.Tensor, attention_mask: torch.Tensor, num_token
                                int(text_only), _ptr(seq_len), _ptr(q_end), _ptr(seg), _ptr(row_lo), _ptr(row_hi),
                                _ptr(src), _ptr(vbits), _ptr(mbits), _ptr(status), _stream()), "aki_mma_segments")
     s = MMASegments(seq_len, q_end, seg, row_lo, row_hi, src, vbits, mbits, None, None, T, None, int(max_spans))
+    s.status = status          # (1,) int32: 1 if some sample was longer than t_cap (outputs truncated); see check()
     if exact_shape:
-        t_max = int(seq_len.max().item())
-        if t_max > T:
+        t_max, overflow = torch.stack([seq_len.max(), status[0]]).tolist()      # ONE host read for both
+        if overflow or t_max > T:
             raise _lib.AkiMmaError(f"t_cap={T} is smaller than the longest spliced sample ({t_max})")
         if t_max < T:
             return s.truncated(t_max)
@@ -245,12 +254,14 @@ def rope_kv_write(qkv: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor, k_cac
         assert past_len_dev.dtype == torch.int32 and past_len_dev.numel() == B
         check(lib.aki_mma_rope_kv_write_dev(_ptr(qkv), qkv.stride(0), qkv.stride(1), _ptr(cos), _ptr(sin), rope_sb, B, T,
                                             num_heads, HEAD_DIM, _ptr(k_cache), _ptr(v_cache), k_cache.stride(0),
-                                            k_cache.stride(1), _ptr(past_len_dev), _ptr(q_rot), _stream()),
+                                            k_cache.stride(1), _ptr(past_len_dev), k_cache.shape[2], _ptr(q_rot),
+                                            _stream()),
               "aki_mma_rope_kv_write_dev")
         return
     check(lib.aki_mma_rope_kv_write(_ptr(qkv), qkv.stride(0), qkv.stride(1), _ptr(cos), _ptr(sin), rope_sb, B, T,
                                     num_heads, HEAD_DIM, _ptr(k_cache), _ptr(v_cache), k_cache.stride(0),
-                                    k_cache.stride(1), int(past_len), _ptr(q_rot), _stream()), "aki_mma_rope_kv_write")
+                                    k_cache.stride(1), int(past_len), k_cache.shape[2], _ptr(q_rot), _stream()),
+          "aki_mma_rope_kv_write")
 
 
 # --------------------------------------------------------------------------------------------------
@@ -420,9 +431,10 @@ attn_packed_op.register_autograd(_packed_backward, setup_context=_packed_setup)
 # --------------------------------------------------------------------------------------------------
 @torch.library.custom_op("aki_mma::decode", mutates_args=())
 def decode_op(q: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tensor, kv_len: torch.Tensor, max_kv_len: int,
-              scale: float) -> torch.Tensor:
-    """q (B,H,D) bf16 post-RoPE; caches (B,H,t_cap,D) bf16; kv_len (B,) int32.  Returns (B,H,D) bf16."""
-    _require_cuda(q, k_cache, v_cache, kv_len)
+              scale: float, kv_start: _OT = None) -> torch.Tensor:
+    """q (B,H,D) bf16 post-RoPE; caches (B,H,t_cap,D) bf16; kv_len (B,) int32; kv_start (B,) int32 or None (first
+    visible key: the leading pad rows of a left-padded prompt).  Returns (B,H,D) bf16."""
+    _require_cuda(q, k_cache, v_cache, kv_len, kv_start)
     B, H, D = q.shape
     q = q.contiguous()
     out = torch.empty_like(q)
@@ -430,11 +442,12 @@ def decode_op(q: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tensor, kv_
     ws = torch.empty(nbytes, dtype=torch.uint8, device=q.device)
     assert k_cache.stride(3) == 1 and k_cache.stride(2) == D and k_cache.stride() == v_cache.stride()
     check(lib.aki_mma_decode(_ptr(q), _ptr(k_cache), _ptr(v_cache), k_cache.stride(0), k_cache.stride(1), _ptr(kv_len),
-                             int(max_kv_len), B, H, D, float(scale), _ptr(out), _ptr(ws), nbytes, _stream()),
+                             _ptr(kv_start), int(max_kv_len), B, H, D, float(scale), _ptr(out), _ptr(ws), nbytes,
+                             _stream()),
           "aki_mma_decode")
     return out
 
 
 @decode_op.register_fake
-def _(q, k_cache, v_cache, kv_len, max_kv_len, scale):
+def _(q, k_cache, v_cache, kv_len, max_kv_len, scale, kv_start=None):
     return torch.empty_like(q)

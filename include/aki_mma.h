@@ -127,18 +127,20 @@ int aki_mma_rope_table(const int64_t* position_ids, const float* inv_freq, float
  *     Reads the packed projection qkv (B,T,3*H*D) bf16 (strides given), rotates K, and writes K (post-RoPE)
  *     and V into caches laid out (B,H,t_cap,D) at rows [past_len, past_len+T).  v_cache may be NULL (training:
  *     V is consumed in place).  q_rot (B,H,T,D) bf16 may be non-NULL to also emit rotated Q (decode path).
- *     cos/sin: (B or 1, T, D/2) fp32, rope_stride_b = 0 broadcasts over batch. */
+ *     cos/sin: (B or 1, T, D/2) fp32, rope_stride_b = 0 broadcasts over batch.
+ *     t_cap (ABI 2) = rows per (b,h) of the caches: past_len + T > t_cap is AKI_ERR_BAD_SHAPE; with the device-resident
+ *     length (_dev) a row at or beyond t_cap is dropped instead of landing in the next head's rows. */
 int aki_mma_rope_kv_write(const void* qkv, int64_t qkv_stride_b, int64_t qkv_stride_t, const float* cos,
                           const float* sin, int64_t rope_stride_b, int B, int T, int H, int D, void* k_cache,
-                          void* v_cache, int64_t cache_stride_b, int64_t cache_stride_h, int past_len, void* q_rot,
-                          aki_stream_t stream);
+                          void* v_cache, int64_t cache_stride_b, int64_t cache_stride_h, int past_len, int t_cap,
+                          void* q_rot, aki_stream_t stream);
 /* Same, with the past length read from DEVICE memory (past_len_dev (B) int32, one per sequence): the decode step can
  * then be captured in a CUDA graph and replayed while the cache grows (aki_generation.py:72-84 derives the position
  * from past_key_values[0][0].shape[2] on the host every step). */
 int aki_mma_rope_kv_write_dev(const void* qkv, int64_t qkv_stride_b, int64_t qkv_stride_t, const float* cos,
                               const float* sin, int64_t rope_stride_b, int B, int T, int H, int D, void* k_cache,
                               void* v_cache, int64_t cache_stride_b, int64_t cache_stride_h,
-                              const int32_t* past_len_dev, void* q_rot, aki_stream_t stream);
+                              const int32_t* past_len_dev, int t_cap, void* q_rot, aki_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------
  * (4) Attention core -- replaces the eager path of Phi3Attention.forward: QK^T/sqrt(D) + additive mask,
@@ -190,7 +192,8 @@ typedef struct AkiMmaAttnBwdParams {
   AkiMmaTensor4 d_v;
   void* workspace;        /* aki_mma_attn_bwd_workspace_bytes() bytes, 256-byte aligned */
   size_t workspace_bytes;
-  int32_t deterministic;  /* reserved; dQ is accumulated with fp32 atomics when 0 */
+  int32_t deterministic;  /* must be 0: dQ partial sums of the key tiles are added with fp32 reductions in L2 (order varies
+                             from run to run, last-bit differences in dQ); anything else returns AKI_ERR_UNSUPPORTED */
 } AkiMmaAttnBwdParams;
 
 size_t aki_mma_attn_bwd_workspace_bytes(int B, int H, int T, int D);
@@ -199,11 +202,13 @@ int aki_mma_attn_bwd(const AkiMmaAttnBwdParams* p, aki_stream_t stream);
 /* (5) Decode -- the generate loop after prefill (aki_generation.py:56-84): a 2-D all-ones mask, i.e. one
  *     query per sequence sees every cached key [0, kv_len[b]).  Memory-bound split-KV kernel.
  *     q (B,H,D) bf16 post-RoPE; caches (B,H,t_cap,D); out (B,H,D) bf16; workspace from
- *     aki_mma_decode_workspace_bytes(). kv_len (B) int32 device array. */
+ *     aki_mma_decode_workspace_bytes(). kv_len (B) int32 device array.  kv_start (B) int32 device array or NULL (ABI 2):
+ *     first visible key of each sequence -- the leading pad rows of a left-padded prompt (padding_side="left",
+ *     aki.py:172-182) stay in the cache and must not be attended (the reference's 2-D mask zeroes them). */
 size_t aki_mma_decode_workspace_bytes(int B, int H, int D, int max_kv_len);
 int aki_mma_decode(const void* q, const void* k_cache, const void* v_cache, int64_t cache_stride_b,
-                   int64_t cache_stride_h, const int32_t* kv_len, int max_kv_len, int B, int H, int D, float scale,
-                   void* out, void* workspace, size_t workspace_bytes, aki_stream_t stream);
+                   int64_t cache_stride_h, const int32_t* kv_len, const int32_t* kv_start, int max_kv_len, int B, int H,
+                   int D, float scale, void* out, void* workspace, size_t workspace_bytes, aki_stream_t stream);
 
 /* Measurement hook (bench.py roofline): the NEXT aki_mma_attn_fwd / aki_mma_attn_bwd call of this host thread
  * records `ev_begin` right before and `ev_end` right after its tcgen05 attention kernel on the call's stream (the

@@ -56,7 +56,7 @@ def test_argument_validation_without_gpu(lib):
     assert L.aki_mma_attn_bwd_workspace_bytes(2, 32, 1000, 96) >= 2 * 32 * 1000 * 96 * (2 + 4)
     assert L.aki_mma_attn_bwd_workspace_bytes(2, 32, 1000, 64) == 0
     assert L.aki_mma_decode_workspace_bytes(1, 32, 96, 1000) == 1 * 32 * 2 * 98 * 4
-    assert L.aki_mma_rope_kv_write(None, 0, 0, None, None, 0, 1, 1, 32, 96, None, None, 0, 0, 0, None, None) == -1
+    assert L.aki_mma_rope_kv_write(None, 0, 0, None, None, 0, 1, 1, 32, 96, None, None, 0, 0, 0, 1, None, None) == -1
 
 
 def test_ops_refuse_cpu_tensors(lib):

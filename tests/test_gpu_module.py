@@ -212,6 +212,173 @@ def test_phi3_model_with_swapped_attention_matches_hf_eager_on_reference_mask():
     assert float(d.pow(2).mean().sqrt()) < 0.01 * max(scale, 1.0)
 
 
+def _small_lm(layers=2, vocab=512, seed=0):
+    from transformers import Phi3ForCausalLM
+    g = np.load(os.path.join(GOLDEN, "attn_cfg1_small.npz"))
+    cfg = _config(g["short_factor"], g["long_factor"], layers=layers, vocab=vocab)
+    torch.manual_seed(seed)
+    return cfg, Phi3ForCausalLM(cfg).to(dev).to(torch.bfloat16).eval()
+
+
+def _teacher_forced_reference_logits(ref_model, embeds, new_ids, S, T):
+    """HF eager model (untouched attention) on prompt + generated tokens in ONE pass with the reference's mask: the MMA
+    (B,1,T,T) block for the prompt, plain causal rows for the generated tokens (the generate loop's all-ones 2-D mask,
+    aki_generation.py:56-62).  Returns the logits that predict each generated token and the one after the last."""
+    n_new = new_ids.shape[1]
+    full = torch.cat([embeds, ref_model.model.embed_tokens(new_ids)], 1)
+    Tt = T + n_new
+    m4 = torch.zeros(1, 1, Tt, Tt, dtype=torch.int64)
+    m4[:, :, :T, :T] = torch.from_numpy(O.expand_segments_to_4d(S))
+    for i in range(T, Tt):
+        m4[0, 0, i, :i + 1] = 1
+    add = O.invert_4d_mask(m4.to(dev), torch.bfloat16).to(torch.bfloat16)
+    pos = torch.arange(Tt, device=dev)[None]
+    with torch.no_grad():
+        logits = ref_model(inputs_embeds=full, attention_mask=add, position_ids=pos, use_cache=False).logits
+    return logits[:, T - 1:]
+
+
+@pytest.mark.parametrize("mode", ["module", "plugin"])
+def test_hf_generate_through_the_dropin(mode):
+    """The reference's generate contract (codes/open_flamingo/src/aki.py:136-209, aki_generation.py:36-86) end to end
+    through transformers' own generate(): inputs_embeds prefill with the MMA description, then greedy decode steps on
+    the KV cache.  `module`: every self_attn replaced by AkiMMAAttention with an AkiKVCache (a transformers Cache) as
+    past_key_values; `plugin`: the stock Phi3Attention with config._attn_implementation = "aki_mma" and HF's own
+    DynamicCache.  Per-step logits against the untouched eager model fed the reference's mask, teacher-forced."""
+    import copy
+    import aki_b200
+    from aki_b200 import ops
+    cfg, model = _small_lm()
+    ref_model = copy.deepcopy(model)
+    B, L, N, n_new = 1, 70, 32, 5
+    lang, am = Hp.make_prompt(B, L, N, 1)
+    segs = ops.build_segments(torch.from_numpy(lang).to(dev), torch.from_numpy(am).to(dev), N, Hp.MEDIA_ID)
+    T = segs.T
+    S = O.segments_ref(lang, am, N, Hp.MEDIA_ID)
+    torch.manual_seed(9)
+    embeds = (torch.randn(B, T, 3072, device=dev) * 0.5).to(torch.bfloat16)
+    kw = dict(inputs_embeds=embeds, attention_mask=segs.spliced_mask_2d(), max_new_tokens=n_new, do_sample=False,
+              use_cache=True, return_dict_in_generate=True, output_logits=True, pad_token_id=0)
+    if mode == "module":
+        assert aki_b200.replace_phi3_attention(model) == 2
+        cache = aki_b200.AkiKVCache(2, B, 32, 96, t_cap=T + n_new + 1, device=dev)
+        kw["past_key_values"] = cache
+    else:
+        aki_b200.register_attention_interface("aki_mma")
+        model.config._attn_implementation = "aki_mma"
+    with aki_b200.mma_context(segs):          # generate() rejects unknown model kwargs, so the description rides the context
+        out = model.generate(**kw)
+    new_ids = out.sequences[:, -n_new:]
+    assert new_ids.shape == (B, n_new)
+    if mode == "module":
+        assert cache.get_seq_length() == T + n_new - 1     # the last generated token is never fed back
+    got = torch.stack(out.logits, 1).float()               # (B, n_new, vocab)
+    ref = _teacher_forced_reference_logits(ref_model, embeds, new_ids, S, T).float()[:, :n_new]
+    scale = float(ref.abs().max())
+    assert float((got - ref).abs().max()) < 0.06 * max(scale, 1.0), (float((got - ref).abs().max()), scale)
+    assert float((got - ref).pow(2).mean().sqrt()) < 0.012 * max(scale, 1.0)
+
+
+def test_plugin_selected_through_config_matches_module_swap():
+    """config._attn_implementation = "aki_mma" (AttentionInterface registry, modeling_utils.py:4832-4870) on the stock
+    Phi3Attention: HF passes attention_mask=None and forwards mma_segments to every layer; logits equal the module swap."""
+    import copy
+    import aki_b200
+    from aki_b200 import ops
+    cfg, model = _small_lm(seed=2)
+    swapped = copy.deepcopy(model)
+    aki_b200.replace_phi3_attention(swapped)
+    aki_b200.register_attention_interface("aki_mma")
+    model.config._attn_implementation = "aki_mma"
+    B, L, N = 2, 60, 16
+    lang, am = Hp.make_prompt(B, L, N, 2, pad_right=7)
+    segs = ops.build_segments(torch.from_numpy(lang).to(dev), torch.from_numpy(am).to(dev), N, Hp.MEDIA_ID)
+    T = segs.T
+    torch.manual_seed(3)
+    embeds = (torch.randn(B, T, 3072, device=dev) * 0.5).to(torch.bfloat16)
+    pos = torch.arange(T, device=dev)[None].expand(B, -1)
+    with torch.no_grad():
+        a_ = model(inputs_embeds=embeds, attention_mask=segs.spliced_mask_2d(), position_ids=pos, use_cache=False,
+                   mma_segments=segs).logits.float()
+        b_ = swapped(inputs_embeds=embeds, attention_mask=segs.spliced_mask_2d(), position_ids=pos, use_cache=False,
+                     mma_segments=segs).logits.float()
+    rows = Hp.live_rows(O.segments_ref(lang, am, N, Hp.MEDIA_ID), B, T).to(dev)
+    d = (a_ - b_)[rows]
+    assert float(d.abs().max()) < 0.03 * max(1.0, float(b_[rows].abs().max()))
+
+
+def test_transformers_441_call_signature():
+    """The call the reference's pinned transformers 4.41.2 decoder layer makes (keywords attention_mask, position_ids,
+    past_key_value, output_attentions, use_cache; three return values; no kwargs pass-through): rope tables from
+    position_ids, MMA description from mma_context()."""
+    import aki_b200
+    from aki_b200 import ops
+    g = np.load(os.path.join(GOLDEN, "attn_cfg1_small.npz"))
+    cfg, mod = _module_like_fixture(g)
+    mod = mod.to(dev).to(torch.bfloat16)
+    T, N = int(g["T"]), int(g["N"])
+    lang = torch.from_numpy(g["lang"]).to(dev)
+    segs = ops.build_segments(lang, torch.ones_like(lang), N, Hp.MEDIA_ID)
+    rope = aki_b200.LongRope(short_factor=g["short_factor"], long_factor=g["long_factor"], device=dev)
+    pos = torch.arange(T, device=dev)[None]
+    cos, sin = rope.tables(pos)
+    torch.manual_seed(4)
+    hidden = torch.randn(1, T, 3072, device=dev).to(torch.bfloat16)
+    with torch.no_grad():
+        ref, _ = mod(hidden, None, None, mma_segments=segs, mma_rope=(cos, sin))
+        with aki_b200.mma_context(segs):
+            ret = mod(hidden_states=hidden, attention_mask=None, position_ids=pos, past_key_value=None,
+                      output_attentions=False, use_cache=False)
+    assert isinstance(ret, tuple) and len(ret) == 3 and ret[1] is None and ret[2] is None
+    assert torch.equal(ret[0], ref)
+
+
+def test_sft_loss_and_parameter_gradients_match_hf_eager_on_reference_mask():
+    """Model-level parity of the training step (codes/open_flamingo/src/aki.py:125-130, train/train_utils.py:143-158):
+    a 2-layer random-init Phi-3 in the reference's amp_bf16 mode (fp32 master weights, bf16 autocast), HF eager attention
+    fed the reference's inverted (B,1,T,T) mask vs the same weights with every self_attn replaced by AkiMMAAttention fed
+    mma_segments.  Loss and the gradients of qkv_proj / o_proj / an MLP weight of both layers within bf16 tolerance."""
+    import copy
+    import aki_b200
+    from aki_b200 import ops
+    from aki_b200.model import AkiPhi3SFT, phi35_mini_config
+    g = np.load(os.path.join(GOLDEN, "attn_cfg1_small.npz"))
+    cfg = phi35_mini_config(num_layers=2, short_factor=g["short_factor"], long_factor=g["long_factor"])
+    sft = AkiPhi3SFT(cfg, device=dev, seed=0)
+    from transformers import Phi3ForCausalLM
+    hf = Phi3ForCausalLM(cfg).to(dev)
+    sd = {k: v for k, v in sft.lm.state_dict().items()}
+    hf.load_state_dict(sd)                                 # identical state-dict keys: the drop-in contract (b1)
+    B, L, N = 2, 90, 32
+    lang, am = Hp.make_prompt(B, L, N, 1, pad_right=11)
+    segs = ops.build_segments(torch.from_numpy(lang).to(dev), torch.from_numpy(am).to(dev), N, Hp.MEDIA_ID)
+    T = segs.T
+    S = O.segments_ref(lang, am, N, Hp.MEDIA_ID)
+    m4 = torch.from_numpy(O.expand_segments_to_4d(S)).to(dev)
+    add = O.invert_4d_mask(m4, torch.bfloat16).float()     # a7: finfo(bf16).min of the embeds dtype, stored in fp32
+    torch.manual_seed(7)
+    embeds = (torch.randn(B, T, 3072, device=dev) * 0.5).to(torch.bfloat16)
+    labels = torch.randint(3, 31000, (B, T), device=dev)
+    q_end = segs.q_end.to(torch.int64)
+    idx = torch.arange(T, device=dev)[None]
+    labels = torch.where((idx >= q_end[:, None]) & (idx < segs.seq_len[:, None]), labels, torch.full_like(labels, -100))
+    pos = torch.arange(T, device=dev)[None].expand(B, -1)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        ref_loss = hf(inputs_embeds=embeds, attention_mask=add, position_ids=pos, labels=labels, use_cache=False).loss
+    ref_loss.backward()
+    loss = sft(embeds, segs, labels)
+    loss.backward()
+    assert abs(float(loss) - float(ref_loss)) < 2e-2 * abs(float(ref_loss)), (float(loss), float(ref_loss))
+    names = [f"model.layers.{l}.self_attn.{w}.weight" for l in range(2) for w in ("qkv_proj", "o_proj")] + \
+            ["model.layers.0.mlp.down_proj.weight", "model.layers.1.mlp.gate_up_proj.weight"]
+    got = dict(sft.lm.named_parameters()); ref = dict(hf.named_parameters())
+    for n in names:
+        a_, b_ = got[n].grad.float(), ref[n].grad.float()
+        rel = float((a_ - b_).norm() / b_.norm())
+        cos_ = float((a_ * b_).sum() / (a_.norm() * b_.norm()))
+        assert rel < 6e-2 and cos_ > 0.998, (n, rel, cos_)
+
+
 @pytest.mark.gpu
 def test_trainable_splice_gradient_matches_torch_cat_reference():
     """Training path of the splice: values equal the gather kernel, gradients equal autograd through
@@ -277,3 +444,62 @@ def test_cuda_graph_decode_equals_eager_decode():
     for l in range(2):
         assert torch.equal(caches[0].k[l][:, :, :n], caches[1].k[l][:, :, :n])
         assert torch.equal(caches[0].v[l][:, :, :n], caches[1].v[l][:, :, :n])
+
+
+@pytest.mark.gpu
+def test_cuda_graph_decode_uses_the_factor_set_of_the_current_position():
+    """A cache allocated beyond original_max_position_embeddings (4096) with a short prompt: the eager step, the
+    prefill and the reference (modeling_rope_utils.py:47-80) all use the SHORT longrope factors while the running
+    position stays below 4096 -- so must the graph-replayed step (it used to pick the set from the cache capacity).
+    Also: capture needs three free rows and a full cache is refused before anything is enqueued."""
+    from aki_b200.model import AkiPhi3Runner, phi35_mini_config
+    dev = torch.device("cuda", 0)
+    short = 1.0 + np.arange(48) / 96.0
+    long = 2.0 + np.arange(48) / 12.0
+    runner = AkiPhi3Runner(phi35_mini_config(num_layers=2, short_factor=short, long_factor=long), device=dev, seed=0)
+    B, T, n_new = 1, 40, 4
+    emb = (torch.randn(B, T, 3072, generator=torch.Generator().manual_seed(2)) * 0.05).to(torch.bfloat16).to(dev)
+    outs = []
+    for graphed in (False, True):
+        cache = runner.new_cache(B, 4200)
+        logits = runner.prefill(emb, None, cache)
+        tok = logits[:, -1].argmax(-1, keepdim=True)
+        toks = [tok]
+        for _ in range(n_new):
+            tok = runner.decode_step_graphed(tok, cache) if graphed else runner.decode_step(tok, cache)[:, -1].argmax(-1, keepdim=True)
+            toks.append(tok)
+        outs.append((torch.cat(toks, 1).cpu(), cache.k[1][:, :, :T + n_new].clone()))
+    assert torch.equal(outs[0][0], outs[1][0])
+    assert torch.equal(outs[0][1], outs[1][1])
+    # capacity: a cache with no free row refuses the step up front
+    tight = runner.new_cache(B, T + 1)
+    tok = runner.prefill(emb, None, tight)[:, -1].argmax(-1, keepdim=True)
+    with pytest.raises(ValueError):
+        runner.decode_step_graphed(tok, tight)              # needs 3 free rows to capture
+    runner.decode_step(tok, tight)
+    with pytest.raises(ValueError):
+        runner.decode_step(tok, tight)                      # full
+
+
+@pytest.mark.gpu
+def test_left_padded_batched_decode_skips_the_pad_rows():
+    """Batched generate pads prompts on the LEFT (aki.py:172-182); the pad rows sit at the front of the KV cache.  The
+    decode steps must not attend them (the reference's 2-D mask zeroes them): per-sample kv_start from the spliced mask."""
+    import aki_b200
+    from aki_b200 import ops
+    H, D, tcap = 32, 96, 300
+    g = torch.Generator().manual_seed(5)
+    q = torch.randn(2, H, D, generator=g).to(torch.bfloat16)
+    kc = torch.randn(2, H, tcap, D, generator=g).to(torch.bfloat16)
+    vc = torch.randn(2, H, tcap, D, generator=g).to(torch.bfloat16)
+    starts, lens = [37, 0], [200, 200]
+    ref = torch.cat([O.decode_attention(q[b:b + 1].float()[:, :, None], kc[b:b + 1, :, starts[b]:].float(),
+                                        vc[b:b + 1, :, starts[b]:].float(), [lens[b] - starts[b]], D ** -0.5)[:, 0]
+                     for b in range(2)])
+    out = ops.decode_op(q.to(dev), kc.to(dev), vc.to(dev), torch.tensor(lens, dtype=torch.int32, device=dev), max(lens),
+                        D ** -0.5, torch.tensor(starts, dtype=torch.int32, device=dev))
+    assert float((out.float().cpu() - ref).abs().max()) < 4e-3
+    cache = aki_b200.AkiKVCache(1, 2, H, D, tcap, dev)
+    m = torch.ones(2, 50, dtype=torch.int64, device=dev); m[0, :37] = 0
+    cache.set_key_start(m)
+    assert cache.kv_start.tolist() == [37, 0]

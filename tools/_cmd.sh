@@ -1,8 +1,8 @@
 cd /root/repo; export PYTHONUNBUFFERED=1
-AKI_MMA_LIB=$PWD/build/libaki_trap.so timeout 400 python tools/bwd_check.py > gpurun_out/bwd_check.log 2>&1
-rc=$?; echo "bwd_check rc=$rc"; tail -14 gpurun_out/bwd_check.log
-if [ $rc -ne 0 ]; then exit $rc; fi
 for i in 1 2; do
-  timeout 120 python tools/bwd_time.py 2>&1 | tail -1
-  AKI_MMA_BWD_SCHED=static timeout 120 python tools/bwd_time.py 2>&1 | tail -1 | sed 's/^/static /'
+for v in r1bwd bg2 bg4 bg16 bg64; do
+  AKI_MMA_LIB=$PWD/build/libaki_$v.so timeout 120 python tools/bwd_time.py 2>&1 | tail -1
 done
+timeout 120 python tools/bwd_time.py 2>&1 | tail -1
+done
+AKI_MMA_LIB=$PWD/build/libaki_trace.so timeout 120 python tools/bwd_trace.py 0 > gpurun_out/bwd_trace_r2.txt 2>&1
