@@ -323,18 +323,21 @@ def test_oracle_parity_at_scale(T, heads, n_img, long_factors):
     m4 = torch.from_numpy(O.expand_segments_to_4d(S, t_out=T))
     add32 = O.invert_4d_mask(m4, torch.float32)
 
-    def oracle(dtype, with_grad):
-        qf = q.to(dtype).requires_grad_(with_grad); kf = k.to(dtype).requires_grad_(with_grad); vf = v.to(dtype).requires_grad_(with_grad)
-        c = torch.cat([cos, cos], -1).to(dtype); s_ = torch.cat([sin, sin], -1).to(dtype)
+    def oracle(dtype, device):
+        qf, kf, vf = (x.to(device).to(dtype).requires_grad_(True) for x in (q, k, v))
+        c = torch.cat([cos, cos], -1).to(device).to(dtype); s_ = torch.cat([sin, sin], -1).to(device).to(dtype)
         qh, kh = O.apply_rope(qf.transpose(1, 2), c, s_), O.apply_rope(kf.transpose(1, 2), c, s_)
-        out = O.eager_attention(qh, kh, vf.transpose(1, 2), add32.to(dtype), SCALE, row_block=1024)
-        if not with_grad:
-            return out.detach(), None, None, None
-        out.backward(d_o.to(dtype))
-        return out.detach(), qf.grad, kf.grad, vf.grad
+        out = O.eager_attention(qh, kh, vf.transpose(1, 2), add32.to(device).to(dtype), SCALE,
+                                row_block=1024 if device == "cpu" else None)
+        out.backward(d_o.to(device).to(dtype))
+        return tuple(x.detach().float().cpu() for x in (out, qf.grad, kf.grad, vf.grad))
 
-    o32, *g32 = oracle(torch.float32, True)
-    o16, *g16 = oracle(torch.bfloat16, True)
+    # the checker: the fp32 oracle on the host cores (seconds at these sizes)
+    o32, *g32 = oracle(torch.float32, "cpu")
+    # the yardstick of the tolerance rule ("2 x the error of the reference-style bf16 eager path"): the same
+    # oracle code in bf16.  bf16 matmuls take minutes on host cores at 8K, so this one pass runs through ATen on the GPU;
+    # it only scales the tolerance, it is never what the kernels are compared with.
+    o16, *g16 = oracle(torch.bfloat16, dev)
     # the kernels take H as a runtime size: same code path as H = 32
     kr = torch.empty(B, heads, T, D, dtype=torch.bfloat16, device=dev)
     qd, kd, vd = q.to(dev), k.to(dev), v.to(dev)
