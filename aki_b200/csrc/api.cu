@@ -1,5 +1,6 @@
 // Status strings / diagnostics of the C ABI (include/aki_mma.h).
 #include <string.h>
+#include <atomic>
 #include "api_common.cuh"
 
 namespace aki {
@@ -8,6 +9,8 @@ void set_last_cuda_error(const char* msg) {
   strncpy(g_last_cuda_error, msg ? msg : "", sizeof(g_last_cuda_error) - 1);
   g_last_cuda_error[sizeof(g_last_cuda_error) - 1] = 0;
 }
+static std::atomic<unsigned long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 static thread_local cudaEvent_t g_ev_begin = nullptr, g_ev_end = nullptr;
 void timing_hook_begin(cudaStream_t st) {
   if (g_ev_begin) cudaEventRecord(g_ev_begin, st);
@@ -26,6 +29,8 @@ extern "C" int aki_mma_set_timing_events(void* ev_begin, void* ev_end) {
 }
 
 extern "C" int aki_mma_abi_version(void) { return AKI_MMA_ABI_VERSION; }
+
+extern "C" unsigned long long aki_mma_launch_count(void) { return aki::g_launches.load(std::memory_order_relaxed); }
 
 extern "C" const char* aki_mma_strerror(int status) {
   switch (status) {

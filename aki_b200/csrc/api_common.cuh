@@ -12,7 +12,10 @@ void set_last_cuda_error(const char* msg);
 void timing_hook_begin(cudaStream_t st);
 void timing_hook_end(cudaStream_t st);
 
+void count_launch();   // aki_mma_launch_count(): one tick per kernel this library enqueues
+
 inline int check_launch() {
+  count_launch();
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_last_cuda_error(cudaGetErrorString(e));

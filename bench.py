@@ -56,6 +56,8 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-prefill", action="store_true", help="skip the AKI-4B prefill/decode section")
+    ap.add_argument("--no-longctx", action="store_true", help="skip the config-5 section (8K multi-image prefill + decode)")
+    ap.add_argument("--no-sft", action="store_true", help="skip the config-4 section (SFT step, DDP when N > 1)")
     ap.add_argument("--prefill-batch", type=int, default=8)
     return ap.parse_args()
 
@@ -144,9 +146,12 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm
-def cpu_reference_run(T, B, n_img, steps, warmup, threads=None):
-    """The reference's CPU path for this workload: materialised 4-D 0/1 mask -> additive fp32 mask -> eager
-    softmax(QK^T*scale + mask) V and its autograd backward, fp32, all host threads (oracle/mma_oracle.py)."""
+def cpu_reference_run(T, B, n_img, steps, warmup, threads=None, row_block=1024, budget_s=None):
+    """The reference's CPU path for this workload: materialised (B,1,T,T) 0/1 mask -> additive fp32 mask -> eager
+    softmax(QK^T*scale + mask) V and its autograd backward, fp32, all host threads (oracle/mma_oracle.py).  The T x T
+    score tensors of the reference do not fit host RAM at 8K x 32 heads in one piece, so the same arithmetic runs in
+    query-row blocks, each block doing its forward and backward (gradients accumulate).  Returns TFLOP/s, ms per step,
+    threads, nnz and the number of steps actually timed (budget_s bounds the run on slow hosts)."""
     from oracle import mma_oracle as O
     threads = threads or os.cpu_count()
     torch.set_num_threads(threads)
@@ -159,18 +164,51 @@ def cpu_reference_run(T, B, n_img, steps, warmup, threads=None):
     inv = O.longrope_inv_freq(D, 10000.0, np.ones(D // 2, dtype=np.float32))
     cos, sin = O.rope_cos_sin(torch.arange(T)[None].expand(B, -1), inv, 1.19)
     times = []
+    t_begin = time.perf_counter()
     for it in range(warmup + steps):
         t0 = time.perf_counter()
         mask = torch.from_numpy(O.expand_segments_to_4d(S))                 # the (B,1,T,T) int64 tensor (a1-a3)
         add = O.invert_4d_mask(mask, torch.float32)                          # a7
+        del mask
         qq = q.clone().requires_grad_(True); kk = k.clone().requires_grad_(True); vv = v.clone().requires_grad_(True)
-        out = O.eager_attention(O.apply_rope(qq, cos, sin), O.apply_rope(kk, cos, sin), vv, add, D ** -0.5)
-        out.backward(d_o)
+        for r0 in range(0, T, row_block):
+            r1 = min(T, r0 + row_block)
+            qr = O.apply_rope(qq[:, :, r0:r1], cos[:, r0:r1], sin[:, r0:r1])
+            out = O.eager_attention(qr, O.apply_rope(kk, cos, sin), vv, add[:, :, r0:r1], D ** -0.5)
+            out.backward(d_o[:, r0:r1])
         dt = time.perf_counter() - t0
         if it >= warmup:
             times.append(dt)
+        if budget_s is not None and it >= warmup and time.perf_counter() - t_begin > budget_s:
+            break
     ms = statistics.median(times) * 1e3
-    return 43008.0 * nnz / (ms * 1e-3) / 1e12, ms, threads, nnz
+    return 43008.0 * nnz / (ms * 1e-3) / 1e12, ms, threads, nnz, len(times)
+
+
+def cpu_cfg1_layer_ms(threads=None):
+    """BASELINE config 1: ONE AKI MMA attention layer forward, Phi-3.5-mini shape, batch 1, 128 image + 256
+    text tokens (T = 384), fp32 on the host cores via the reference's eager 4-D mask path.  Returns ms (median of 5)."""
+    from oracle import mma_oracle as O
+    torch.set_num_threads(threads or os.cpu_count())
+    g = np.random.default_rng(0)
+    L, N = 257, 128
+    lang = g.integers(3, 31000, size=(1, L)).astype(np.int64)
+    lang[0, 8] = MEDIA_ID; lang[0, 224] = ASST_ID
+    S = O.segments_ref(lang, np.ones_like(lang), N, MEDIA_ID)
+    T = L - 1 + N
+    torch.manual_seed(0)
+    w_qkv = torch.randn(3 * H * D, H * D) * 0.02; w_o = torch.randn(H * D, H * D) * 0.02
+    hidden = torch.randn(1, T, H * D, generator=torch.Generator().manual_seed(1))
+    inv = O.longrope_inv_freq(D, 10000.0, np.ones(D // 2, dtype=np.float32))
+    cos, sin = O.rope_cos_sin(torch.arange(T)[None], inv, 1.19)
+    ts = []
+    for it in range(7):
+        t0 = time.perf_counter()
+        add = O.invert_4d_mask(torch.from_numpy(O.expand_segments_to_4d(S)), torch.float32)
+        O.attention_module_forward(hidden, w_qkv, w_o, cos, sin, add)
+        if it >= 2:
+            ts.append((time.perf_counter() - t0) * 1e3)
+    return statistics.median(ts)
 
 
 # ------------------------------------------------------------------------------------------------ AKI-4B prefill
@@ -288,24 +326,26 @@ def prefill_section(dev, rank, world, steps, warmup, longctx=None):
 
 
 # ------------------------------------------------------------------------------------------------ SFT step (config 4)
-def sft_main(args, rank, world, local):
+def sft_section(args, dev, rank, world, local, steps, warmup):
     """BASELINE config 4: AKI-4B language model (random init, Phi-3.5-mini geometry) instruction-finetune step in the
     reference's amp_bf16 precision, per-GPU batch 4, L = 513 tokens with one <image> (144 vision tokens) -> T = 656,
     labels -100 up to <|assistant|> (sft.yaml:19-21, base.py:81-87), AdamW, grad-norm clip 1.0 every step
-    (train_utils.py:143-158); torch DDP over NCCL is the only collective.  Vision tokens are synthetic N(0,0.02)."""
+    (train_utils.py:143-158); torch DDP over NCCL is the only collective (train/instruction_finetune.py:128-130).
+    Vision tokens are synthetic N(0,0.02).  Besides the step time: the same step with the gradient all-reduce switched
+    off (DDP no_sync) -> the all-reduce time that backward did NOT hide, and NCCL's bus bandwidth on a 1 GiB buffer."""
     import torch.distributed as dist
     from torch.nn.parallel import DistributedDataParallel as DDP
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
     import aki_b200
     from aki_b200.model import AkiPhi3SFT, phi35_mini_config
     Bp, L, N = 4, 513, 144
     T = L - 1 + N
     model = AkiPhi3SFT(phi35_mini_config(num_layers=args.sft_layers), device=dev, seed=0)
     n_params = sum(p.numel() for p in model.parameters())
-    net = DDP(model, device_ids=[local], gradient_as_bucket_view=True) if world > 1 else model
+    bucket_mb = int(os.environ.get("AKI_DDP_BUCKET_MB", "256"))
+    # 15.3 GB of fp32 gradients per step: large buckets (NCCL reaches its NVLink bandwidth only on >= 100 MB messages;
+    # DDP's 25 MB default left 16.7 ms exposed on 2 GPUs), bucket views instead of copies, static graph
+    net = DDP(model, device_ids=[local], gradient_as_bucket_view=True, bucket_cap_mb=bucket_mb, static_graph=True) \
+        if world > 1 else model
     if world > 1 and args.sft_bf16_reduce:
         # gradients cross NVLink in bf16, as the reference's FSDP mixed-precision config reduces them
         # (train/distributed.py:163-167); halves the 15.3 GB fp32 all-reduce but adds two cast passes per bucket
@@ -325,11 +365,16 @@ def sft_main(args, rank, world, local):
                      (torch.randn(Bp, 1, N, 3072) * 0.02).to(torch.bfloat16).pin_memory()))
     host_loss = torch.empty(1, dtype=torch.float32).pin_memory()
 
-    def step(i):
+    def step(i, sync=True):
         ids, am, lab, vis = (x.to(dev, non_blocking=True) for x in host[i % len(host)])
         pr = aki_b200.prepare_inputs_for_forward(me, vis, ids, am, labels=lab, padding_side="right")
-        loss = net(pr["inputs_embeds"].float(), pr["mma_segments"], pr["labels"])
-        loss.backward()
+        if sync or world == 1:
+            loss = net(pr["inputs_embeds"].float(), pr["mma_segments"], pr["labels"])
+            loss.backward()
+        else:
+            with net.no_sync():
+                loss = net(pr["inputs_embeds"].float(), pr["mma_segments"], pr["labels"])
+                loss.backward()
         torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
         opt.step(); opt.zero_grad(set_to_none=True)
         host_loss.copy_(loss.detach().reshape(1), non_blocking=True)
@@ -339,37 +384,76 @@ def sft_main(args, rank, world, local):
             dist.barrier()
         torch.cuda.synchronize()
 
-    sampler = ClockSampler(local)
-    sampler.start()
-    for i in range(args.warmup):
+    def timed(n, sync):
+        barrier()
+        a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(n):
+            step(i, sync)
+        b_.record()
+        barrier()
+        return a.elapsed_time(b_) / n
+
+    for i in range(max(3, warmup)):
         step(i)
-    barrier(); sampler.mark_begin()
-    a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    for i in range(args.steps):
-        step(i)
-    b_.record()
-    barrier()
-    clocks = sampler.stop()
-    ms = a.elapsed_time(b_) / args.steps
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    ms = timed(steps, True)
+    ms_nosync = timed(max(3, steps // 2), False) if world > 1 else ms
+    # NCCL all-reduce alone on a 1 GiB fp32 buffer (the pool's measured reference: 725 GB/s bus bandwidth at 8 ranks)
+    busbw = None
+    if world > 1:
+        buf = torch.zeros(256 * 1024 * 1024, dtype=torch.float32, device=dev)
+        for _ in range(2):
+            dist.all_reduce(buf)
+        barrier()
+        a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(5):
+            dist.all_reduce(buf)
+        b_.record()
+        barrier()
+        ar_ms = a.elapsed_time(b_) / 5
+        busbw = 2.0 * (world - 1) / world * buf.numel() * 4 / (ar_ms * 1e-3) / 1e9
+        del buf
+    t = torch.tensor([ms, ms_nosync], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t[0])
+    ms, ms_nosync = float(t[0]), float(t[1])
+    loss_val = float(host_loss[0])
+    grad_bytes = n_params * (2 if args.sft_bf16_reduce else 4)
+    del model, net, opt
+    torch.cuda.empty_cache()
+    return {"workload": f"AKI-4B LM SFT step ({args.sft_layers} layers, {n_params / 1e9:.2f} B params, random init) B={Bp}/gpu "
+                        f"L={L} 1 image x {N} -> T={T}, amp_bf16 (fp32 master weights), AdamW(fused), clip 1.0, host batches "
+                        "copied in and loss read back every step",
+            "parallelism": f"DDP x{world} (NCCL gradient all-reduce, {grad_bytes / 1e9:.1f} GB "
+                           f"{'bf16' if args.sft_bf16_reduce else 'fp32'} per step, buckets of {bucket_mb} MB, static graph)",
+            "step_ms": ms, "tokens_per_s": world * Bp * T / (ms * 1e-3), "n_params": n_params, "loss": loss_val,
+            "step_ms_without_allreduce": ms_nosync, "exposed_allreduce_ms": max(0.0, ms - ms_nosync),
+            "allreduce_bytes_per_step": grad_bytes,
+            "allreduce_ideal_ms_at_measured_busbw": (2.0 * (world - 1) / world * grad_bytes / (busbw * 1e9) * 1e3) if busbw else 0.0,
+            "nccl_allreduce_busbw_gbs_1gib": busbw, "nccl_busbw_reference_gbs": 725.0,
+            "h2d_bytes_per_step": int(Bp * L * 8 * 3 + Bp * N * 3072 * 2), "d2h_bytes_per_step": 4}
+
+
+def sft_main(args, rank, world, local):
+    import torch.distributed as dist
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    sampler = ClockSampler(local)
+    sampler.start(); sampler.mark_begin()
+    r = sft_section(args, dev, rank, world, local, args.steps, args.warmup)
+    clocks = sampler.stop()
     if rank == 0:
         emit(({
-            "metric": "sft_tokens_per_s", "value": world * Bp * T / (ms * 1e-3), "unit": "tokens/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "bf16 autocast, fp32 master weights", "data": "synthetic",
-            "config": {"workload": f"AKI-4B LM SFT step ({args.sft_layers} layers, {n_params / 1e9:.2f} B params, random "
-                                   f"init) B={Bp}/gpu L={L} 1 image x {N} -> T={T}, AdamW(fused), clip 1.0, host batches "
-                                   "copied in and loss read back every step",
-                       "parallelism": f"DDP x{world} (NCCL gradient all-reduce, "
-                                      f"{n_params * (2 if args.sft_bf16_reduce else 4) / 1e9:.1f} GB "
-                                      f"{'bf16' if args.sft_bf16_reduce else 'fp32'} per step)"},
-            "loss": float(host_loss[0]), "clocks": clocks,
-            "e2e": {"value": world * Bp * T / (ms * 1e-3), "unit": "tokens/s",
-                    "h2d_bytes_per_step": int(Bp * L * 8 * 3 + Bp * N * 3072 * 2), "d2h_bytes_per_step": 4}}))
+            "metric": "sft_tokens_per_s", "value": r["tokens_per_s"], "unit": "tokens/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["step_ms"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16 autocast, fp32 master weights", "data": "synthetic",
+            "config": {"workload": r["workload"], "parallelism": r["parallelism"]},
+            "sft": r, "loss": r["loss"], "clocks": clocks,
+            "e2e": {"value": r["tokens_per_s"], "unit": "tokens/s", "h2d_bytes_per_step": r["h2d_bytes_per_step"],
+                    "d2h_bytes_per_step": 4}}))
     if world > 1:
         dist.destroy_process_group()
 
@@ -438,13 +522,17 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        Ts, Bs = min(T, 2048), 1
-        val, ms, threads, nnz = cpu_reference_run(Ts, Bs, min(n_img, 4), max(1, min(args.steps, 3)), min(args.warmup, 1))
-        sample = f"T={Ts} B={Bs} H={H} images={min(n_img, 4)} fwd+bwd fp32 eager with materialised 4-D mask"
+        # The reference's own CPU path on the SAME config as our arm (T, B, images): one step = one forward + backward
+        # of the attention core over the batch, fp32, all host threads, row-blocked so the T x T tensors fit host RAM.
+        # ~4-10 s per step at T=8192 B=2: every requested step is run unless the whole run would pass ~4 minutes, in
+        # which case the steps actually timed are reported in "steps".
+        val, ms, threads, nnz, n_timed = cpu_reference_run(T, B, n_img, args.steps, min(args.warmup, 1), budget_s=240.0)
+        sample = (f"T={T} B={B} H={H} images={n_img} fwd+bwd fp32 eager with the materialised 4-D mask, row blocks of 1024 "
+                  f"queries, {n_timed} timed step(s) of {ms:.0f} ms after {min(args.warmup, 1)} warm-up")
         emit(({"impl": "reference", "metric": "mma_attn_fwd_bwd_tflops", "value": val, "unit": "TFLOP/s",
-                          "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+                          "n_gpus": args.gpus, "steps": n_timed, "warmup": min(args.warmup, 1), "ms_per_step": ms,
                           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-                          "data": "synthetic", "config": dict(cfg, reference_sample=sample),
+                          "data": "synthetic", "config": cfg,
                           "cpu_baseline": {"value": val, "unit": "TFLOP/s", "cores": threads, "kind": "port",
                                            "sample": sample},
                           "e2e": {"value": val, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -463,7 +551,12 @@ def main():
     lang, am = make_prompt(B, T, n_img, seed=rank)
     segs = ops.build_segments(torch.from_numpy(lang).to(dev), torch.from_numpy(am).to(dev), N_VIS, MEDIA_ID, t_cap=T,
                               exact_shape=False)
-    nnz = O.count_allowed(O.segments_ref(lang, am, N_VIS, MEDIA_ID))
+    nnz = O.count_allowed(O.segments_ref(lang, am, N_VIS, MEDIA_ID))       # closed form from the oracle's segments ...
+    nnz_dev = int(sum(int(ops.rebuild_tile_bounds(ops.MMASegments(
+        segs.seq_len[b_:b_ + 1], segs.q_end[b_:b_ + 1], segs.seg[b_:b_ + 1], segs.row_lo[b_:b_ + 1], segs.row_hi[b_:b_ + 1],
+        segs.src[b_:b_ + 1], segs.kv_valid_bits[b_:b_ + 1], segs.kv_mutual_bits[b_:b_ + 1], None, None, T)).expand_to_4d().sum())
+        for b_ in range(B))) if T <= 16384 else nnz                        # ... and counted on the device from the kernels' own description
+    assert nnz_dev == nnz, (nnz_dev, nnz)
     meta = ops.meta_tuple(segs)
     g = torch.Generator(device=dev).manual_seed(rank)
     qkv = torch.randn(B, T, 3 * H * D, generator=g, device=dev, dtype=torch.float32).to(torch.bfloat16)
@@ -513,10 +606,12 @@ def main():
     barrier()
     sampler.mark_begin()
     t_start, t_end = ev(), ev()
+    launches0 = _clib.aki_mma_launch_count()
     t_start.record()
     for _ in range(args.steps):
         step(True)
     t_end.record()
+    gpu_launches = int(_clib.aki_mma_launch_count() - launches0)      # kernels of libaki_mma.so enqueued in the timed region
     barrier()
     clocks = sampler.stop()
     ms_total = t_start.elapsed_time(t_end)
@@ -611,11 +706,17 @@ def main():
         total_flops = float(sm[4])
     else:
         e2e_ms_r = float(stats[3]); total_flops = flops
-    prefill = None
+    prefill = longctx = sft = None
+    del qkv, d_o, d_qkv, k_rot
+    torch.cuda.empty_cache()
     if not args.no_prefill:
-        del qkv, d_o, d_qkv, k_rot
-        torch.cuda.empty_cache()
         prefill = prefill_section(dev, rank, world, args.steps, args.warmup)
+    if not args.no_longctx:
+        # BASELINE config 5 at every N of the scaling run: 4 x 128 image tokens in an 8K context, B=2 per GPU, 128 decode steps
+        longctx = prefill_section(dev, rank, world, max(10, args.steps // 2), args.warmup, longctx=(2, 8192, 4, 128))
+    if not args.no_sft:
+        # BASELINE config 4 at every N of the scaling run: the one workload of the path with a real collective (DDP)
+        sft = sft_section(args, dev, rank, world, local, max(4, args.steps // 8), 3)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -631,6 +732,21 @@ def main():
     tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(tp) and T == 8192 and B == 2 and n_img == 4:
         traffic = json.load(open(tp)).get("attn_bwd_sm100_kernel")
+    # Peak rule (B200_PROFILING.md): the burst figure for a kernel timed alone / in a short region at full clocks, the
+    # sustained one for a kernel inside a seconds-long step under the power cap.  The timed region here is well under a
+    # second; if the SM clock sampled during it stayed within 10 % of the maximum the burst peak is the denominator.
+    sm_mhz, sm_max = clocks.get("sm_mhz"), clocks.get("sm_max_mhz")
+    region_s = ms_total * 1e-3
+    use_burst = (region_s < 2.0) and (sm_mhz is None or sm_max is None or sm_mhz >= 0.9 * sm_max)
+    peak = pk["bf16_tflops"] if use_burst else pk["bf16_tflops_sustained"]
+    roofline = {"bound": "tensor", "kernel": "attn_bwd_sm100_kernel", "achieved": bwd_k_tf, "peak": peak,
+                "unit": "TFLOP/s", "frac": bwd_k_tf / peak,
+                "peak_source": pk_src + (", burst (timed region %.2f s at %s of %s MHz)" % (region_s, sm_mhz, sm_max) if use_burst
+                                         else ", sustained (timed region %.2f s at %s of %s MHz)" % (region_s, sm_mhz, sm_max)),
+                "frac_of_burst_peak": bwd_k_tf / pk["bf16_tflops"], "frac_of_sustained_peak": bwd_k_tf / pk["bf16_tflops_sustained"],
+                "algorithmic": "30720 * nnz FLOP per launch (SURVEY 8d)", "traffic": traffic,
+                "forward_kernel": {"kernel": "attn_fwd_sm100_kernel", "achieved": fwd_k_tf, "frac": fwd_k_tf / peak,
+                                   "algorithmic": "12288 * nnz FLOP per launch"}}
     line = {
         "metric": "mma_attn_fwd_bwd_tflops", "value": value, "unit": "TFLOP/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
@@ -641,16 +757,14 @@ def main():
                     "attn_bwd_sm100_kernel_ms": bwd_k_ms, "attn_bwd_sm100_kernel_tflops": bwd_k_tf,
                     "note": "fwd/bwd = whole C-ABI calls (rope_kv_write + forward; preprocess + memset + backward + "
                             "finalize); *_kernel = the tcgen05 kernel alone between events recorded by the library"},
-        "roofline": {"bound": "tensor", "kernel": "attn_bwd_sm100_kernel",
-                     "achieved": bwd_k_tf, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                     "frac": bwd_k_tf / pk["bf16_tflops_sustained"], "frac_of_burst_peak": bwd_k_tf / pk["bf16_tflops"],
-                     "peak_source": pk_src + ", sustained (kernel timed inside a long step)",
-                     "algorithmic": "30720 * nnz FLOP per launch (SURVEY 8d)", "traffic": traffic},
+        "roofline": roofline,
         "decode_kernel": {"bound": "hbm", "workload": f"aki_mma_decode B={Bd} H={H} T_kv={Td} D={D} (one layer)",
                           "ms": dec_ms, "achieved": dec_bytes / (dec_ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"],
                           "unit": "GB/s", "frac": dec_bytes / (dec_ms * 1e-3) / 1e9 / pk["hbm_gbs"],
                           "algorithmic": "2*B*H*T_kv*D*2 bytes (K and V read once)"},
-        "clocks": clocks, "gpu_launches": 5 * args.steps,
+        "clocks": clocks, "gpu_launches": gpu_launches,
+        "gpu_launches_note": "counted by libaki_mma.so (aki_mma_launch_count): per step rope_kv_write, attn_fwd_sm100, "
+                             "bwd_preprocess, attn_bwd_sm100, dq_finalize (+ one cudaMemsetAsync, not counted)",
     }
     if not args.no_e2e:
         line["e2e"] = {"value": total_flops / (e2e_ms_r * 1e-3) / 1e12, "unit": "TFLOP/s",
@@ -659,11 +773,21 @@ def main():
                               "next step's pinned-host input uploads on a copy stream while this step computes"}
     if prefill is not None:
         line["prefill"] = prefill
-    if not args.no_cpu and world >= 1:
-        Ts = min(T, 2048)
-        val, ms, threads, _ = cpu_reference_run(Ts, 1, min(n_img, 4), 2, 1)
+    if longctx is not None:
+        line["longctx"] = longctx
+    if sft is not None:
+        line["sft"] = sft
+    if not args.no_cpu and world == 1:
+        # bounded sample of the SAME workload on the host cores (rank 0, N=1 only): same T / images / geometry, half the
+        # batch (B=1), one warm-up + two timed steps (~10-25 s); TFLOP/s is normalised by the exact nnz, so it compares
+        # directly with `value`.  Plus config 1 (one layer forward on the CPU) in ms.
+        val, ms, threads, _, n_timed = cpu_reference_run(T, 1, n_img, 2, 1, budget_s=60.0)
         line["cpu_baseline"] = {"value": val, "unit": "TFLOP/s", "cores": threads, "kind": "port",
-                                "sample": f"T={Ts} B=1 H={H} images={min(n_img, 4)} fwd+bwd fp32 eager, {ms:.0f} ms/step"}
+                                "sample": f"T={T} B=1 of {B} H={H} images={n_img} fwd+bwd fp32 eager (materialised 4-D mask, "
+                                          f"row blocks of 1024 queries), {n_timed} timed step(s) of {ms:.0f} ms",
+                                "cfg1_layer_forward_ms": cpu_cfg1_layer_ms(threads),
+                                "cfg1_note": "BASELINE config 1: one MMA attention layer forward (qkv_proj, RoPE, 4-D mask, "
+                                             "eager softmax, o_proj), batch 1, 128 image + 256 text tokens, fp32, host cores"}
     emit(line)
     if world > 1:
         dist.destroy_process_group()

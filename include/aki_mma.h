@@ -216,6 +216,10 @@ int aki_mma_decode(const void* q, const void* k_cache, const void* v_cache, int6
  * Both are cudaEvent_t created by the caller with timing enabled; pass NULL, NULL to cancel.  No reference
  * counterpart (the reference has no profiling hooks). */
 int aki_mma_set_timing_events(void* ev_begin, void* ev_end);
+/* Number of CUDA kernels this library has enqueued since it was loaded (process-wide, all threads): bench.py reports
+ * the difference over its timed region as "gpu_launches".  cudaMemsetAsync of the backward workspace is not a kernel of
+ * this library and is not counted.  No reference counterpart. */
+unsigned long long aki_mma_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------------------
  * Verification kernels (tests only): the same maths as (4) written as plain SIMT CUDA with no tensor cores,

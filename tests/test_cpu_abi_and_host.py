@@ -147,6 +147,9 @@ def test_bench_reference_arm_prints_exactly_one_json_line():
     assert d["impl"] == "reference" and d["metric"] == "mma_attn_fwd_bwd_tflops" and d["unit"] == "TFLOP/s"
     assert d["value"] > 0 and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    # the line reports what actually ran: the requested config (not a reduced sample) and the steps really timed
+    assert d["steps"] == 1 and d["warmup"] == 0 and "T=512 B=1" in d["config"]["workload"]
+    assert "T=512 B=1" in d["cpu_baseline"]["sample"]
     quiet = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
                             "--warmup", "0"], capture_output=True, text=True, timeout=600,
                            env=dict(env, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1"), cwd=ROOT)
