@@ -31,9 +31,8 @@
 // item's tail; the dK / dV epilogue of item n overlaps S^T / dP^T of item n+1.
 // 16 warps: 0 TMA producer | 1, 2 MMA issuers (streams A / B; 2 also allocates TMEM) | 3 scheduler: next item id, list of
 // the query tiles to visit | 4-11 compute (thread <-> key row r; the two warpgroups split the 128 query columns of a
-// tile in halves) | 12-15 dQ drain + per-tile mask statistics (lane <-> query row: row_lo / width of the mutual
-// interval, published one step ahead through a 2-stage mbarrier ring; only tiles that are not fully visible read
-// them).  Tensor-pipe order per query tile: dV(i) S(i+1) dQ(i) dK(i) dP(i+1) -- the dQ drain overlaps dK, the
+// tile in halves; on the few tiles that are not fully visible they read the query rows' mutual intervals from
+// global memory) | 12-15 dQ drain.  Tensor-pipe order per query tile: dV(i) S(i+1) dQ(i) dK(i) dP(i+1) -- the dQ drain overlaps dK, the
 // exponentials of tile i+1 overlap dQ/dK/dP.
 // TMEM columns: S^T [0,128)  dP^T/dQ [128,256)  dV [256,352)  dK [352,448)  P^T (bf16 pairs) [448,512).
 // Shared memory: K, V 24 KB each (resident), Q ring 2x(24+2) KB (the [128][8] row statistics travel with Q), dO ring
@@ -69,10 +68,8 @@ constexpr int SMEM_QAUG = SMEM_DQ + 2 * DQ_ATOM_BYTES;      // Q_STAGES x AUG_BY
 constexpr int SMEM_ONES = SMEM_QAUG + Q_STAGES * AUG_BYTES; // core matrix [8][16 B] of [1,1,1,0,0,0,0,0] rows (selects -LSE/scale)
 constexpr int SMEM_ONES_D = SMEM_ONES + 128;                // core matrix of [0,0,0,0,1,1,1,0] rows (selects -delta)
 constexpr int SMEM_ZERO = SMEM_ONES_D + 128;                // one all-zero core matrix
-constexpr int SMEM_STATS = SMEM_ZERO + 128;                 // 2 stages x {lo[128], width[128], flags[4]} int32
-constexpr int STATS_STAGE_INTS = 260;           // lo[128], width[128], one "relevant" flag per drain warp
 constexpr int SLOTS = 2;                      // item ring: the current item and the next one
-constexpr int SMEM_QLIST = SMEM_STATS + 2 * STATS_STAGE_INTS * 4 + 32;   // SLOTS x uint16[MAX_TILES]
+constexpr int SMEM_QLIST = SMEM_ZERO + 128;                 // SLOTS x uint16[MAX_TILES]
 constexpr int SMEM_TOTAL = SMEM_QLIST + SLOTS * MAX_TILES * 2;
 #ifndef AKI_BWD_SLICES_PER_GROUP
 #define AKI_BWD_SLICES_PER_GROUP 8
@@ -124,8 +121,8 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
   constexpr int KV_FULL = 0, KV_EMPTY = 1, Q_FULL = 2, Q_EMPTY = Q_FULL + Q_STAGES, DO_FULL = Q_EMPTY + Q_STAGES,
                 DO_EMPTY = DO_FULL + DO_STAGES, S_FULL = DO_EMPTY + DO_STAGES, P_READY = S_FULL + 1,
                 DP_FULL = P_READY + 1, DS_READY = DP_FULL + 1, DQ_FULL = DS_READY + 1, DQ_DRAINED = DQ_FULL + 1,
-                ALL_DONE = DQ_DRAINED + 1, ACC_FREE = ALL_DONE + 1, ST_FULL = ACC_FREE + 1, ST_EMPTY = ST_FULL + 2,
-                ITEM_FULL = ST_EMPTY + 2, ITEM_EMPTY = ITEM_FULL + SLOTS, CLC_BAR = ITEM_EMPTY + SLOTS, N_BARS = CLC_BAR + 1;
+                ALL_DONE = DQ_DRAINED + 1, ACC_FREE = ALL_DONE + 1,
+                ITEM_FULL = ACC_FREE + 1, ITEM_EMPTY = ITEM_FULL + SLOTS, CLC_BAR = ITEM_EMPTY + SLOTS, N_BARS = CLC_BAR + 1;
   __shared__ __align__(8) uint64_t bars[N_BARS];
   __shared__ __align__(16) int4 item_ring[SLOTS][2];   // {valid, b, h, kt} {n_q, keys_all_valid, len, 0}
   __shared__ __align__(16) uint4 clc_resp;
@@ -135,7 +132,6 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   uint16_t* const qlist_all = reinterpret_cast<uint16_t*>(smem_gen + SMEM_QLIST);
-  int* const stats_gen = reinterpret_cast<int*>(smem_gen + SMEM_STATS);
 
   if (tid == 0) {
     mbar_init(BAR(KV_FULL), 1); mbar_init(BAR(KV_EMPTY), 2);
@@ -145,7 +141,6 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
     mbar_init(BAR(S_FULL), 1); mbar_init(BAR(P_READY), 256); mbar_init(BAR(DP_FULL), 1);
     mbar_init(BAR(DS_READY), 256); mbar_init(BAR(DQ_FULL), 1); mbar_init(BAR(DQ_DRAINED), 128);
     mbar_init(BAR(ALL_DONE), 2); mbar_init(BAR(ACC_FREE), 256);
-    for (int i = 0; i < 2; ++i) { mbar_init(BAR(ST_FULL + i), 128); mbar_init(BAR(ST_EMPTY + i), 256); }
     for (int i = 0; i < SLOTS; ++i) { mbar_init(BAR(ITEM_FULL + i), 1); mbar_init(BAR(ITEM_EMPTY + i), 15); }
     mbar_init(BAR(CLC_BAR), 1);
     fence_barrier_init();
@@ -583,24 +578,23 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
 #endif
         }
         if (!full) {
-          // c visible iff (c >= cmin, causal) or (row c of the tile is an image row whose interval holds key j)
-          const int st = c & 1;
-          mbar_wait(BAR(ST_FULL + st), (c >> 1) & 1);
-          const int* sp = stats_gen + st * STATS_STAGE_INTS;
+          // c visible iff (c >= cmin, causal) or (row c of the tile is an image row whose interval holds key j).  The
+          // intervals of this half's 64 query rows come straight from global memory (warp-uniform addresses: one
+          // broadcast transaction per load, L1-resident); only tiles that are not fully visible get here -- the diagonal,
+          // key tiles with padding and the image-row visits before the diagonal.  (They used to travel through a
+          // 2-stage shared-memory ring filled by another warp; releasing a stage of that ring without having waited
+          // for it -- fully visible tiles skip the wait -- let the consumer overtake the producer by a whole phase.)
           const int cmin = k_valid ? (j - i0 - 64 * hq) : (1 << 30);
-          if ((sp[256] | sp[257] | sp[258] | sp[259]) && k_mutual) {
-            const int4* lo4 = reinterpret_cast<const int4*>(sp + 64 * hq);
-            const int4* w4 = reinterpret_cast<const int4*>(sp + 128 + 64 * hq);
+          if (P.mm.row_lo && k_mutual) {
+            const int32_t* lo_p = P.mm.row_lo + (size_t)b * P.mm.meta_pitch + i0 + 64 * hq;
+            const int32_t* hi_p = P.mm.row_hi + (size_t)b * P.mm.meta_pitch + i0 + 64 * hq;
+            const int n_live = len - (i0 + 64 * hq);       // rows c >= n_live lie beyond the sequence
 #pragma unroll
-            for (int c4 = 0; c4 < 16; ++c4) {
-              const int4 a = lo4[c4], w = w4[c4];
-              const int lo[4] = {a.x, a.y, a.z, a.w}, wd[4] = {w.x, w.y, w.z, w.w};
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const int cc = 4 * c4 + e;
-                const bool ok = (cc >= cmin) || ((unsigned)(j - lo[e]) < (unsigned)wd[e]);
-                p[cc] = ok ? p[cc] : 0.f;
-              }
+            for (int cc = 0; cc < 64; ++cc) {
+              int lo = 0, wd = 0;
+              if (cc < n_live) { lo = __ldg(lo_p + cc); wd = max(__ldg(hi_p + cc) - lo, 0); }
+              const bool ok = (cc >= cmin) || ((unsigned)(j - lo) < (unsigned)wd);
+              p[cc] = ok ? p[cc] : 0.f;
             }
           } else {
 #pragma unroll
@@ -616,7 +610,6 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
         tc_fence_before();
         mbar_arrive(BAR(P_READY));
         TRB(slot, it, 3);
-        mbar_arrive(BAR(ST_EMPTY + (c & 1)));
       };
 
       auto phase_b = [&](int it) {
@@ -743,49 +736,10 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
     }
   } else {
     // ------------------------------------------------------------------ dQ drain warps (lane r <-> QUERY row r)
-    // They also publish, one step ahead, the mask statistics of the query tile the compute warps will mask next
-    // (row_lo / width of each query row's mutual interval): the statistics cursor runs one step ahead of the drain.
     setmaxnreg_dec<REGS_DRAIN>();
     const int r = tid - 384;
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     uint32_t n_it = 0, gs = 0;
-    // statistics cursor
-    uint32_t s_item = 0, s_gs = 0;
-    int s_it = 0;
-    int4 sv0 = make_int4(0, 0, 0, 0), sv1 = sv0;
-    bool s_have = false, s_end = false;
-    // publishes the statistics of the next step unless that step lies beyond item `limit` (a slot of the item ring is
-    // only recycled once this warpgroup has released it, so the cursor never waits for an item further ahead)
-    auto try_publish_stats = [&](uint32_t limit) -> bool {
-      for (;;) {
-        if (s_end || s_item > limit) return false;
-        if (!s_have) {
-          item_wait(s_item, sv0, sv1);
-          if (!sv0.x) { s_end = true; return false; }
-          s_have = true; s_it = 0;
-        }
-        if (s_it < sv1.x) break;
-        s_have = false; ++s_item;       // item exhausted (or empty): move on
-      }
-      const int b = sv0.y, j0 = sv0.w * BN, len = sv1.z;
-      const int i0 = (int)(qlist_all + (s_item % SLOTS) * MAX_TILES)[s_it];
-      const int st = s_gs & 1;
-      mbar_wait(BAR(ST_EMPTY + st), ((s_gs >> 1) & 1) ^ 1);
-      int* dst = stats_gen + st * STATS_STAGE_INTS;
-      const int i = i0 + r;
-      int lo = 0, w = 0;
-      if (i < len && P.mm.row_lo) {
-        lo = __ldg(P.mm.row_lo + (size_t)b * P.mm.meta_pitch + i);
-        w = max(__ldg(P.mm.row_hi + (size_t)b * P.mm.meta_pitch + i) - lo, 0);
-      }
-      const bool rel = __any_sync(0xffffffffu, w > 0 && lo < j0 + BN && lo + w > j0);
-      dst[r] = lo;
-      dst[128 + r] = w;
-      if (lane == 0) dst[256 + (warp & 3)] = rel ? 1 : 0;
-      mbar_arrive(BAR(ST_FULL + st));
-      ++s_it; ++s_gs;
-      return true;
-    };
     for (;;) {
       int4 v0, v1;
       item_wait(n_it, v0, v1);
@@ -795,11 +749,9 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
 #ifdef AKI_FWD_TRACE
       const bool tracing = P.trace && (int)blockIdx.x == P.trace_cta && r == 0 && n_it == 0;
 #endif
-      while (s_gs < gs + 1 && try_publish_stats(n_it)) { }       // this item's first step (if not published yet)
       for (int it = 0; it < n_q; ++it) {
         const uint32_t c = gs + it;
         const int i0 = (int)qlist[it];
-        while (s_gs < c + 2 && try_publish_stats(n_it + 1)) { }  // step c + 1 (possibly the first step of the next item)
         TRB(4, it, 0);
         mbar_wait(BAR(DQ_FULL), c & 1);
         tc_fence_after();

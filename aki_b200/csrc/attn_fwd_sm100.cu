@@ -369,8 +369,15 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
 #ifdef AKI_FWD_TRACE
         const bool tracing = P.trace && (int)blockIdx.x == P.trace_cta && n_it == 0;
 #endif
-        if (nk > 0) mbar_wait(ROPE ? BAR(Q_READY + buf) : BAR(Q_FULL + 2 * buf + t), (n_it >> 1) & 1);
-        else mbar_arrive(BAR(Q_EMPTY + buf));
+        if (nk > 0) {
+          mbar_wait(ROPE ? BAR(Q_READY + buf) : BAR(Q_FULL + 2 * buf + t), (n_it >> 1) & 1);
+        } else {
+          // this tile does not exist in the item: release the Q buffer -- but only once the producer has armed it for
+          // THIS item (a plain arrive on Q_FULL).  An unconditional arrive would let this warp run two items ahead on
+          // tiny items and complete a Q_EMPTY phase with two arrivals of its own while the other tile still reads Q.
+          mbar_wait(BAR(Q_FULL + 2 * buf + t), (n_it >> 1) & 1);
+          mbar_arrive(BAR(Q_EMPTY + buf));
+        }
         auto handle_k = [&](int j) {
           const uint32_t c = kc + j, s = c % K_STAGES;
           // waited for even when this tile skips the keys: it keeps the tile from running a whole ring ahead and

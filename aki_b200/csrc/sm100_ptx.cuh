@@ -61,9 +61,10 @@ __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
 // hammers the MIO queue the MUFU instructions of the softmax warps go through -- ncu: a third of all warp instructions
 // of the forward kernel were such spins).  Release builds never trap: a kernel that is merely slowed down (profiler
 // replay, compute-sanitizer, MPS time slicing, a debugger) keeps waiting.  Bring-up builds (make TRAP=1 ->
-// -DAKI_MBAR_TRAP) turn a protocol bug into a CUDA error after AKI_MBAR_SPIN_LIMIT expired waits instead of hanging the box.
-#ifndef AKI_MBAR_SPIN_LIMIT
-#define AKI_MBAR_SPIN_LIMIT 400u
+// -DAKI_MBAR_TRAP) turn a protocol bug into a CUDA error after AKI_MBAR_TRAP_NS of wall clock instead of hanging the box
+// (the hardware may return from try_wait long before the hint expires, so expired waits are not counted).
+#ifndef AKI_MBAR_TRAP_NS
+#define AKI_MBAR_TRAP_NS 4000000000ull   // bring-up builds: a wait longer than 4 s of wall clock is a protocol bug
 #endif
 #ifndef AKI_MBAR_SUSPEND_NS
 #define AKI_MBAR_SUSPEND_NS 0x989680u   // 10 ms per try_wait
@@ -81,9 +82,11 @@ __device__ __forceinline__ bool mbar_try_wait_hint(uint32_t bar, uint32_t parity
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 #ifdef AKI_MBAR_TRAP
-  uint32_t spins = 0;
+  unsigned long long t0 = 0, now;
   while (!mbar_try_wait_hint(bar, parity)) {
-    if (++spins > AKI_MBAR_SPIN_LIMIT) __trap();
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+    if (t0 == 0) t0 = now;
+    else if (now - t0 > AKI_MBAR_TRAP_NS) __trap();
   }
 #else
   while (!mbar_try_wait_hint(bar, parity)) { }

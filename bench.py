@@ -489,6 +489,7 @@ def longctx_main(args, rank, world, local):
 
 # ------------------------------------------------------------------------------------------------ main
 _REAL_STDOUT_FD = None
+_T0 = time.time()
 
 
 def emit(obj):
@@ -709,14 +710,19 @@ def main():
     prefill = longctx = sft = None
     del qkv, d_o, d_qkv, k_rot
     torch.cuda.empty_cache()
+    note = lambda m: (sys.stderr.write(f"[bench rank {rank}] {m} t={time.time() - _T0:.1f}s\n"), sys.stderr.flush())
+    note("attention + e2e done")
     if not args.no_prefill:
         prefill = prefill_section(dev, rank, world, args.steps, args.warmup)
+    note("prefill section done")
     if not args.no_longctx:
         # BASELINE config 5 at every N of the scaling run: 4 x 128 image tokens in an 8K context, B=2 per GPU, 128 decode steps
         longctx = prefill_section(dev, rank, world, max(10, args.steps // 2), args.warmup, longctx=(2, 8192, 4, 128))
+    note("longctx section done")
     if not args.no_sft:
         # BASELINE config 4 at every N of the scaling run: the one workload of the path with a real collective (DDP)
         sft = sft_section(args, dev, rank, world, local, max(4, args.steps // 8), 3)
+    note("sft section done")
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
