@@ -11,8 +11,10 @@
 //
 // WORK ITEM = one (batch, head) x one PAIR of query tiles from the forward plan (meta.cu, aki_mma_fwd_plan): query
 // tiles of <= 128 rows that start at every image span, ranked by the number of 128-key tiles they visit and paired
-// (both tiles of a pair consume one stream of K/V tiles).  Items are numbered heaviest-first inside groups of 64
-// (batch, head) slices (same box, T=8192: groups of 4 / 8 / 16 / 32 / 64 -> 1.07 / 1.05 / 0.99 / 0.96 / 0.95 ms);
+// (both tiles of a pair consume one stream of K/V tiles).  Items are numbered heaviest-first inside groups of 32
+// (batch, head) slices: the group size trades DRAM re-reads of K/V against L2 hot spots (many CTAs streaming the
+// same K/V lines at the same moment) -- same box, T=8192, 4 images: groups of 16 / 32 / 64 -> 1.066 / 1.013 / 0.990 ms
+// with 0.59 / 1.19 / 2.47 GB read from DRAM per launch (algorithmic: 0.3 GB);
 // a CTA keeps asking the hardware queue for the next item
 // (clusterlaunchcontrol.try_cancel) until the grid is exhausted.
 //
@@ -62,7 +64,7 @@ constexpr uint32_t TM_S = 0, TM_O = 256, TM_P = 448;       // S: 128 t; O: 96 t;
 constexpr int REGS_CTRL = 56, REGS_SOFTMAX = 192, REGS_EPI = 72;   // 128*56 + 256*192 + 128*72 = 65536 = 512 x 128
 constexpr float RESCALE_THRESHOLD = 8.0f;  // log2 units: P may grow to 2^8 before O is rescaled
 #ifndef AKI_FWD_HEADS_PER_GROUP
-#define AKI_FWD_HEADS_PER_GROUP 64
+#define AKI_FWD_HEADS_PER_GROUP 32
 #endif
 constexpr int HEADS_PER_GROUP = AKI_FWD_HEADS_PER_GROUP;
 }  // namespace fwd

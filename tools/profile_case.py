@@ -1,6 +1,6 @@
 """One forward + backward of the bench workload (T=8192, B=2, 4 image spans) for ncu:
-  ncu --set full --clock-control none --import-source on -k regex:'attn_fwd_sm100|attn_bwd_sm100|bwd_preprocess|dq_finalize' \
-      -c 4 -o gpurun_out/prof python tools/profile_case.py
+  ncu --set full --clock-control none --import-source on -k regex:'attn_fwd_sm100|attn_bwd_sm100|bwd_preprocess|dq_finalize|decode_partial|decode_combine|rope_kv_write|fwd_plan' \
+      -c 9 -o gpurun_out/prof python tools/profile_case.py
 then tools/ncu_summary.py gpurun_out/prof.ncu-rep profiles/<name>.csv"""
 import os, sys
 import numpy as np, torch
@@ -25,4 +25,10 @@ dq = torch.empty_like(q4.contiguous()); dk = torch.empty_like(dq); dv = torch.em
 ops.rope_kv_write(qkv, cos, sin, k_rot, None, 0, H)
 o, lse = ops.attn_fwd_raw(q4, k_rot.transpose(1, 2), v4, cos, sin, meta, D ** -0.5)
 ops.attn_bwd_raw(d_o, q4, k_rot.transpose(1, 2), v4, o, lse, cos, sin, meta, D ** -0.5, dq, dk, dv)
+torch.cuda.synchronize()
+# decode attention against an 8K cache (HBM-bound): B=8 sequences x 32 heads
+Bd, Td = 8, 8192
+kc = torch.randn(Bd, H, Td, D, device=dev).to(torch.bfloat16); vc = torch.randn(Bd, H, Td, D, device=dev).to(torch.bfloat16)
+qd = torch.randn(Bd, H, D, device=dev).to(torch.bfloat16)
+ops.decode_op(qd, kc, vc, torch.full((Bd,), Td, dtype=torch.int32, device=dev), Td, D ** -0.5)
 torch.cuda.synchronize()
