@@ -62,6 +62,18 @@ def parse():
     return ap.parse_args()
 
 
+def init_nccl(dev):
+    """One process per GPU over NCCL.  The communicator's kernels run on HIGH-PRIORITY streams: DDP's bucket all-reduces
+    are launched while backward GEMMs fill every SM, and without priority their CTAs wait for whole GEMM waves to drain
+    (measured on 2 B200s: the 27 ms of all-reduce left 17.5 ms exposed behind an 85 ms backward)."""
+    import torch.distributed as dist
+    try:
+        opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+        dist.init_process_group("nccl", device_id=dev, pg_options=opts)
+    except Exception:
+        dist.init_process_group("nccl", device_id=dev)
+
+
 def make_prompt(B, T, n_img, seed=0):
     """lang_x (B,L) whose spliced length is exactly T: n_img <image> tokens evenly spaced (first at 8),
     <|assistant|> so that q_end = T - 64."""
@@ -331,8 +343,8 @@ def sft_section(args, dev, rank, world, local, steps, warmup):
     reference's amp_bf16 precision, per-GPU batch 4, L = 513 tokens with one <image> (144 vision tokens) -> T = 656,
     labels -100 up to <|assistant|> (sft.yaml:19-21, base.py:81-87), AdamW, grad-norm clip 1.0 every step
     (train_utils.py:143-158); torch DDP over NCCL is the only collective (train/instruction_finetune.py:128-130).
-    Vision tokens are synthetic N(0,0.02).  Besides the step time: the same step with the gradient all-reduce switched
-    off (DDP no_sync) -> the all-reduce time that backward did NOT hide, and NCCL's bus bandwidth on a 1 GiB buffer."""
+    Vision tokens are synthetic N(0,0.02).  Besides the step time: the same step on the bare module (no gradient
+    all-reduce) in the same run -> the all-reduce time that backward did NOT hide, and NCCL's bus bandwidth at 1 GiB."""
     import torch.distributed as dist
     from torch.nn.parallel import DistributedDataParallel as DDP
     import aki_b200
@@ -368,13 +380,9 @@ def sft_section(args, dev, rank, world, local, steps, warmup):
     def step(i, sync=True):
         ids, am, lab, vis = (x.to(dev, non_blocking=True) for x in host[i % len(host)])
         pr = aki_b200.prepare_inputs_for_forward(me, vis, ids, am, labels=lab, padding_side="right")
-        if sync or world == 1:
-            loss = net(pr["inputs_embeds"].float(), pr["mma_segments"], pr["labels"])
-            loss.backward()
-        else:
-            with net.no_sync():
-                loss = net(pr["inputs_embeds"].float(), pr["mma_segments"], pr["labels"])
-                loss.backward()
+        # sync=False: the same step on the bare module (no DDP hooks, no all-reduce): this rank's compute-only time
+        loss = (net if sync else model)(pr["inputs_embeds"].float(), pr["mma_segments"], pr["labels"])
+        loss.backward()
         torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
         opt.step(); opt.zero_grad(set_to_none=True)
         host_loss.copy_(loss.detach().reshape(1), non_blocking=True)
@@ -440,7 +448,7 @@ def sft_main(args, rank, world, local):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        init_nccl(dev)
     sampler = ClockSampler(local)
     sampler.start(); sampler.mark_begin()
     r = sft_section(args, dev, rank, world, local, args.steps, args.warmup)
@@ -467,7 +475,7 @@ def longctx_main(args, rank, world, local):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        init_nccl(dev)
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
@@ -544,7 +552,7 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        init_nccl(dev)
     import aki_b200
     from aki_b200 import ops
     from oracle import mma_oracle as O

@@ -1,6 +1,9 @@
 cd /root/repo; export PYTHONUNBUFFERED=1
-for v in hg16 hg32 hg48 default; do
-  if [ $v = default ]; then unset AKI_MMA_LIB; else export AKI_MMA_LIB=$PWD/build/libaki_$v.so; fi
-  timeout 100 python tools/fwd_time.py 2>&1 | tail -1
-  timeout 100 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:attn_fwd_sm100 -s 2 -c 1 python tools/fwd_only.py 2>&1 | grep -E "dram__bytes" | awk '{print "   ", $1, $2, $3}'
-done
+run() { timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --workload sft --steps 10 --warmup 3 2>gpurun_out/sft.err | python -c "
+import sys,json
+d=json.loads(sys.stdin.read())['sft']
+print('$1', 'step', round(d['step_ms'],1), 'compute-only', round(d['step_ms_without_allreduce'],1), 'exposed', round(d['exposed_allreduce_ms'],1), 'busbw', round(d['nccl_allreduce_busbw_gbs_1gib'],0))"; }
+run highprio
+AKI_DDP_BUCKET_MB=100 run highprio_b100
+AKI_DDP_BUCKET_MB=25 run highprio_b25
+grep -i "error\|Traceback" gpurun_out/sft.err | head -3
