@@ -209,44 +209,71 @@ fwd_plan_kernel(const int32_t* __restrict__ seq_len, const int32_t* __restrict__
     }
     if (bad) atomicMin(&s_first_bad, kt);
   }
-  // span starts (cuts), as many as the pair budget allows
+  // change points of the rows' mutual interval: a span STARTS where a row with a non-empty interval follows a row with
+  // a different (or no) interval, and ENDS where a row without one follows
   const int n_aligned = n_kt;
   const int budget = min(max(2 * max_pairs - n_aligned - 1, 0), PLAN_MAX_CUTS);
   if ((flags & 1) && lo && budget > 0) {
     for (int i = 1 + tid; i < len; i += PLAN_THREADS) {
-      const int a = lo[i], e = hi[i];
-      if (e > a) {
-        const int a0 = lo[i - 1], e0 = hi[i - 1];
-        if (!(e0 > a0) || a0 != a) {
-          const int k = atomicAdd(&s_ncut, 1);
-          if (k < PLAN_MAX_CUTS) s_cut[k] = i;
-        }
+      const int a = lo[i], e = hi[i], a0 = lo[i - 1], e0 = hi[i - 1];
+      const int id = (e > a) ? a : -1, id0 = (e0 > a0) ? a0 : -1;     // identity of the span a row belongs to
+      if (id != id0) {
+        const int k = atomicAdd(&s_ncut, 1);
+        if (k < PLAN_MAX_CUTS) s_cut[k] = i;
       }
     }
   }
   __syncthreads();
-  const int ncut_all = min(s_ncut, PLAN_MAX_CUTS);
-  // rank sort of the cuts (ascending), keep the first `budget`
-  for (int k = tid; k < ncut_all; k += PLAN_THREADS) {
+  const int nchg = min(s_ncut, PLAN_MAX_CUTS);
+  // rank sort of the change points (ascending) into s_seg_tile0 (scratch until the walk below)
+  for (int k = tid; k < nchg; k += PLAN_THREADS) {
     const int v = s_cut[k];
     int rank = 0;
-    for (int m = 0; m < ncut_all; ++m) rank += (s_cut[m] < v) ? 1 : 0;
-    s_cut_sorted[1 + rank] = v;
+    for (int m = 0; m < nchg; ++m) rank += (s_cut[m] < v) ? 1 : 0;
+    s_seg_tile0[rank] = v;
   }
   __syncthreads();
-  const int ncut = min(ncut_all, budget);
   if (tid == 0) {
+    // Walk the change points and decide where the 128-row grid is cut.  Cutting at a span start p makes the span its
+    // own query tile (only ONE tile walks the keys up to <|assistant|>) but leaves a short tile in front of p and puts
+    // the following tiles off the 128-key grid (each then straddles one more key tile on its diagonal); cutting again
+    // at the next multiple of 128 behind the span puts them back.  Each cut is taken only when the key-tile visits it
+    // adds (unused rows of a short tile x the key tiles that tile visits) are fewer than those it saves.
+    int nb = 0, prev = 0;                      // boundaries so far (excluding 0), last boundary
     s_cut_sorted[0] = 0;
-    s_cut_sorted[1 + ncut] = T;
+    for (int k = 0; k < nchg && nb < budget; ++k) {
+      const int c = s_seg_tile0[k];
+      const int a = lo[c], e = hi[c];
+      const int off = (c - prev) % AKI_MMA_TILE;               // rows of the short tile a cut at c would leave behind
+      if (e > a) {                                             // span start
+        if (off != 0) {
+          const int waste_cut = (AKI_MMA_TILE - off) * ((c + AKI_MMA_TILE - 1) / AKI_MMA_TILE);          // x 1/128
+          const int waste_nocut = ((min(e, len) + AKI_MMA_TILE - 1) / AKI_MMA_TILE - (c + AKI_MMA_TILE - 1) / AKI_MMA_TILE) * AKI_MMA_TILE;
+          if (waste_cut <= waste_nocut) { s_cut_sorted[++nb] = c; prev = c; }
+        }
+      } else if (prev % AKI_MMA_TILE != 0) {                   // span end on a grid that is off the key tiles: realign?
+        const int G = (c + AKI_MMA_TILE - 1) / AKI_MMA_TILE * AKI_MMA_TILE;
+        const int next_chg = (k + 1 < nchg) ? s_seg_tile0[k + 1] : len;
+        if (G > c && G < next_chg && G < len) {
+          const int r = (G - prev) % AKI_MMA_TILE;             // rows of the short tile in front of G
+          const int waste_realign = (r == 0) ? 0 : (AKI_MMA_TILE - r) * (G / AKI_MMA_TILE);              // x 1/128
+          const int waste_stay = (min(next_chg, len) - G);     // one more key tile for every later tile: x 1/128 too
+          if (waste_realign < waste_stay) { s_cut_sorted[++nb] = G; prev = G; }
+        }
+      }
+    }
+    s_ncut = nb;
+    s_cut_sorted[1 + nb] = T;
     int n = 0;
-    for (int k = 0; k <= ncut; ++k) {
+    for (int k = 0; k <= nb; ++k) {
       s_seg_tile0[k] = n;
       n += (s_cut_sorted[k + 1] - s_cut_sorted[k] + AKI_MMA_TILE - 1) / AKI_MMA_TILE;
     }
-    s_seg_tile0[ncut + 1] = n;
+    s_seg_tile0[nb + 1] = n;
     s_ntiles = n;
   }
   __syncthreads();
+  const int ncut = s_ncut;
   const int n_tiles = s_ntiles;   // <= n_aligned + ncut <= 2 * max_pairs - 1
   // tiles of each segment
   for (int k = warp; k <= ncut; k += PLAN_THREADS / 32) {
