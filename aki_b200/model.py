@@ -75,6 +75,49 @@ class AkiPhi3Runner(nn.Module):
         h = self._run_layers(h, cos, sin, None, cache)
         return self.lm.lm_head(h)
 
+    # ---- fused decode layers ("next" row f-1 of SURVEY 8): 7 launches per layer instead of ~15 --------------------------
+    @torch.no_grad()
+    def _fused_layers(self, h: torch.Tensor, cos, sin, cache: AkiKVCache, past: Optional[int]):
+        """One decode step through all decoder layers for h (B<=8, 3072): RMSNorm->qkv_proj, RoPE + KV write, decode
+        attention, o_proj + residual, RMSNorm->gate_up_proj->SiLU gate, down_proj + residual -- each GEMM one
+        weight-streaming kernel (ops.skinny_linear) with the norm / activation / residual fused in.  past=None: the write
+        row and key count come from device memory (CUDA-graph replay).  Returns the last-layer hidden state (B,3072)."""
+        B = h.shape[0]
+        H, D, eps = 32, 96, self.config.rms_norm_eps
+        for li, layer in enumerate(self.lm.model.layers):
+            attn = layer.self_attn
+            qkv = ops.skinny_linear(h, attn.qkv_proj.weight, layer.input_layernorm.weight, eps)
+            q_rot = torch.empty(B, H, 1, D, dtype=torch.bfloat16, device=h.device)
+            if past is None:
+                ops.rope_kv_write(qkv.view(B, 1, -1), cos, sin, cache.k[li], cache.v[li], 0, H, q_rot=q_rot,
+                                  past_len_dev=cache.past_dev)
+                max_kv = cache.t_cap
+            else:
+                ops.rope_kv_write(qkv.view(B, 1, -1), cos, sin, cache.k[li], cache.v[li], past, H, q_rot=q_rot)
+                max_kv = past + 1
+            o = ops.decode_op(q_rot.view(B, H, D), cache.k[li], cache.v[li], cache.kv_len, max_kv, attn.scaling, cache.kv_start)
+            h = ops.skinny_linear(o.view(B, H * D), attn.o_proj.weight, residual=h)
+            act = ops.skinny_linear(h, layer.mlp.gate_up_proj.weight, layer.post_attention_layernorm.weight, eps, swiglu=True)
+            h = ops.skinny_linear(act, layer.mlp.down_proj.weight, residual=h)
+        return h
+
+    @torch.no_grad()
+    def decode_step_fused(self, token_ids: torch.Tensor, cache: AkiKVCache):
+        """decode_step through the fused layers (host-driven cache bookkeeping); returns logits (B,1,vocab)."""
+        past = cache.get_seq_length()
+        cache._check(past + 1)
+        B = token_ids.shape[0]
+        if B > 8:
+            return self.decode_step(token_ids, cache)
+        h = self.lm.model.embed_tokens(token_ids).view(B, -1)
+        pos = torch.full((1, 1), past, device=h.device, dtype=torch.long)
+        cos, sin = self.rope.tables(pos, max_position=past)
+        cache.kv_len.fill_(past + 1)
+        h = self._fused_layers(h, cos, sin, cache, past)
+        cache._len = [n + 1 for n in cache._len]
+        logits = ops.skinny_linear(h, self.lm.lm_head.weight, self.lm.model.norm.weight, self.config.rms_norm_eps)
+        return logits.view(B, 1, -1)
+
     # ---- CUDA-graph decode ("next" row f-4 of SURVEY 8): the whole 32-layer step is one graph launch -----------------
     @torch.no_grad()
     def _graph_body(self, cache: AkiKVCache):
@@ -84,25 +127,33 @@ class AkiPhi3Runner(nn.Module):
         h = self.lm.model.embed_tokens(st["tok"])
         inv = self.rope.inv_freq_long if st["capturing_long"] else self.rope.inv_freq_short
         cos, sin = ops.rope_table(st["pos"], inv, self.rope.attention_factor)
-        h = self._run_layers(h, cos, sin, None, cache)
-        st["next"].copy_(self.lm.lm_head(h)[:, -1].argmax(-1, keepdim=True))
+        if st["fused"]:
+            hf = self._fused_layers(h.view(h.shape[0], -1), cos, sin, cache, None)
+            logits = ops.skinny_linear(hf, self.lm.lm_head.weight, self.lm.model.norm.weight, self.config.rms_norm_eps)
+            st["next"].copy_(logits.argmax(-1, keepdim=True))
+        else:
+            h = self._run_layers(h, cos, sin, None, cache)
+            st["next"].copy_(self.lm.lm_head(h)[:, -1].argmax(-1, keepdim=True))
         cache.past_dev.add_(1)
 
     @torch.no_grad()
-    def decode_step_graphed(self, token_ids: torch.Tensor, cache: AkiKVCache) -> torch.Tensor:
-        """Greedy decode step replayed from a CUDA graph: returns the next token ids (B,1).  A graph is captured on first
+    def decode_step_graphed(self, token_ids: torch.Tensor, cache: AkiKVCache, fused: bool = True) -> torch.Tensor:
+        """Greedy decode step replayed from a CUDA graph: returns the next token ids (B,1).  fused (default, B <= 8): the
+        layers run through the weight-streaming kernels of _fused_layers.  A graph is captured on first
         use for this cache and for each longrope factor set; the write row, the key count and the position id live in
         device memory (cache.past_dev), so replays need no host-side arguments.  The factor set follows the running
         maximum position exactly as the eager step and the reference do (modeling_rope_utils.py:47-80): short factors
         while past + 1 <= original_max, long factors afterwards -- the step switches graphs when the boundary is crossed."""
         past = cache.get_seq_length()
         cache._check(past + 1)                                       # BEFORE anything is enqueued: the row must exist
+        fused = bool(fused) and token_ids.shape[0] <= 8
         g = getattr(self, "_g", None)
-        if g is None or g["cache"] is not cache:
+        if g is None or g["cache"] is not cache or g["fused"] != fused:
             B = token_ids.shape[0]
             dev = token_ids.device
             self._g = g = {"cache": cache, "tok": token_ids.clone(), "next": torch.zeros(B, 1, dtype=torch.int64, device=dev),
-                           "pos": torch.zeros(1, 1, dtype=torch.int64, device=dev), "capturing_long": False, "graphs": {}}
+                           "pos": torch.zeros(1, 1, dtype=torch.int64, device=dev), "capturing_long": False, "graphs": {},
+                           "fused": fused}
         use_long = (past + 1) > self.rope.original_max
         if use_long not in g["graphs"]:
             # warm-up (2 steps) + capture (1 step) write rows past .. past+2: they must exist, and they are restored below

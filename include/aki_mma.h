@@ -210,6 +210,19 @@ int aki_mma_decode(const void* q, const void* k_cache, const void* v_cache, int6
                    int64_t cache_stride_h, const int32_t* kv_len, const int32_t* kv_start, int max_kv_len, int B, int H,
                    int D, float scale, void* out, void* workspace, size_t workspace_bytes, aki_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------------
+ * (6) Decode-sized linear layers around the attention op (ABI 2) -- for B <= 8 tokens (one per sequence of
+ *     a decode step) replaces Phi3RMSNorm.forward + nn.Linear + the SiLU gate of Phi3MLP + the residual adds of
+ *     Phi3DecoderLayer.forward (transformers/models/phi3/modeling_phi3.py:49-64, 295-335):
+ *        y (B,N) = epilogue( prologue(x) (B,K) . W (N,K)^T )         bf16 in / out, fp32 accumulation, W row-major
+ *     rms_weight (K) bf16 or NULL: RMSNorm prologue with HF's rounding points ((x * rsqrt(mean x^2 + eps)).bf16 * weight)
+ *     mode 0: store | 1: y = residual + (.) (residual (B,N) bf16) | 2: SwiGLU, W has 2N rows (gate rows [0,N), up rows
+ *     [N,2N) as gate_up_proj stores them), y = up * silu(gate).
+ *     N % 16 == 0; K % 1024 == 0; strides in elements.  HBM-bound: N*K*2 bytes per call. */
+int aki_mma_skinny_linear(const void* x, int64_t x_stride, const void* w, const void* rms_weight, float rms_eps,
+                          const void* residual, int64_t residual_stride, void* y, int64_t y_stride, int B, int N, int K,
+                          int mode, aki_stream_t stream);
+
 /* Measurement hook (bench.py roofline): the NEXT aki_mma_attn_fwd / aki_mma_attn_bwd call of this host thread
  * records `ev_begin` right before and `ev_end` right after its tcgen05 attention kernel on the call's stream (the
  * preprocess / memset / finalize launches of the backward stay outside), then the hook clears itself.

@@ -433,7 +433,7 @@ def test_cuda_graph_decode_equals_eager_decode():
         toks = [tok]
         for _ in range(n_new):
             if graphed:
-                tok = runner.decode_step_graphed(tok, cache)
+                tok = runner.decode_step_graphed(tok, cache, fused=False)
             else:
                 tok = runner.decode_step(tok, cache)[:, -1].argmax(-1, keepdim=True)
             toks.append(tok)
@@ -466,7 +466,7 @@ def test_cuda_graph_decode_uses_the_factor_set_of_the_current_position():
         tok = logits[:, -1].argmax(-1, keepdim=True)
         toks = [tok]
         for _ in range(n_new):
-            tok = runner.decode_step_graphed(tok, cache) if graphed else runner.decode_step(tok, cache)[:, -1].argmax(-1, keepdim=True)
+            tok = runner.decode_step_graphed(tok, cache, fused=False) if graphed else runner.decode_step(tok, cache)[:, -1].argmax(-1, keepdim=True)
             toks.append(tok)
         outs.append((torch.cat(toks, 1).cpu(), cache.k[1][:, :, :T + n_new].clone()))
     assert torch.equal(outs[0][0], outs[1][0])
@@ -503,3 +503,70 @@ def test_left_padded_batched_decode_skips_the_pad_rows():
     m = torch.ones(2, 50, dtype=torch.int64, device=dev); m[0, :37] = 0
     cache.set_key_start(m)
     assert cache.kv_start.tolist() == [37, 0]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,K,N,mode", [(1, 3072, 9216, "norm"), (8, 3072, 9216, "norm"), (3, 3072, 3072, "residual"),
+                                        (8, 3072, 8192, "swiglu"), (5, 8192, 3072, "residual"), (8, 3072, 32064, "norm"),
+                                        (2, 3072, 3072, "plain")])
+def test_skinny_linear_matches_the_layers_it_replaces(B, K, N, mode):
+    """aki_mma_skinny_linear vs the HF modules it stands in for at decode size (modeling_phi3.py:49-64, 295-335):
+    Phi3RMSNorm + nn.Linear, nn.Linear + residual add, gate_up_proj + SiLU gate -- same rounding points, so the difference
+    is accumulation order only."""
+    from aki_b200 import ops
+    from transformers.models.phi3.modeling_phi3 import Phi3RMSNorm
+    dev_ = torch.device("cuda", 0)
+    g = torch.Generator().manual_seed(B * 7 + N)
+    x = torch.randn(B, K, generator=g).to(torch.bfloat16).to(dev_)
+    w = (torch.randn((2 * N if mode == "swiglu" else N), K, generator=g) * K ** -0.5).to(torch.bfloat16).to(dev_)
+    if mode == "norm":
+        norm = Phi3RMSNorm(K, eps=1e-5).to(dev_).to(torch.bfloat16)
+        norm.weight.data = (1 + 0.1 * torch.randn(K, generator=g)).to(torch.bfloat16).to(dev_)
+        ref = torch.nn.functional.linear(norm(x), w)
+        got = ops.skinny_linear(x, w, norm.weight, 1e-5)
+    elif mode == "residual":
+        res = torch.randn(B, N, generator=g).to(torch.bfloat16).to(dev_)
+        ref = res + torch.nn.functional.linear(x, w)
+        got = ops.skinny_linear(x, w, residual=res)
+    elif mode == "swiglu":
+        gu = torch.nn.functional.linear(x, w)
+        gate, up = gu.chunk(2, dim=-1)
+        ref = up * torch.nn.functional.silu(gate)
+        got = ops.skinny_linear(x, w, swiglu=True)
+    else:
+        ref = torch.nn.functional.linear(x, w)
+        got = ops.skinny_linear(x, w)
+    assert got.shape == ref.shape
+    d = (got.float() - ref.float()).abs().max().item()
+    assert d <= 2e-2 * max(1.0, ref.float().abs().max().item()), (d, ref.float().abs().max().item())
+
+
+@pytest.mark.gpu
+def test_fused_decode_step_matches_the_hf_layer_path():
+    """SURVEY 8 f-1 for decode: the fused step (7 launches per layer) against the step through HF's Phi3DecoderLayer
+    objects (RMSNorm / Linear / MLP in ATen + cuBLAS around the same attention kernels): logits of every step, the greedy
+    tokens, and the cache contents; then the graph-replayed fused step against the eager fused step."""
+    from aki_b200.model import AkiPhi3Runner, phi35_mini_config
+    dev_ = torch.device("cuda", 0)
+    runner = AkiPhi3Runner(phi35_mini_config(num_layers=2), device=dev_, seed=0)
+    B, T, n_new = 3, 50, 5
+    emb = (torch.randn(B, T, 3072, generator=torch.Generator().manual_seed(3)) * 0.05).to(torch.bfloat16).to(dev_)
+    caches = [runner.new_cache(B, T + n_new + 3) for _ in range(3)]
+    toks = []
+    for c in caches:
+        toks.append(runner.prefill(emb, None, c)[:, -1].argmax(-1, keepdim=True))
+    assert torch.equal(toks[0], toks[1])
+    tok = toks[0]
+    for step in range(n_new):
+        ref = runner.decode_step(tok, caches[0]).float()
+        got = runner.decode_step_fused(tok, caches[1]).float()
+        scale = float(ref.abs().max())
+        assert float((got - ref).abs().max()) < 3e-2 * max(scale, 1.0), (step, float((got - ref).abs().max()), scale)
+        nxt_graph = runner.decode_step_graphed(tok, caches[2], fused=True)
+        assert torch.equal(nxt_graph, got[:, -1].argmax(-1, keepdim=True)), step
+        tok = ref[:, -1].argmax(-1, keepdim=True)
+    n = T + n_new
+    for l in range(2):
+        a_, b_ = caches[0].k[l][:, :, :n].float(), caches[1].k[l][:, :, :n].float()
+        assert float((a_ - b_).abs().max()) < 3e-2 * max(1.0, float(a_.abs().max()))
+        assert torch.equal(caches[1].k[l][:, :, :n], caches[2].k[l][:, :, :n])
