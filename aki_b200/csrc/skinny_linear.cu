@@ -7,8 +7,8 @@
 //             multiply by the weight, round to bf16); every CTA recomputes it for its own copy of x (B x K bf16 in shared
 //             memory, L2-resident source)
 //   product   one CTA = 16 warps = 1 or 4 tiles of 16 output features (x2 weight rows for the gate/up pair of the SwiGLU
-//             mode) x 16 or 4 K slices; a warp streams its 16 x K/slices weights with 16-byte no-allocate loads,
-//             double-buffered in registers, straight into mma.sync m16n8k16 A fragments
+//             mode) x 16 or 4 K slices; a warp streams its 16 x K/slices weights with 16-byte no-allocate loads through
+//             a register ring (64 registers = 8 KB per warp in flight) straight into mma.sync m16n8k16 A fragments
 //             (M = weight rows, N = 8 = tokens, fp32 accumulation).  The K positions of a fragment are permuted so that
 //             one thread's 8 consecutive weights / activations are one 16-byte load -- a dot product does not care.
 //             (tcgen05 needs M = 128 x N >= 16 tiles fed through shared memory; at 8 tokens the legacy warp-level MMA with
@@ -17,6 +17,7 @@
 // HBM-bound: algorithmic bytes = N*K*2 (x2 in mode 2) per call.
 #include <cuda_bf16.h>
 #include <math.h>
+#include <stdlib.h>
 #include "api_common.cuh"
 
 namespace aki {
@@ -47,6 +48,36 @@ skinny_linear_kernel(const __nv_bfloat16* __restrict__ x, int64_t x_stride, cons
   const int row_bytes = K * 2 + 64;            // +64: the two rows of a quarter-warp's 16-byte reads hit disjoint banks
   __shared__ float inv_rms[8];
   __shared__ float red[WARPS][8];
+  // ---- this warp: row tile `rt` of the CTA, K slice `ks`.  Its weights go through a ring of R 32-wide K chunks held in
+  // registers: half a ring is reloaded for K + 32 R as soon as the tensor core has consumed it, so 4 - 8 KB per warp stay
+  // in flight, and the reloads of one weight row are 64 R / 2 contiguous bytes issued back to back (single 64-byte
+  // requests per row, spread in time, measured 35 % slower: DRAM page locality).  The first R chunks are requested before anything else -- weights do not depend on the previous kernel,
+  // so with programmatic dependent launch they stream in while the producer of x is still draining.
+  const int rt = warp / KSPLIT, ks = warp % KSPLIT;
+  const int n0 = (blockIdx.x * TILES + rt) * SK_ROWS;
+  const int k_per_warp = K / KSPLIT;                 // multiple of 64
+  const int kb = ks * k_per_warp;
+  const bool live = n0 < N;
+  const __nv_bfloat16* w_lo = w + (size_t)((live ? n0 : 0) + g) * K + kb + 8 * c;
+  const __nv_bfloat16* w_hi = w_lo + (size_t)8 * K;
+  constexpr int NB = (MODE == 2) ? 4 : 2;            // uint4 per chunk: lo, hi rows (+ the up rows)
+  constexpr int R = (MODE == 2) ? 4 : 8;             // 64 registers of weights per thread either way
+  uint4 ring[R][NB];
+  auto load = [&](uint4 (&d)[NB], int k0) {
+    d[0] = ldg_stream_v4(w_lo + k0);
+    d[1] = ldg_stream_v4(w_hi + k0);
+    if (MODE == 2) {
+      d[2] = ldg_stream_v4(w_lo + (size_t)N * K + k0);
+      d[3] = ldg_stream_v4(w_hi + (size_t)N * K + k0);
+    }
+  };
+  if (live) {
+#pragma unroll
+    for (int u = 0; u < R; ++u)
+      if (32 * u < k_per_warp) load(ring[u], 32 * u);
+  }
+  asm volatile("griddepcontrol.wait;" ::: "memory");          // x / residual come from the previous kernel
+  asm volatile("griddepcontrol.launch_dependents;");
   // ---- stage x (B x K) into shared memory in ONE pass over global memory (every CTA reads all of x: keep it to one
   // pass and to few CTAs); the RMSNorm is then applied in place
   {
@@ -99,51 +130,33 @@ skinny_linear_kernel(const __nv_bfloat16* __restrict__ x, int64_t x_stride, cons
     }
   }
   __syncthreads();
-  // ---- this warp: row tile `rt` of the CTA, K slice `ks`; weights double-buffered in registers (the loads of the
-  // next 64 K positions are in flight while the current ones go through the tensor cores)
-  const int rt = warp / KSPLIT, ks = warp % KSPLIT;
-  const int n0 = (blockIdx.x * TILES + rt) * SK_ROWS;
-  const int k_per_warp = K / KSPLIT;                 // multiple of 64
-  const int kb = ks * k_per_warp;
-  const bool live = n0 < N;
-  const __nv_bfloat16* w_lo = w + (size_t)((live ? n0 : 0) + g) * K + kb + 8 * c;
-  const __nv_bfloat16* w_hi = w_lo + (size_t)8 * K;
   const uint8_t* xs = sk_smem + (size_t)g * row_bytes + (size_t)(kb + 8 * c) * 2;
   float acc[4] = {0.f, 0.f, 0.f, 0.f}, acc2[4] = {0.f, 0.f, 0.f, 0.f};
-  constexpr int U = 2;                               // 32-wide K chunks per buffer
-  constexpr int NB = (MODE == 2) ? 4 : 2;            // uint4 per chunk: lo, hi rows (+ the up rows)
-  uint4 buf[2][U][NB];
-  auto load = [&](uint4 (&d)[U][NB], int k0) {
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      d[u][0] = ldg_stream_v4(w_lo + k0 + 32 * u);
-      d[u][1] = ldg_stream_v4(w_hi + k0 + 32 * u);
-      if (MODE == 2) {
-        d[u][2] = ldg_stream_v4(w_lo + (size_t)N * K + k0 + 32 * u);
-        d[u][3] = ldg_stream_v4(w_hi + (size_t)N * K + k0 + 32 * u);
-      }
-    }
-  };
-  auto compute = [&](const uint4 (&d)[U][NB], int k0) {
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const uint4 xv = *reinterpret_cast<const uint4*>(xs + (size_t)(k0 + 32 * u) * 2);
-      mma_bf16_16x8x16(acc, d[u][0].x, d[u][1].x, d[u][0].y, d[u][1].y, xv.x, xv.y);
-      mma_bf16_16x8x16(acc, d[u][0].z, d[u][1].z, d[u][0].w, d[u][1].w, xv.z, xv.w);
-      if (MODE == 2) {
-        mma_bf16_16x8x16(acc2, d[u][2].x, d[u][3].x, d[u][2].y, d[u][3].y, xv.x, xv.y);
-        mma_bf16_16x8x16(acc2, d[u][2].z, d[u][3].z, d[u][2].w, d[u][3].w, xv.z, xv.w);
-      }
-    }
-  };
   if (live) {
-    constexpr int STEP = 32 * U;
-    load(buf[0], 0);
-    for (int k0 = 0; k0 < k_per_warp; k0 += 2 * STEP) {
-      if (k0 + STEP < k_per_warp) load(buf[1], k0 + STEP);
-      compute(buf[0], k0);
-      if (k0 + 2 * STEP < k_per_warp) load(buf[0], k0 + 2 * STEP);
-      if (k0 + STEP < k_per_warp) compute(buf[1], k0 + STEP);
+    constexpr int H = R / 2;                         // reload half a ring at a time: 64 H contiguous bytes per weight row
+    for (int k0 = 0; k0 < k_per_warp; k0 += 32 * R) {
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+#pragma unroll
+        for (int u = half * H; u < half * H + H; ++u) {
+          const int kk = k0 + 32 * u;
+          if (kk < k_per_warp) {
+            const uint4 xv = *reinterpret_cast<const uint4*>(xs + (size_t)kk * 2);
+            const uint4 (&d)[NB] = ring[u];
+            mma_bf16_16x8x16(acc, d[0].x, d[1].x, d[0].y, d[1].y, xv.x, xv.y);
+            mma_bf16_16x8x16(acc, d[0].z, d[1].z, d[0].w, d[1].w, xv.z, xv.w);
+            if (MODE == 2) {
+              mma_bf16_16x8x16(acc2, d[2].x, d[3].x, d[2].y, d[3].y, xv.x, xv.y);
+              mma_bf16_16x8x16(acc2, d[2].z, d[3].z, d[2].w, d[3].w, xv.z, xv.w);
+            }
+          }
+        }
+#pragma unroll
+        for (int u = half * H; u < half * H + H; ++u) {
+          const int kk = k0 + 32 * u + 32 * R;
+          if (kk < k_per_warp) load(ring[u], kk);
+        }
+      }
     }
   }
   // ---- sum the K slices' partial 16 x 8 tiles, epilogue
@@ -159,8 +172,8 @@ skinny_linear_kernel(const __nv_bfloat16* __restrict__ x, int64_t x_stride, cons
     }
   }
   __syncthreads();
-  if (tid < 128 * TILES) {
-    const int tile = tid >> 7, e = tid & 127, r = e >> 3, b = e & 7;       // output feature n + r of token b
+  for (int idx = tid; idx < 128 * TILES; idx += WARPS * 32) {
+    const int tile = idx >> 7, e = idx & 127, r = e >> 3, b = e & 7;       // output feature n + r of token b
     const int n = (blockIdx.x * TILES + tile) * SK_ROWS;
     float s = 0.f, s2 = 0.f;
 #pragma unroll
@@ -195,10 +208,22 @@ static int launch_skinny(const void* x, int64_t xs, const void* w, const void* g
     }
   }
   const int tiles = N / SK_ROWS;
-  kern<<<(tiles + TILES - 1) / TILES, 512, smem, st>>>(static_cast<const __nv_bfloat16*>(x), xs, static_cast<const __nv_bfloat16*>(w),
-                                                       static_cast<const __nv_bfloat16*>(gamma), eps,
-                                                       static_cast<const __nv_bfloat16*>(res), rs,
-                                                       static_cast<__nv_bfloat16*>(y), ys, B, N, K);
+  // programmatic dependent launch: the CTAs may start (and request their first weights) while the previous kernel of the
+  // stream drains; the kernel waits (griddepcontrol.wait) before it touches x / residual / y
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((tiles + TILES - 1) / TILES);
+  cfg.blockDim = dim3(512);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  static const int pdl = getenv("AKI_MMA_SKINNY_PDL") ? atoi(getenv("AKI_MMA_SKINNY_PDL")) : 1;   // 0: plain stream order
+  cfg.numAttrs = pdl ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kern, static_cast<const __nv_bfloat16*>(x), xs, static_cast<const __nv_bfloat16*>(w),
+                     static_cast<const __nv_bfloat16*>(gamma), eps, static_cast<const __nv_bfloat16*>(res), rs,
+                     static_cast<__nv_bfloat16*>(y), ys, B, N, K);
   return check_launch();
 }
 
@@ -216,12 +241,24 @@ extern "C" int aki_mma_skinny_linear(const void* x, int64_t x_stride, const void
   AKI_REQUIRE(x_stride % 8 == 0 && (size_t)8 * (K * 2 + 64) <= 200 * 1024, AKI_ERR_UNSUPPORTED);
   AKI_REQUIRE(aligned16(x) && aligned16(w) && (!rms_weight || aligned16(rms_weight)), AKI_ERR_MISALIGNED);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  // few fat CTAs when there are enough row tiles (every CTA re-reads x from L2): 4 row tiles x 4 K slices per CTA from
-  // 4 x 148 tiles on, else 1 row tile x 16 K slices so that the small projections still fill the SMs
-  const bool fat = (N / SK_ROWS) >= 4 * 128;
+  // one wave of CTAs: the fewest row tiles per CTA (1, 2, 4 or 16; the 16 warps split K 16 / 4 / ... / 1 ways) that keeps
+  // the grid within the SM count -- every CTA stages all of x, and a second, partial wave would cost a whole pass
+  static int sm_count[64] = {};                       // benign race: every writer stores the same value
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) { set_last_cuda_error("cudaGetDevice failed"); return AKI_ERR_CUDA; }
+  if (sm_count[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    sm_count[dev] = n;
+  }
+  const int sms = sm_count[dev];
+  const int tiles = N / SK_ROWS;
+  const int per = tiles <= sms ? 1 : tiles <= 2 * sms ? 2 : tiles <= 4 * sms ? 4 : 16;
 #define AKI_SK(T, M) launch_skinny<T, M>(x, x_stride, w, rms_weight, rms_eps, residual, residual_stride, y, y_stride, B, N, K, st)
-  if (mode == 0) return fat ? AKI_SK(4, 0) : AKI_SK(1, 0);
-  if (mode == 1) return fat ? AKI_SK(4, 1) : AKI_SK(1, 1);
-  return fat ? AKI_SK(4, 2) : AKI_SK(1, 2);
+#define AKI_SK_MODE(M) (per == 1 ? AKI_SK(1, M) : per == 2 ? AKI_SK(2, M) : per == 4 ? AKI_SK(4, M) : AKI_SK(16, M))
+  if (mode == 0) return AKI_SK_MODE(0);
+  if (mode == 1) return AKI_SK_MODE(1);
+  return AKI_SK_MODE(2);
+#undef AKI_SK_MODE
 #undef AKI_SK
 }
