@@ -1,3 +1,3 @@
 cd /root/repo; export PYTHONUNBUFFERED=1
-timeout 900 python -m pytest tests -m gpu -x -q --timeout 150 2>&1 | tail -6
-timeout 300 python tools/decode_time.py 2>&1 | grep -v rope_param | tee gpurun_out/r02_decode_time.txt | tail -12
+AKI_MMA_LIB=build/libaki_trace.so timeout 120 python tools/bwd_trace.py 5 > gpurun_out/bwd_trace_q3.txt 2>&1
+grep -E "(cmp_h0|mma_A|mma_B|drain) it=(4|5|6|7|8|9):" gpurun_out/bwd_trace_q3.txt
