@@ -371,13 +371,16 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
 #ifdef AKI_FWD_TRACE
         const bool tracing = P.trace && (int)blockIdx.x == P.trace_cta && n_it == 0;
 #endif
-        if (nk > 0) {
-          mbar_wait(ROPE ? BAR(Q_READY + buf) : BAR(Q_FULL + 2 * buf + t), (n_it >> 1) & 1);
-        } else {
-          // this tile does not exist in the item: release the Q buffer -- but only once the producer has armed it for
-          // THIS item (a plain arrive on Q_FULL).  An unconditional arrive would let this warp run two items ahead on
-          // tiny items and complete a Q_EMPTY phase with two arrivals of its own while the other tile still reads Q.
-          mbar_wait(BAR(Q_FULL + 2 * buf + t), (n_it >> 1) & 1);
+        // Every barrier this warp ever waits on is waited on for EVERY item, whether or not its tile exists in the item:
+        // a wait that is skipped for one phase lets the warp arrive at the next one a whole phase early, and a parity
+        // wait cannot tell "phase p+1 complete" from "phase p not yet complete" (found by tools/stress.py: with RoPE the
+        // epilogue warps lag by the rotation of the next item's Q, this warp skipped O_FREE on an item without its tile
+        // and overwrote an O accumulator that was still being read).
+        mbar_wait(ROPE ? BAR(Q_READY + buf) : BAR(Q_FULL + 2 * buf + t), (n_it >> 1) & 1);
+        if (nk == 0) {
+          // this tile does not exist in the item: release the Q buffer (the wait above also guarantees that the producer
+          // has armed it for THIS item, so this warp cannot complete a Q_EMPTY phase with two arrivals of its own while
+          // the other tile still reads Q)
           mbar_arrive(BAR(Q_EMPTY + buf));
         }
         auto handle_k = [&](int j) {
@@ -429,6 +432,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
             mbar_arrive(BAR(V_EMPTY + s));
           }
         }
+        if (nk == 0 && n_it > 0) mbar_wait(BAR(O_FREE + t), (n_it - 1) & 1);   // observed every item (see above)
         kc += n_max; vc += n_max;
         mbar_arrive(BAR(ITEM_EMPTY + n_it % SLOTS));
         ++n_it;

@@ -1,3 +1,4 @@
 cd /root/repo; export PYTHONUNBUFFERED=1
-AKI_MMA_LIB=build/libaki_trace.so timeout 120 python tools/bwd_trace.py 5 > gpurun_out/bwd_trace_q3.txt 2>&1
-grep -E "(cmp_h0|mma_A|mma_B|drain) it=(4|5|6|7|8|9):" gpurun_out/bwd_trace_q3.txt
+timeout 200 python tools/stress.py 60 2 2>&1 | grep -v rope_param | tail -4
+AKI_MMA_LIB=$PWD/build/libaki_trap.so timeout 200 python tools/stress.py 45 3 2>&1 | grep -v rope_param | tail -4
+for i in 1 2; do timeout 120 python tools/step_repro.py 8 2>&1 | tail -2; done
