@@ -20,3 +20,14 @@ def test_back_to_back_launches_on_random_geometries(seed):
     tail = "\n".join((r.stdout + r.stderr).splitlines()[-12:])
     assert r.returncode == 0, tail
     assert " 0 bad" in r.stdout, tail
+
+
+@pytest.mark.gpu
+def test_decode_path_is_bit_identical_run_to_run():
+    """tools/stress_decode.py: prefill + graph-replayed fused decode steps (dependent-launch chained linear layers) on random
+    batch sizes and prompt lengths, every scenario twice: identical tokens and caches; every 4th against HF's layers."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "stress_decode.py"), "8", "3"], capture_output=True,
+                       text=True, timeout=110)
+    tail = "\n".join((r.stdout + r.stderr).splitlines()[-12:])
+    assert r.returncode == 0, tail
+    assert " 0 bad" in r.stdout, tail
