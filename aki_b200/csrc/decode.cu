@@ -39,6 +39,8 @@ decode_partial_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* 
                       float* __restrict__ ws_m, float* __restrict__ ws_l, float* __restrict__ ws_acc) {
   const int split = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, s = lane & 3;
+  pdl_wait();          // q and the newest K / V row come from the previous kernel of a decode step
+  pdl_trigger();
   const int len = kv_len[b];
   // keys [kv_start[b], kv_len[b]) are visible: left-padded prompts (padding_side="left" in AKI.generate) keep their pad
   // rows at the front of the cache
@@ -146,6 +148,8 @@ __global__ void __launch_bounds__(DEC_D)
 decode_combine_kernel(const float* __restrict__ ws_m, const float* __restrict__ ws_l, const float* __restrict__ ws_acc,
                       int H, int n_splits, __nv_bfloat16* __restrict__ out) {
   const int h = blockIdx.x, b = blockIdx.y, d = threadIdx.x;
+  pdl_wait();
+  pdl_trigger();
   const size_t base = ((size_t)b * H + h) * n_splits;
   float M = -INFINITY;
   for (int s = 0; s < n_splits; ++s) M = fmaxf(M, ws_m[base + s]);
@@ -186,12 +190,13 @@ extern "C" int aki_mma_decode(const void* q, const void* k_cache, const void* v_
   float* ws_acc = ws_l + (size_t)B * H * n_splits;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const float scale_log2 = scale * 1.4426950408889634f;
-  decode_partial_kernel<<<dim3(n_splits, H, B), DEC_THREADS, 0, st>>>(
-      static_cast<const __nv_bfloat16*>(q), static_cast<const __nv_bfloat16*>(k_cache),
-      static_cast<const __nv_bfloat16*>(v_cache), cache_stride_b, cache_stride_h, kv_len, kv_start, H, scale_log2, n_splits,
-      ws_m, ws_l, ws_acc);
+  launch_pdl(decode_partial_kernel, dim3(n_splits, H, B), dim3(DEC_THREADS), 0, st,
+             static_cast<const __nv_bfloat16*>(q), static_cast<const __nv_bfloat16*>(k_cache),
+             static_cast<const __nv_bfloat16*>(v_cache), cache_stride_b, cache_stride_h, kv_len, kv_start, H, scale_log2,
+             n_splits, ws_m, ws_l, ws_acc);
   int rc = check_launch();
   if (rc != AKI_OK) return rc;
-  decode_combine_kernel<<<dim3(H, B), DEC_D, 0, st>>>(ws_m, ws_l, ws_acc, H, n_splits, static_cast<__nv_bfloat16*>(out));
+  launch_pdl(decode_combine_kernel, dim3(H, B), dim3(DEC_D), 0, st, ws_m, ws_l, ws_acc, H, n_splits,
+             static_cast<__nv_bfloat16*>(out));
   return check_launch();
 }

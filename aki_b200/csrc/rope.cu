@@ -61,6 +61,8 @@ rope_kv_write_kernel(const __nv_bfloat16* __restrict__ qkv, int64_t qkv_stride_b
                      const int32_t* __restrict__ past_len_dev, int t_cap, __nv_bfloat16* __restrict__ q_rot) {
   constexpr int D = 96, HALF = 48;
   const int t = blockIdx.x, b = blockIdx.y;
+  pdl_wait();          // qkv comes from the previous kernel of a decode step
+  pdl_trigger();
   const int past_len = past_len_dev ? past_len_dev[b] : past_len_host;   // device-resident length: CUDA-graph decode
   const float* cr = cos_t + (size_t)b * rope_stride_b + (size_t)t * HALF;
   const float* sr = sin_t + (size_t)b * rope_stride_b + (size_t)t * HALF;
@@ -124,10 +126,10 @@ static int rope_kv_write_impl(const void* qkv, int64_t qkv_stride_b, int64_t qkv
   AKI_REQUIRE(aligned16(qkv) && aligned16(k_cache) && aligned16(cos) && aligned16(sin) &&
                   (!v_cache || aligned16(v_cache)) && (!q_rot || aligned16(q_rot)),
               AKI_ERR_MISALIGNED);
-  rope_kv_write_kernel<<<dim3(T, B), 192, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(qkv), qkv_stride_b, qkv_stride_t, cos, sin, rope_stride_b, T, H,
-      static_cast<__nv_bfloat16*>(k_cache), static_cast<__nv_bfloat16*>(v_cache), cache_stride_b, cache_stride_h,
-      past_len, past_len_dev, t_cap, static_cast<__nv_bfloat16*>(q_rot));
+  launch_pdl(rope_kv_write_kernel, dim3(T, B), dim3(192), 0, static_cast<cudaStream_t>(stream),
+             static_cast<const __nv_bfloat16*>(qkv), qkv_stride_b, qkv_stride_t, cos, sin, rope_stride_b, T, H,
+             static_cast<__nv_bfloat16*>(k_cache), static_cast<__nv_bfloat16*>(v_cache), cache_stride_b, cache_stride_h,
+             past_len, past_len_dev, t_cap, static_cast<__nv_bfloat16*>(q_rot));
   return check_launch();
 }
 

@@ -76,8 +76,8 @@ skinny_linear_kernel(const __nv_bfloat16* __restrict__ x, int64_t x_stride, cons
     for (int u = 0; u < R; ++u)
       if (32 * u < k_per_warp) load(ring[u], 32 * u);
   }
-  asm volatile("griddepcontrol.wait;" ::: "memory");          // x / residual come from the previous kernel
-  asm volatile("griddepcontrol.launch_dependents;");
+  pdl_wait();          // x / residual come from the previous kernel
+  pdl_trigger();
   // ---- stage x (B x K) into shared memory in ONE pass over global memory (every CTA reads all of x: keep it to one
   // pass and to few CTAs); the RMSNorm is then applied in place
   {
@@ -208,22 +208,11 @@ static int launch_skinny(const void* x, int64_t xs, const void* w, const void* g
     }
   }
   const int tiles = N / SK_ROWS;
-  // programmatic dependent launch: the CTAs may start (and request their first weights) while the previous kernel of the
-  // stream drains; the kernel waits (griddepcontrol.wait) before it touches x / residual / y
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((tiles + TILES - 1) / TILES);
-  cfg.blockDim = dim3(512);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr;
-  static const int pdl = getenv("AKI_MMA_SKINNY_PDL") ? atoi(getenv("AKI_MMA_SKINNY_PDL")) : 1;   // 0: plain stream order
-  cfg.numAttrs = pdl ? 1 : 0;
-  cudaLaunchKernelEx(&cfg, kern, static_cast<const __nv_bfloat16*>(x), xs, static_cast<const __nv_bfloat16*>(w),
-                     static_cast<const __nv_bfloat16*>(gamma), eps, static_cast<const __nv_bfloat16*>(res), rs,
-                     static_cast<__nv_bfloat16*>(y), ys, B, N, K);
+  // programmatic dependent launch (api_common.cuh): the CTAs start, and request their first weights, while the previous
+  // kernel of the stream drains; the kernel waits before it touches x / residual / y
+  launch_pdl(kern, dim3((tiles + TILES - 1) / TILES), dim3(512), smem, st, static_cast<const __nv_bfloat16*>(x), xs,
+             static_cast<const __nv_bfloat16*>(w), static_cast<const __nv_bfloat16*>(gamma), eps,
+             static_cast<const __nv_bfloat16*>(res), rs, static_cast<__nv_bfloat16*>(y), ys, B, N, K);
   return check_launch();
 }
 

@@ -1,6 +1,6 @@
 """One forward + backward of the bench workload (T=8192, B=2, 4 image spans) for ncu:
-  ncu --set full --clock-control none --import-source on -k regex:'attn_fwd_sm100|attn_bwd_sm100|bwd_preprocess|dq_finalize|decode_partial|decode_combine|rope_kv_write|fwd_plan' \
-      -c 9 -o gpurun_out/prof python tools/profile_case.py
+  ncu --set full --clock-control none --import-source on -k regex:'attn_fwd_sm100|attn_bwd_sm100|bwd_preprocess|dq_finalize|decode_partial|decode_combine|rope_kv_write|fwd_plan|skinny_linear' \
+      -c 13 -o gpurun_out/prof python tools/profile_case.py
 then tools/ncu_summary.py gpurun_out/prof.ncu-rep profiles/<name>.csv"""
 import os, sys
 import numpy as np, torch
@@ -31,4 +31,15 @@ Bd, Td = 8, 8192
 kc = torch.randn(Bd, H, Td, D, device=dev).to(torch.bfloat16); vc = torch.randn(Bd, H, Td, D, device=dev).to(torch.bfloat16)
 qd = torch.randn(Bd, H, D, device=dev).to(torch.bfloat16)
 ops.decode_op(qd, kc, vc, torch.full((Bd,), Td, dtype=torch.int32, device=dev), Td, D ** -0.5)
+torch.cuda.synchronize()
+# the decode step's linear layers at B=8 tokens (HBM-bound weight streams): qkv (RMSNorm prologue), o_proj (+residual),
+# gate_up (RMSNorm, SwiGLU), down (+residual)
+x = torch.randn(8, 3072, device=dev).to(torch.bfloat16); xi = torch.randn(8, 8192, device=dev).to(torch.bfloat16)
+gamma = torch.ones(3072, device=dev, dtype=torch.bfloat16); res = torch.randn(8, 3072, device=dev).to(torch.bfloat16)
+w_qkv = torch.randn(9216, 3072, device=dev).to(torch.bfloat16); w_o = torch.randn(3072, 3072, device=dev).to(torch.bfloat16)
+w_gu = torch.randn(16384, 3072, device=dev).to(torch.bfloat16); w_d = torch.randn(3072, 8192, device=dev).to(torch.bfloat16)
+ops.skinny_linear(x, w_qkv, gamma, 1e-5)
+ops.skinny_linear(x, w_o, residual=res)
+ops.skinny_linear(x, w_gu, gamma, 1e-5, swiglu=True)
+ops.skinny_linear(xi, w_d, residual=res)
 torch.cuda.synchronize()
