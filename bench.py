@@ -318,6 +318,7 @@ def prefill_section(dev, rank, world, steps, warmup, longctx=None):
     barrier()
     dec_ms = a.elapsed_time(b_) / (n_dec - 1)
     kv_bytes = 2 * B * 32 * (T + n_dec / 2) * 96 * 2 * 32          # K+V read per step, all layers
+    w_bytes = 2.0 * (32 * (9216 * 3072 + 3072 * 3072 + 16384 * 3072 + 3072 * 8192) + 32064 * 3072)   # bf16 weights streamed once per step
     stats = torch.tensor([res["resident"], res["e2e"], dec_ms, dec_eager_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(stats, op=dist.ReduceOp.MAX)
@@ -331,10 +332,15 @@ def prefill_section(dev, rank, world, steps, warmup, longctx=None):
             "prefill_e2e_tokens_per_s": world * B * T / (e_ms * 1e-3), "prefill_e2e_ms": e_ms,
             "e2e_h2d_bytes": int(host_ids.numel() * 8 * 2 + host_vis.numel() * 2), "e2e_d2h_bytes": B * 8,
             "decode_tokens_per_s": world * B / (d_ms * 1e-3), "decode_ms_per_step": d_ms,
-            "decode_note": "greedy step for all 32 layers replayed from one CUDA graph",
+            "decode_note": "greedy step for all 32 layers replayed from one CUDA graph; per layer 7 kernels of this "
+                           "library chained by programmatic dependent launch (aki_mma_skinny_linear x4 with RMSNorm / "
+                           "residual / SwiGLU fused, rope_kv_write, decode attention + combine)",
             "decode_eager_ms_per_step": de_ms,
             "decode_attn_kv_bytes_per_step": kv_bytes,
-            "decode_attn_kv_gbs_floor": kv_bytes / (d_ms * 1e-3) / 1e9}
+            "decode_attn_kv_gbs_floor": kv_bytes / (d_ms * 1e-3) / 1e9,
+            "decode_weight_bytes_per_step": w_bytes,
+            "decode_hbm_gbs": (kv_bytes + w_bytes) / (d_ms * 1e-3) / 1e9,
+            "decode_hbm_floor_ms": (kv_bytes + w_bytes) / (peaks()[0]["hbm_gbs"] * 1e9) * 1e3}
 
 
 # ------------------------------------------------------------------------------------------------ SFT step (config 4)
