@@ -56,13 +56,37 @@ class AkiPhi3Runner(nn.Module):
                 h = h[0]
         return self.lm.model.norm(h)
 
+    def _run_layers_fused(self, h, cos, sin, segs, cache):
+        """Inference-only pass through the decoder layers with the element-wise work fused ("next" row f-1 of SURVEY 8):
+        residual add + RMSNorm in one kernel, SiLU gate in one kernel (ops.add_rmsnorm / ops.swiglu) instead of the ~12
+        ATen kernels per layer of Phi3DecoderLayer.forward (modeling_phi3.py:295-335), which took 42 % of the prefill's
+        kernel time (tools/prefill_profile.py).  The GEMMs stay cuBLAS; attention is the drop-in module.  Same rounding
+        points as the eager layers.  Returns the final-norm output."""
+        F = torch.nn.functional
+        eps = self.config.rms_norm_eps
+        layers = self.lm.model.layers
+        res, x = ops.add_rmsnorm(h, layers[0].input_layernorm.weight, eps)        # res is the caller's tensor: not ours yet
+        ours = False
+        for li, layer in enumerate(layers):
+            a = layer.self_attn(x, position_embeddings=None, attention_mask=None, past_key_values=cache,
+                                mma_segments=segs, mma_rope=(cos, sin))[0]
+            res, x = ops.add_rmsnorm(a, layer.post_attention_layernorm.weight, eps, residual=res, inplace_residual=ours)
+            ours = True
+            d = F.linear(ops.swiglu(F.linear(x, layer.mlp.gate_up_proj.weight)), layer.mlp.down_proj.weight)
+            nxt = layers[li + 1].input_layernorm if li + 1 < len(layers) else self.lm.model.norm
+            res, x = ops.add_rmsnorm(d, nxt.weight, eps, residual=res)
+        return x
+
     @torch.no_grad()
     def prefill(self, inputs_embeds: torch.Tensor, segs: Optional[ops.MMASegments], cache: Optional[AkiKVCache],
-                last_only: bool = True):
-        """inputs_embeds (B,T,3072); positions arange(T) as AKI.generate passes them (aki.py:184-191)."""
+                last_only: bool = True, fused: bool = True):
+        """inputs_embeds (B,T,3072); positions arange(T) as AKI.generate passes them (aki.py:184-191).  fused=False runs
+        HF's Phi3DecoderLayer objects (the parity reference of the fused pass)."""
         B, T, _ = inputs_embeds.shape
         cos, sin = self.rope.tables(torch.arange(T, device=inputs_embeds.device)[None], max_position=T - 1)
-        h = self._run_layers(inputs_embeds, cos, sin, segs, cache)
+        fused = fused and inputs_embeds.dtype == torch.bfloat16 and inputs_embeds.shape[-1] <= 4096
+        h = (self._run_layers_fused if fused else self._run_layers)(inputs_embeds.contiguous() if fused else inputs_embeds,
+                                                                      cos, sin, segs, cache)
         return self.lm.lm_head(h[:, -1:] if last_only else h)
 
     @torch.no_grad()

@@ -473,3 +473,36 @@ def skinny_linear(x: torch.Tensor, weight: torch.Tensor, rms_weight: _OT = None,
                                     residual.stride(0) if residual is not None else 0, _ptr(out), out.stride(0), B, N, K,
                                     mode, _stream()), "aki_mma_skinny_linear")
     return out
+
+
+def add_rmsnorm(x: torch.Tensor, weight: torch.Tensor, eps: float, residual: _OT = None, inplace_residual: bool = True):
+    """(h, y) with h = residual + x (h = x when residual is None) and y = Phi3RMSNorm(h), for (..., K) bf16 rows at prefill
+    size: one pass over HBM instead of the ATen kernels of the eager residual add + Phi3RMSNorm.forward
+    (modeling_phi3.py:49-64, 317-335).  With inplace_residual the sum overwrites `residual`."""
+    _require_cuda(x, weight, residual)
+    K = x.shape[-1]
+    x2 = x.reshape(-1, K)
+    assert x2.dtype == torch.bfloat16 and x2.stride(1) == 1 and weight.dtype == torch.bfloat16 and weight.is_contiguous()
+    y = torch.empty(x2.shape, dtype=torch.bfloat16, device=x.device)
+    h = None
+    r2 = None
+    if residual is not None:
+        r2 = residual.reshape(-1, K)
+        assert r2.shape == x2.shape and r2.dtype == torch.bfloat16 and r2.stride(1) == 1
+        h = r2 if (inplace_residual and r2.data_ptr() == residual.data_ptr()) else torch.empty_like(y)
+    check(lib.aki_mma_add_rmsnorm(_ptr(x2), x2.stride(0), _ptr(r2), r2.stride(0) if r2 is not None else 0, _ptr(weight),
+                                  float(eps), _ptr(h), h.stride(0) if h is not None else 0, _ptr(y), y.stride(0),
+                                  x2.shape[0], K, _stream()), "aki_mma_add_rmsnorm")
+    return (h.view(x.shape) if h is not None else x), y.view(x.shape)
+
+
+def swiglu(gate_up: torch.Tensor) -> torch.Tensor:
+    """up * silu(gate) for gate_up (..., 2N) bf16 = [gate | up] as Phi3MLP's gate_up_proj produces it (modeling_phi3.py:
+    295-306): one pass instead of chunk + silu + mul on strided views."""
+    _require_cuda(gate_up)
+    N = gate_up.shape[-1] // 2
+    g2 = gate_up.reshape(-1, 2 * N)
+    assert g2.dtype == torch.bfloat16 and g2.stride(1) == 1
+    y = torch.empty(g2.shape[0], N, dtype=torch.bfloat16, device=gate_up.device)
+    check(lib.aki_mma_swiglu(_ptr(g2), g2.stride(0), _ptr(y), y.stride(0), g2.shape[0], N, _stream()), "aki_mma_swiglu")
+    return y.view(*gate_up.shape[:-1], N)

@@ -223,6 +223,20 @@ int aki_mma_skinny_linear(const void* x, int64_t x_stride, const void* w, const 
                           const void* residual, int64_t residual_stride, void* y, int64_t y_stride, int B, int N, int K,
                           int mode, aki_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------------
+ * (7) Element-wise work of the decoder layer at PREFILL size (ABI 2) -- one pass over HBM each, replacing
+ *     the ATen kernels of Phi3RMSNorm.forward, the residual adds of Phi3DecoderLayer.forward and the SiLU gate of
+ *     Phi3MLP.forward (transformers/models/phi3/modeling_phi3.py:49-64, 295-306, 317-335); the GEMMs between them stay
+ *     with the caller.  bf16 in / out, HF's rounding points; strides in elements (rows of M tokens).
+ *     aki_mma_add_rmsnorm: h = residual + x (skipped when residual is NULL; written to h_out when non-NULL, h_out may
+ *     alias residual), y = weight * (h * rsqrt(mean(h^2) + eps)).bf16.  K % 256 == 0, K <= 4096.
+ *     aki_mma_swiglu: y (M,N) = up * silu(gate) with gate = gate_up[:, :N], up = gate_up[:, N:2N].  N % 8 == 0. */
+int aki_mma_add_rmsnorm(const void* x, int64_t x_stride, const void* residual, int64_t residual_stride, const void* weight,
+                        float eps, void* h_out, int64_t h_stride, void* y, int64_t y_stride, int M, int K,
+                        aki_stream_t stream);
+int aki_mma_swiglu(const void* gate_up, int64_t gate_up_stride, void* y, int64_t y_stride, int M, int N,
+                   aki_stream_t stream);
+
 /* Measurement hook (bench.py roofline): the NEXT aki_mma_attn_fwd / aki_mma_attn_bwd call of this host thread
  * records `ev_begin` right before and `ev_end` right after its tcgen05 attention kernel on the call's stream (the
  * preprocess / memset / finalize launches of the backward stay outside), then the hook clears itself.

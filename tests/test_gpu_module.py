@@ -570,3 +570,71 @@ def test_fused_decode_step_matches_the_hf_layer_path():
         a_, b_ = caches[0].k[l][:, :, :n].float(), caches[1].k[l][:, :, :n].float()
         assert float((a_ - b_).abs().max()) < 3e-2 * max(1.0, float(a_.abs().max()))
         assert torch.equal(caches[1].k[l][:, :, :n], caches[2].k[l][:, :, :n])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("M,K,with_res", [(1, 3072, False), (37, 3072, True), (5240, 3072, True), (64, 1024, True),
+                                          (9, 4096, False)])
+def test_add_rmsnorm_matches_the_eager_layer_code(M, K, with_res):
+    """aki_mma_add_rmsnorm vs `residual + hidden_states` followed by Phi3RMSNorm.forward (modeling_phi3.py:49-64, 317-335)."""
+    from transformers.models.phi3.modeling_phi3 import Phi3RMSNorm
+    from aki_b200 import ops
+    dev_ = torch.device("cuda", 0)
+    g = torch.Generator(device=dev_).manual_seed(M + K)
+    x = torch.randn(M, K, generator=g, device=dev_).to(torch.bfloat16)
+    res = (torch.randn(M, K, generator=g, device=dev_) * 3).to(torch.bfloat16) if with_res else None
+    norm = Phi3RMSNorm(K, eps=1e-5).to(dev_).to(torch.bfloat16)
+    with torch.no_grad():
+        norm.weight.copy_((1 + 0.1 * torch.randn(K, generator=g, device=dev_)).to(torch.bfloat16))
+        h_ref = res + x if with_res else x
+        y_ref = norm(h_ref)
+    res_in = res.clone() if with_res else None
+    h, y = ops.add_rmsnorm(x, norm.weight, 1e-5, residual=res_in)
+    assert torch.equal(h, h_ref)
+    if with_res:
+        assert h.data_ptr() == res_in.data_ptr()            # the sum overwrote the residual stream in place
+    # the row sum of squares is accumulated in a different order: allow one bf16 ulp on a handful of elements
+    d = (y.float() - y_ref.float()).abs()
+    assert float(d.max()) <= 2 ** -7 * float(y_ref.float().abs().max())
+    assert float((d > 0).float().mean()) < 0.01
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("M,N", [(1, 8192), (77, 8192), (5240, 8192), (16, 64)])
+def test_swiglu_matches_phi3_mlp(M, N):
+    """aki_mma_swiglu vs the middle of Phi3MLP.forward: gate, up = gate_up.chunk(2); up * silu(gate) (modeling_phi3.py:295-306)."""
+    from aki_b200 import ops
+    dev_ = torch.device("cuda", 0)
+    gu = (torch.randn(M, 2 * N, generator=torch.Generator(device=dev_).manual_seed(N + M), device=dev_) * 2).to(torch.bfloat16)
+    gate, up = gu.chunk(2, dim=-1)
+    ref = up * torch.nn.functional.silu(gate)
+    got = ops.swiglu(gu)
+    d = (got.float() - ref.float()).abs()
+    assert float(d.max()) <= 2 ** -7 * float(ref.float().abs().max())
+    assert float((d > 0).float().mean()) < 0.01
+
+
+@pytest.mark.gpu
+def test_fused_prefill_matches_the_hf_layer_path():
+    """SURVEY 8 f-1 for prefill: the pass with fused residual + RMSNorm / SiLU-gate kernels against the pass through HF's
+    Phi3DecoderLayer objects -- logits, caches, with image segments and a ragged batch; the caller's embeddings stay intact."""
+    from aki_b200 import ops
+    from aki_b200.model import AkiPhi3Runner, phi35_mini_config
+    dev_ = torch.device("cuda", 0)
+    runner = AkiPhi3Runner(phi35_mini_config(num_layers=3), device=dev_, seed=0)
+    B, L, N = 3, 200, 144
+    lang, am = Hp.make_prompt(B, L, N, 2, pad_right=31)
+    segs = ops.build_segments(torch.from_numpy(lang).to(dev_), torch.from_numpy(am).to(dev_), N, Hp.MEDIA_ID)
+    T = segs.T
+    emb = (torch.randn(B, T, 3072, generator=torch.Generator().manual_seed(5)) * 0.05).to(torch.bfloat16).to(dev_)
+    keep = emb.clone()
+    c_ref, c_fused = runner.new_cache(B, T + 4), runner.new_cache(B, T + 4)
+    ref = runner.prefill(emb, segs, c_ref, last_only=False, fused=False).float()
+    got = runner.prefill(emb, segs, c_fused, last_only=False, fused=True).float()
+    assert torch.equal(emb, keep)
+    valid = torch.arange(T, device=dev_)[None] < segs.seq_len[:, None]
+    err = float((got - ref)[valid].abs().max())
+    assert err < 3e-2 * max(1.0, float(ref[valid].abs().max())), err
+    for l in range(3):
+        a_, b_ = c_ref.k[l][:, :, :T].float(), c_fused.k[l][:, :, :T].float()
+        assert float((a_ - b_).abs().max()) < 3e-2 * max(1.0, float(a_.abs().max()))

@@ -1,5 +1,4 @@
 cd /root/repo; export PYTHONUNBUFFERED=1
-timeout 400 python -m pytest tests/test_gpu_module.py tests/test_gpu_soak.py -m gpu -x -q --timeout 150 2>&1 | tail -3
-timeout 200 python tools/stress_decode.py 30 7 2>&1 | grep -v rope_param | tail -3
-timeout 300 python tools/decode_time.py 2>&1 | grep -v rope_param | grep decode
-AKI_MMA_PDL=0 timeout 300 python tools/decode_time.py 2>&1 | grep -v rope_param | grep "fused" | sed 's/^/PDL=0 /'
+timeout 300 python -m pytest tests/test_gpu_module.py -m gpu -q --timeout 150 -k "add_rmsnorm or swiglu or fused_prefill or fused_decode" 2>&1 | tail -12
+timeout 200 python tools/prefill_profile.py 8 655 2>&1 | grep -v rope_param | grep -A8 "ms of kernels"
+timeout 200 python tools/prefill_profile.py 2 8192 2>&1 | grep -v rope_param | grep -A10 "ms of kernels"

@@ -6,7 +6,7 @@ name=$1; shift
 root=$(cd "$(dirname "$0")/.." && pwd)
 obj=$root/build/obj_$name
 mkdir -p $obj
-for f in api meta rope decode skinny_linear attn_simt attn_fwd_sm100 attn_bwd_sm100; do
+for f in api meta rope decode skinny_linear layer_elementwise attn_simt attn_fwd_sm100 attn_bwd_sm100; do
   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC --expt-relaxed-constexpr "$@" \
     -c $root/aki_b200/csrc/$f.cu -o $obj/$f.o &
 done
