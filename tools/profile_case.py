@@ -1,6 +1,6 @@
 """One forward + backward of the bench workload (T=8192, B=2, 4 image spans) for ncu:
-  ncu --set full --clock-control none --import-source on -k regex:'attn_fwd_sm100|attn_bwd_sm100|bwd_preprocess|dq_finalize|decode_partial|decode_combine|rope_kv_write|fwd_plan|skinny_linear' \
-      -c 13 -o gpurun_out/prof python tools/profile_case.py
+  ncu --set full --clock-control none --import-source on -k regex:'attn_fwd_sm100|attn_bwd_sm100|bwd_preprocess|dq_finalize|decode_partial|decode_combine|rope_kv_write|fwd_plan|skinny_linear|add_rmsnorm|swiglu' \
+      -c 15 -o gpurun_out/prof python tools/profile_case.py
 then tools/ncu_summary.py gpurun_out/prof.ncu-rep profiles/<name>.csv"""
 import os, sys
 import numpy as np, torch
@@ -42,4 +42,10 @@ ops.skinny_linear(x, w_qkv, gamma, 1e-5)
 ops.skinny_linear(x, w_o, residual=res)
 ops.skinny_linear(x, w_gu, gamma, 1e-5, swiglu=True)
 ops.skinny_linear(xi, w_d, residual=res)
+torch.cuda.synchronize()
+# the prefill-size element-wise kernels of the decoder layer (B=8, T=655: 5240 tokens)
+xm = torch.randn(5240, 3072, device=dev).to(torch.bfloat16); rm = torch.randn(5240, 3072, device=dev).to(torch.bfloat16)
+gu = torch.randn(5240, 16384, device=dev).to(torch.bfloat16)
+ops.add_rmsnorm(xm, gamma, 1e-5, residual=rm)
+ops.swiglu(gu)
 torch.cuda.synchronize()
