@@ -638,3 +638,45 @@ def test_fused_prefill_matches_the_hf_layer_path():
     for l in range(3):
         a_, b_ = c_ref.k[l][:, :, :T].float(), c_fused.k[l][:, :, :T].float()
         assert float((a_ - b_).abs().max()) < 3e-2 * max(1.0, float(a_.abs().max()))
+
+
+@pytest.mark.gpu
+def test_hf_generate_with_fused_elementwise_layers():
+    """aki_b200.fuse_phi3_elementwise on a Phi3ForCausalLM driven by HF generate(): same greedy tokens and logits as the
+    same model without the swap (module-level f-1 for callers that keep HF's layer objects); the swap steps aside under
+    autograd (training), and unfuse restores the original forwards."""
+    import copy
+    import aki_b200
+    from aki_b200 import ops
+    cfg, model = _small_lm(seed=4)
+    aki_b200.replace_phi3_attention(model)
+    fused = copy.deepcopy(model)
+    n_mod = aki_b200.fuse_phi3_elementwise(fused)
+    assert n_mod == 2 * 2 + 1 + 2                        # per layer two norms + one MLP, plus the final norm
+    assert aki_b200.fuse_phi3_elementwise(fused) == 0    # idempotent
+    B, L, N, n_new = 2, 90, 32, 6
+    lang, am = Hp.make_prompt(B, L, N, 2)
+    segs = ops.build_segments(torch.from_numpy(lang).to(dev), torch.from_numpy(am).to(dev), N, Hp.MEDIA_ID)
+    T = segs.T
+    torch.manual_seed(11)
+    embeds = (torch.randn(B, T, 3072, device=dev) * 0.5).to(torch.bfloat16)
+    outs = []
+    for m in (model, fused):
+        cache = aki_b200.AkiKVCache(2, B, 32, 96, t_cap=T + n_new + 1, device=dev)
+        with aki_b200.mma_context(segs):
+            outs.append(m.generate(inputs_embeds=embeds, attention_mask=segs.spliced_mask_2d(), max_new_tokens=n_new,
+                                   do_sample=False, use_cache=True, return_dict_in_generate=True, output_logits=True,
+                                   pad_token_id=0, past_key_values=cache))
+    ref, got = (torch.stack(o.logits, 1).float() for o in outs)
+    scale = float(ref.abs().max())
+    assert float((got - ref).abs().max()) < 0.03 * max(scale, 1.0)
+    top2 = ref[:, 0].topk(2, dim=-1).values                 # first generated token: same prompt state in both runs
+    clear = (top2[..., 0] - top2[..., 1]) > 0.05 * scale
+    assert torch.equal(ref[:, 0].argmax(-1)[clear], got[:, 0].argmax(-1)[clear])
+    # under autograd the original forwards run: gradients flow as before
+    x = (torch.randn(1, 8, 3072, device=dev) * 0.1).to(torch.bfloat16).requires_grad_(True)
+    y = fused.model.layers[0].mlp(fused.model.layers[0].post_attention_layernorm(x))
+    y.float().sum().backward()
+    assert x.grad is not None and torch.isfinite(x.grad.float()).all()
+    assert aki_b200.unfuse_phi3_elementwise(fused) == n_mod
+    assert not hasattr(fused.model.norm, "_aki_orig_forward")

@@ -1,2 +1,2 @@
 cd /root/repo; export PYTHONUNBUFFERED=1
-timeout 300 python tools/sft_profile.py 32 2>&1 | grep -v rope_param | grep -A32 "ms of kernels"
+timeout 300 python -m pytest tests/test_gpu_module.py -m gpu -q --timeout 150 -k "fused_elementwise or hf_generate" 2>&1 | tail -8
