@@ -242,6 +242,7 @@ class AkiPhi3SFT(nn.Module):
             self.lm = Phi3ForCausalLM(config)           # fp32 master weights
         replace_phi3_attention(self.lm)
         self.config = config
+        self.fused_ce = True
         rp = config.rope_parameters
         self.rope = LongRope(96, rp["rope_theta"], rp["short_factor"], rp["long_factor"], config.max_position_embeddings,
                              rp["original_max_position_embeddings"], device=device)
@@ -257,6 +258,9 @@ class AkiPhi3SFT(nn.Module):
                 if isinstance(h, tuple):
                     h = h[0]
             logits = self.lm.lm_head(self.lm.model.norm(h))
+        if self.fused_ce and logits.dtype == torch.bfloat16 and logits.shape[-1] % 8 == 0:
+            # one kernel forward, one backward, no fp32 copy of the (B,T,32064) logits
+            return ops.cross_entropy_shifted(logits, labels.contiguous())
         logits = logits[:, :-1].float()
         return nn.functional.cross_entropy(logits.reshape(-1, logits.shape[-1]), labels[:, 1:].reshape(-1),
                                            ignore_index=-100)

@@ -506,3 +506,40 @@ def swiglu(gate_up: torch.Tensor) -> torch.Tensor:
     y = torch.empty(g2.shape[0], N, dtype=torch.bfloat16, device=gate_up.device)
     check(lib.aki_mma_swiglu(_ptr(g2), g2.stride(0), _ptr(y), y.stride(0), g2.shape[0], N, _stream()), "aki_mma_swiglu")
     return y.view(*gate_up.shape[:-1], N)
+
+
+class _ShiftedCrossEntropy(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, labels, ignore_index):
+        B, T, V = logits.shape
+        row_loss = torch.empty(B, T, dtype=torch.float32, device=logits.device)
+        row_lse = torch.empty_like(row_loss)
+        check(lib.aki_mma_cross_entropy_fwd(_ptr(logits), logits.stride(0), logits.stride(1), _ptr(labels), labels.stride(0),
+                                            B, T, V, int(ignore_index), _ptr(row_loss), _ptr(row_lse), _stream()),
+              "aki_mma_cross_entropy_fwd")
+        tgt = labels[:, 1:]
+        n_valid = ((tgt != ignore_index) & (tgt >= 0) & (tgt < V)).sum().clamp_(min=1).to(torch.float32)
+        ctx.save_for_backward(logits, labels, row_lse, n_valid)
+        ctx.ignore_index = int(ignore_index)
+        return row_loss.sum() / n_valid
+
+    @staticmethod
+    def backward(ctx, g):
+        logits, labels, row_lse, n_valid = ctx.saved_tensors
+        B, T, V = logits.shape
+        scale = (g.to(torch.float32) / n_valid).reshape(1).contiguous()
+        d = torch.empty(B, T, V, dtype=torch.bfloat16, device=logits.device)
+        check(lib.aki_mma_cross_entropy_bwd(_ptr(logits), logits.stride(0), logits.stride(1), _ptr(labels), labels.stride(0),
+                                            B, T, V, ctx.ignore_index, _ptr(row_lse), _ptr(scale), _ptr(d), d.stride(0),
+                                            d.stride(1), _stream()), "aki_mma_cross_entropy_bwd")
+        return d, None, None
+
+
+def cross_entropy_shifted(logits: torch.Tensor, labels: torch.Tensor, ignore_index: int = -100) -> torch.Tensor:
+    """Mean next-token cross-entropy of logits (B,T,V) bf16 against labels (B,T) int64 (row t pairs with labels[:, t+1];
+    ignore_index rows skipped) = the loss Phi3ForCausalLM(labels=...) returns to AKI.forward (aki.py:125-130), without the
+    fp32 copy of the logits; differentiable w.r.t. logits (gradient in bf16)."""
+    _require_cuda(logits, labels)
+    assert logits.dim() == 3 and logits.dtype == torch.bfloat16 and logits.stride(2) == 1
+    assert labels.shape == logits.shape[:2] and labels.dtype == torch.int64 and labels.stride(1) == 1
+    return _ShiftedCrossEntropy.apply(logits, labels, ignore_index)

@@ -237,6 +237,22 @@ int aki_mma_add_rmsnorm(const void* x, int64_t x_stride, const void* residual, i
 int aki_mma_swiglu(const void* gate_up, int64_t gate_up_stride, void* y, int64_t y_stride, int M, int N,
                    aki_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------------
+ * (8) Next-token cross-entropy over the LM head's logits (ABI 2) -- the loss Phi3ForCausalLM(labels=...)
+ *     hands AKI.forward (codes/open_flamingo/src/aki.py:125-130; HF: logits.float(), shift by one, CrossEntropyLoss with
+ *     ignore_index): logits (B,T,V) bf16 (strides in elements), labels (B,T) int64.  Row (b,t) pairs with
+ *     labels[b,t+1]; rows whose target is ignore_index (or t = T-1) contribute 0.
+ *     fwd: row_loss, row_lse (B,T) fp32 = logsumexp - target logit, computed in fp32 from the bf16 logits.
+ *     bwd: dlogits (B,T,V) bf16 = (softmax - onehot) * *scale_dev (device scalar: dloss / number of valid targets).
+ *     V % 8 == 0.  HBM-bound: V*2 bytes per row forward, 2*V*2 backward. */
+int aki_mma_cross_entropy_fwd(const void* logits, int64_t stride_b, int64_t stride_t, const int64_t* labels,
+                              int64_t labels_stride_b, int B, int T, int V, long long ignore_index, float* row_loss,
+                              float* row_lse, aki_stream_t stream);
+int aki_mma_cross_entropy_bwd(const void* logits, int64_t stride_b, int64_t stride_t, const int64_t* labels,
+                              int64_t labels_stride_b, int B, int T, int V, long long ignore_index, const float* row_lse,
+                              const float* scale_dev, void* dlogits, int64_t d_stride_b, int64_t d_stride_t,
+                              aki_stream_t stream);
+
 /* Measurement hook (bench.py roofline): the NEXT aki_mma_attn_fwd / aki_mma_attn_bwd call of this host thread
  * records `ev_begin` right before and `ev_end` right after its tcgen05 attention kernel on the call's stream (the
  * preprocess / memset / finalize launches of the backward stay outside), then the hook clears itself.

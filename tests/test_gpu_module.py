@@ -680,3 +680,28 @@ def test_hf_generate_with_fused_elementwise_layers():
     assert x.grad is not None and torch.isfinite(x.grad.float()).all()
     assert aki_b200.unfuse_phi3_elementwise(fused) == n_mod
     assert not hasattr(fused.model.norm, "_aki_orig_forward")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,T,V", [(2, 33, 512), (4, 656, 32064), (1, 5, 40)])
+def test_fused_cross_entropy_matches_hf_loss(B, T, V):
+    """aki_mma_cross_entropy_{fwd,bwd} vs what Phi3ForCausalLM(labels=...) computes (logits.float(), shift, CrossEntropyLoss
+    with ignore_index=-100; the loss AKI.forward returns, aki.py:125-130): loss and the bf16 gradient w.r.t. the logits."""
+    from aki_b200 import ops
+    g = torch.Generator(device=dev).manual_seed(V + T)
+    logits = (torch.randn(B, T, V, generator=g, device=dev) * 3).to(torch.bfloat16)
+    labels = torch.randint(0, V, (B, T), generator=g, device=dev)
+    labels[:, : T // 3] = -100                                  # prompt part ignored, as the SFT collate does
+    labels[0, -1] = -100
+    a = logits.clone().requires_grad_(True)
+    ref = torch.nn.functional.cross_entropy(a[:, :-1].float().reshape(-1, V), labels[:, 1:].reshape(-1), ignore_index=-100)
+    (ref * 1.7).backward()
+    b = logits.clone().requires_grad_(True)
+    got = ops.cross_entropy_shifted(b, labels)
+    (got * 1.7).backward()
+    assert abs(float(got) - float(ref)) < 1e-5 * max(1.0, abs(float(ref)))
+    assert b.grad.dtype == torch.bfloat16 and b.grad.shape == a.grad.shape
+    d = (b.grad.float() - a.grad.float()).abs()
+    assert float(d.max()) <= 2 ** -7 * float(a.grad.float().abs().max()) + 1e-12     # one bf16 ulp of the largest entry
+    assert torch.equal(b.grad[:, -1], torch.zeros_like(b.grad[:, -1]))              # the last position has no target
+    assert torch.equal(b.grad[:, : T // 3 - 1], torch.zeros_like(b.grad[:, : T // 3 - 1]))
