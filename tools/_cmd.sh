@@ -1,3 +1,9 @@
 cd /root/repo; export PYTHONUNBUFFERED=1
-timeout 300 python -m pytest tests/test_gpu_module.py -m gpu -q --timeout 150 -k "cross_entropy or sft_loss" 2>&1 | tail -8
-timeout 300 python bench.py --workload sft --steps 8 --warmup 3 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d.get('value'), d.get('ms_per_step'), d.get('sft',{}).get('step_ms'))"
+run() { echo "== $*"; env "$@" timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus 2 --workload sft --steps 6 --warmup 3 2>/dev/null | python -c "
+import sys,json
+d=json.loads(sys.stdin.read()); s=d.get('sft',d)
+print({k:round(s[k],2) for k in ('step_ms','step_ms_without_allreduce','exposed_allreduce_ms','nccl_allreduce_busbw_gbs_1gib') if k in s})"; }
+run A=1
+run NCCL_MAX_NCHANNELS=4
+run NCCL_MAX_NCHANNELS=8
+run NCCL_MAX_NCHANNELS=16 AKI_DDP_BUCKET_MB=64
