@@ -20,3 +20,23 @@ ops.attn_bwd_raw(d_o, q, k, v, o, lse, None, None, meta, D ** -0.5, dq, dk, dv)
 torch.cuda.synchronize()
 os_, lse_s = ops.attn_fwd_raw(q, k, v, None, None, meta, D ** -0.5, simt=True)
 print("ran", B, H, T, "max|o - o_simt|", float((o.float() - os_.float()).abs().max()), "max|dq|", float(dq.float().abs().max()))
+# the HBM-bound kernels of the decode / prefill paths on small shapes (odd row counts: every bounds check is exercised)
+import aki_b200
+rope = aki_b200.LongRope(device=dev)
+cos, sin = rope.tables(torch.arange(T, device=dev)[None], max_position=T - 1)
+o2, _ = ops.attn_fwd_raw(q, k, v, cos, sin, meta, D ** -0.5)                       # RoPE instantiation of the forward
+x = torch.randn(3, 1024, device=dev).to(torch.bfloat16); w = torch.randn(48, 1024, device=dev).to(torch.bfloat16)
+gam = torch.ones(1024, device=dev, dtype=torch.bfloat16); res = torch.randn(3, 48, device=dev).to(torch.bfloat16)
+ops.skinny_linear(x, w, gam, 1e-5); ops.skinny_linear(x, w, residual=res)
+ops.skinny_linear(x, torch.randn(96, 1024, device=dev).to(torch.bfloat16), swiglu=True)
+xm = torch.randn(13, 1024, device=dev).to(torch.bfloat16)
+ops.add_rmsnorm(xm, gam, 1e-5, residual=torch.randn(13, 1024, device=dev).to(torch.bfloat16))
+ops.swiglu(torch.randn(13, 2 * 72, device=dev).to(torch.bfloat16))
+lg = torch.randn(2, 7, 40, device=dev).to(torch.bfloat16).requires_grad_(True)
+lab = torch.randint(0, 40, (2, 7), device=dev); lab[:, :2] = -100
+ops.cross_entropy_shifted(lg, lab).backward()
+kc = torch.randn(2, H, 40, D, device=dev).to(torch.bfloat16); vc = torch.randn_like(kc)
+ops.decode_op(torch.randn(2, H, D, device=dev).to(torch.bfloat16), kc, vc, torch.tensor([33, 40], dtype=torch.int32, device=dev), 40,
+              D ** -0.5, torch.tensor([5, 0], dtype=torch.int32, device=dev))
+torch.cuda.synchronize()
+print("helper kernels ran")
