@@ -59,6 +59,46 @@ def test_argument_validation_without_gpu(lib):
     assert L.aki_mma_rope_kv_write(None, 0, 0, None, None, 0, 1, 1, 32, 96, None, None, 0, 0, 0, 1, None, None) == -1
 
 
+def test_layer_kernel_argument_validation_without_gpu(lib):
+    """Status codes of the f-1 / f-2 entry points (no launch happens: every call fails validation first)."""
+    L = lib.lib
+    assert L.aki_mma_skinny_linear(None, 0, None, None, 1e-5, None, 0, None, 0, 1, 16, 1024, 0, None) == -1
+    buf = (C.c_int64 * 64)()
+    assert L.aki_mma_skinny_linear(buf, 1024, buf, None, 1e-5, None, 0, buf, 16, 9, 16, 1024, 0, None) == -2      # B > 8
+    assert L.aki_mma_skinny_linear(buf, 1024, buf, None, 1e-5, None, 0, buf, 16, 1, 24, 1024, 0, None) == -3      # N % 16
+    assert L.aki_mma_skinny_linear(buf, 1024, buf, None, 1e-5, None, 0, buf, 16, 1, 16, 1000, 0, None) == -3      # K % 1024
+    assert L.aki_mma_add_rmsnorm(None, 0, None, 0, None, 1e-5, None, 0, None, 0, 1, 1024, None) == -1
+    assert L.aki_mma_add_rmsnorm(buf, 1024, None, 0, buf, 1e-5, None, 0, buf, 1024, 0, 1024, None) == -2          # M = 0
+    assert L.aki_mma_add_rmsnorm(buf, 1024, None, 0, buf, 1e-5, None, 0, buf, 1024, 1, 8192, None) == -3          # K > 4096
+    assert L.aki_mma_add_rmsnorm(buf, 1024, None, 0, buf, 1e-5, buf, 1024, buf, 1024, 1, 1024, None) == -2        # h_out without residual
+    assert L.aki_mma_swiglu(None, 0, None, 0, 1, 8, None) == -1
+    assert L.aki_mma_swiglu(buf, 16, buf, 8, 1, 12, None) == -3                                                   # N % 8
+    assert L.aki_mma_cross_entropy_fwd(None, 0, 0, None, 0, 1, 1, 8, -100, None, None, None) == -1
+    assert L.aki_mma_cross_entropy_fwd(buf, 80, 40, buf, 2, 1, 2, 36, -100, buf, buf, None) == -3                 # V % 8
+    assert L.aki_mma_cross_entropy_bwd(buf, 80, 40, buf, 2, 1, 2, 40, -100, buf, None, buf, 80, 40, None) == -1   # scale NULL
+
+
+def test_fuse_phi3_elementwise_is_reversible_and_steps_aside_on_cpu():
+    """aki_b200.fuse_phi3_elementwise: per-instance rebinding, idempotent, undone by unfuse; on tensors the fused kernels do
+    not serve (CPU, fp32, autograd on) the original forwards run and the outputs are unchanged."""
+    import aki_b200
+    from transformers import Phi3Config, Phi3ForCausalLM
+    cfg = Phi3Config(hidden_size=256, num_attention_heads=4, num_key_value_heads=4, intermediate_size=512, vocab_size=64,
+                     num_hidden_layers=2, pad_token_id=0)
+    torch.manual_seed(0)
+    m = Phi3ForCausalLM(cfg).eval()
+    ids = torch.randint(1, 64, (2, 9))
+    with torch.no_grad():
+        ref = m(input_ids=ids).logits
+    assert aki_b200.fuse_phi3_elementwise(m) == 2 * 3 + 1
+    assert aki_b200.fuse_phi3_elementwise(m) == 0
+    with torch.no_grad():
+        got = m(input_ids=ids).logits
+    assert torch.equal(ref, got)
+    assert aki_b200.unfuse_phi3_elementwise(m) == 7
+    assert not any(hasattr(x, "_aki_orig_forward") for x in m.modules())
+
+
 def test_ops_refuse_cpu_tensors(lib):
     from aki_b200 import ops
     x = torch.zeros(1, 8, dtype=torch.int64)
