@@ -165,13 +165,23 @@ def _edge_prompt(kind):
         L, N = 400, 128
         lang = g.integers(3, 31000, size=(1, L)).astype(np.int64); am = np.ones_like(lang)
         lang[0, 10] = M; lang[0, 11] = M; lang[0, 390] = A
+    elif kind == "more-spans-than-plan-cuts":  # 14 / 11 images of 40 tokens: more spans than the forward plan may cut at
+        L, N = 700, 40                          # (max_spans = 8): the remaining spans ride in aligned tiles
+        lang = g.integers(3, 31000, size=(2, L)).astype(np.int64); am = np.ones_like(lang)
+        for i in range(14):
+            lang[0, 7 + 45 * i] = M
+        lang[0, 690] = A
+        for i in range(11):
+            lang[1, 3 + 50 * i] = M
+        lang[1, 600] = A; lang[1, 640:] = PAD; am[1, 640:] = 0
     else:
         raise KeyError(kind)
     return lang, am, N, text_only
 
 
 @pytest.mark.parametrize("kind", ["left-pad-generate", "mixed-image-counts", "tile-edges", "assistant-before-image",
-                                  "no-assistant", "text-only-variant", "span-straddles-tiles", "back-to-back-spans"])
+                                  "no-assistant", "text-only-variant", "span-straddles-tiles", "back-to-back-spans",
+                                  "more-spans-than-plan-cuts"])
 def test_edge_geometries_forward_and_backward(kind):
     """Padding inside a sample, ragged batches, 0..3 images, tile-edge lengths, degenerate <|assistant|> positions and
     the text-only multi-image variant: bit-exact mask expansion, forward and gradients within the bf16 tolerance."""
