@@ -90,6 +90,12 @@ _SIGNATURES = {
     "aki_mma_cross_entropy_bwd": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int,
                                             C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64,
                                             C.c_void_p]),
+    "aki_mma_add_rmsnorm_amp_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p,
+                                              C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "aki_mma_rmsnorm_amp_bwd_partials": (C.c_int, [C.c_int]),
+    "aki_mma_rmsnorm_amp_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                          C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "aki_mma_swiglu_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "aki_mma_set_timing_events": (C.c_int, [C.c_void_p, C.c_void_p]),
     "aki_mma_launch_count": (C.c_ulonglong, []),
     "aki_mma_attn_fwd_simt": (C.c_int, [C.POINTER(AttnParams), C.c_void_p]),

@@ -255,3 +255,213 @@ extern "C" int aki_mma_cross_entropy_bwd(const void* logits, int64_t stride_b, i
       scale_dev, static_cast<__nv_bfloat16*>(dlogits), d_stride_b, d_stride_t);
   return check_launch();
 }
+
+// ------------------------------------------------------------------------------------------------------------------
+// TRAINING layout of the same element-wise work (SURVEY 8 f-1 for the SFT step; reference precision amp_bf16,
+// configs/sft.yaml:55): the residual stream and the norm weights are fp32, the GEMM operands bf16.
+//   add_rmsnorm_amp_fwd  h' = h + float(a) (a = the bf16 output of o_proj / down_proj; skipped when NULL),
+//                        r = rsqrt(mean(h'^2) + eps), x = bf16(w * (h' * r))      = residual add + Phi3RMSNorm + the
+//                        autocast cast of the next Linear's input, one pass instead of ~9 ATen kernels
+//   rmsnorm_amp_bwd      g = float(dx) * w;  dh = dh_out + r * g - h' * (r^3 / K) * sum_k(g_k h'_k);
+//                        dw_partial[warp] += float(dx) * h' * r over the rows this warp walks (summed by the caller:
+//                        deterministic, no atomics).  dh is the gradient of both h and (after a cast) a.
+//   swiglu_bwd           d_up = d_out * silu(gate).bf16;  d_act = (d_out * up).bf16;  d_gate = d_act * silu'(gate)
+// One warp per token row; the backward reads its row twice (second read from L1/L2).
+namespace aki {
+
+constexpr int AMP_MAX_CHUNKS = 12;       // 8-element chunks per lane: K <= 32 * 8 * 12 = 3072
+
+__device__ __forceinline__ void ld8_f32(const float* p, float* f) {
+  *reinterpret_cast<float4*>(f) = *reinterpret_cast<const float4*>(p);
+  *reinterpret_cast<float4*>(f + 4) = *reinterpret_cast<const float4*>(p + 4);
+}
+__device__ __forceinline__ void st8_f32(float* p, const float* f) {
+  *reinterpret_cast<float4*>(p) = *reinterpret_cast<const float4*>(f);
+  *reinterpret_cast<float4*>(p + 4) = *reinterpret_cast<const float4*>(f + 4);
+}
+__device__ __forceinline__ void ld8_bf16(const __nv_bfloat16* p, float* f) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) { const float2 v = __bfloat1622float2(h[e]); f[2 * e] = v.x; f[2 * e + 1] = v.y; }
+}
+__device__ __forceinline__ void st8_bf16(__nv_bfloat16* p, const float* f) {
+  uint4 u;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+
+__global__ void __launch_bounds__(NORM_WARPS * 32)
+add_rmsnorm_amp_fwd_kernel(const float* h_in, const __nv_bfloat16* __restrict__ a, const float* __restrict__ w, float eps,
+                           float* h_out, __nv_bfloat16* __restrict__ x, float* __restrict__ r_out, int M, int K) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * NORM_WARPS + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const int n_chunks = K >> 8;
+  float v[AMP_MAX_CHUNKS][8];
+  float ss = 0.f;
+#pragma unroll
+  for (int c = 0; c < AMP_MAX_CHUNKS; ++c) {
+    if (c < n_chunks) {
+      const size_t k = (size_t)row * K + (c * 32 + lane) * 8;
+      ld8_f32(h_in + k, v[c]);
+      if (a) {
+        float fa[8];
+        ld8_bf16(a + k, fa);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[c][e] += fa[e];
+        st8_f32(h_out + k, v[c]);
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) ss += v[c][e] * v[c][e];
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  const float r = rsqrtf(ss / (float)K + eps);
+  if (lane == 0) r_out[row] = r;
+#pragma unroll
+  for (int c = 0; c < AMP_MAX_CHUNKS; ++c) {
+    if (c < n_chunks) {
+      const int kk = (c * 32 + lane) * 8;
+      float wv[8], out[8];
+      ld8_f32(w + kk, wv);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) out[e] = wv[e] * (v[c][e] * r);
+      st8_bf16(x + (size_t)row * K + kk, out);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(NORM_WARPS * 32)
+rmsnorm_amp_bwd_kernel(const __nv_bfloat16* __restrict__ dx, const float* dh_out, const float* __restrict__ h,
+                       const float* __restrict__ r_in, const float* __restrict__ w, float* dh,
+                       float* __restrict__ dw_partial, int M, int K) {
+  const int lane = threadIdx.x & 31;
+  const int gwarp = blockIdx.x * NORM_WARPS + (threadIdx.x >> 5), n_warps = gridDim.x * NORM_WARPS;
+  const int n_chunks = K >> 8;
+  float dw[AMP_MAX_CHUNKS][8];
+#pragma unroll
+  for (int c = 0; c < AMP_MAX_CHUNKS; ++c)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) dw[c][e] = 0.f;
+  for (int row = gwarp; row < M; row += n_warps) {
+    const float r = r_in[row];
+    float dot = 0.f;
+#pragma unroll
+    for (int c = 0; c < AMP_MAX_CHUNKS; ++c) {
+      if (c < n_chunks) {
+        const int kk = (c * 32 + lane) * 8;
+        float g[8], hv[8], wv[8];
+        ld8_bf16(dx + (size_t)row * K + kk, g);
+        ld8_f32(h + (size_t)row * K + kk, hv);
+        ld8_f32(w + kk, wv);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          dw[c][e] += g[e] * hv[e] * r;
+          dot += g[e] * wv[e] * hv[e];
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+    const float coef = r * r * r * dot / (float)K;
+#pragma unroll
+    for (int c = 0; c < AMP_MAX_CHUNKS; ++c) {
+      if (c < n_chunks) {
+        const int kk = (c * 32 + lane) * 8;
+        const size_t k = (size_t)row * K + kk;
+        float g[8], hv[8], wv[8], out[8];
+        ld8_bf16(dx + k, g);
+        ld8_f32(h + k, hv);
+        ld8_f32(w + kk, wv);
+        if (dh_out) ld8_f32(dh_out + k, out);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) out[e] = (dh_out ? out[e] : 0.f) + r * g[e] * wv[e] - hv[e] * coef;
+        st8_f32(dh + k, out);
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < AMP_MAX_CHUNKS; ++c)
+    if (c < n_chunks) st8_f32(dw_partial + (size_t)gwarp * K + (c * 32 + lane) * 8, dw[c]);
+}
+
+__global__ void __launch_bounds__(256)
+swiglu_bwd_kernel(const __nv_bfloat16* __restrict__ d_out, const __nv_bfloat16* __restrict__ gate_up,
+                  __nv_bfloat16* __restrict__ d_gate_up, int M, int N) {
+  const int per_row = N >> 3;
+  const long long total = (long long)M * per_row;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int row = (int)(i / per_row), k = (int)(i % per_row) * 8;
+    float d[8], g[8], u[8], dg[8], du[8];
+    ld8_bf16(d_out + (size_t)row * N + k, d);
+    ld8_bf16(gate_up + (size_t)row * 2 * N + k, g);
+    ld8_bf16(gate_up + (size_t)row * 2 * N + N + k, u);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float s = 1.f / (1.f + expf(-g[e]));
+      const float act = __bfloat162float(__float2bfloat16(g[e] * s));          // silu(gate) as the forward rounded it
+      du[e] = d[e] * act;                                                      // d_up = d_out * act (bf16 product)
+      const float d_act = __bfloat162float(__float2bfloat16(d[e] * u[e]));     // d_act = d_out * up, rounded to bf16
+      dg[e] = d_act * (s * (1.f + g[e] * (1.f - s)));                          // silu_backward in fp32
+    }
+    st8_bf16(d_gate_up + (size_t)row * 2 * N + k, dg);
+    st8_bf16(d_gate_up + (size_t)row * 2 * N + N + k, du);
+  }
+}
+
+}  // namespace aki
+
+extern "C" int aki_mma_add_rmsnorm_amp_fwd(const float* h_in, const void* a, const float* weight, float eps, float* h_out,
+                                           void* x, float* r_out, int M, int K, aki_stream_t stream) {
+  AKI_REQUIRE(h_in && weight && x && r_out, AKI_ERR_NULL);
+  AKI_REQUIRE((a != nullptr) == (h_out != nullptr), AKI_ERR_NULL);
+  AKI_REQUIRE(M > 0 && K > 0, AKI_ERR_BAD_SHAPE);
+  AKI_REQUIRE(K % 256 == 0 && K <= 256 * aki::AMP_MAX_CHUNKS, AKI_ERR_UNSUPPORTED);
+  AKI_REQUIRE(aki::aligned16(h_in) && aki::aligned16(weight) && aki::aligned16(x) && (!a || aki::aligned16(a)) &&
+                  (!h_out || aki::aligned16(h_out)),
+              AKI_ERR_MISALIGNED);
+  aki::add_rmsnorm_amp_fwd_kernel<<<(M + aki::NORM_WARPS - 1) / aki::NORM_WARPS, aki::NORM_WARPS * 32, 0,
+                                    static_cast<cudaStream_t>(stream)>>>(
+      h_in, static_cast<const __nv_bfloat16*>(a), weight, eps, h_out, static_cast<__nv_bfloat16*>(x), r_out, M, K);
+  return aki::check_launch();
+}
+
+extern "C" int aki_mma_rmsnorm_amp_bwd_partials(int M) {
+  if (M <= 0) return 0;
+  const int ctas = (M + aki::NORM_WARPS - 1) / aki::NORM_WARPS;
+  return (ctas < 296 ? ctas : 296) * aki::NORM_WARPS;
+}
+
+extern "C" int aki_mma_rmsnorm_amp_bwd(const void* dx, const float* dh_out, const float* h, const float* r,
+                                       const float* weight, float* dh, float* dw_partial, int M, int K,
+                                       aki_stream_t stream) {
+  AKI_REQUIRE(dx && h && r && weight && dh && dw_partial, AKI_ERR_NULL);
+  AKI_REQUIRE(M > 0 && K > 0, AKI_ERR_BAD_SHAPE);
+  AKI_REQUIRE(K % 256 == 0 && K <= 256 * aki::AMP_MAX_CHUNKS, AKI_ERR_UNSUPPORTED);
+  AKI_REQUIRE(aki::aligned16(dx) && aki::aligned16(h) && aki::aligned16(weight) && aki::aligned16(dh) &&
+                  aki::aligned16(dw_partial) && (!dh_out || aki::aligned16(dh_out)),
+              AKI_ERR_MISALIGNED);
+  const int grid = aki_mma_rmsnorm_amp_bwd_partials(M) / aki::NORM_WARPS;
+  aki::rmsnorm_amp_bwd_kernel<<<grid, aki::NORM_WARPS * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(dx), dh_out, h, r, weight, dh, dw_partial, M, K);
+  return aki::check_launch();
+}
+
+extern "C" int aki_mma_swiglu_bwd(const void* d_out, const void* gate_up, void* d_gate_up, int M, int N,
+                                  aki_stream_t stream) {
+  AKI_REQUIRE(d_out && gate_up && d_gate_up, AKI_ERR_NULL);
+  AKI_REQUIRE(M > 0 && N > 0, AKI_ERR_BAD_SHAPE);
+  AKI_REQUIRE(N % 8 == 0, AKI_ERR_UNSUPPORTED);
+  AKI_REQUIRE(aki::aligned16(d_out) && aki::aligned16(gate_up) && aki::aligned16(d_gate_up), AKI_ERR_MISALIGNED);
+  const long long total = (long long)M * (N / 8);
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  aki::swiglu_bwd_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(d_out), static_cast<const __nv_bfloat16*>(gate_up),
+      static_cast<__nv_bfloat16*>(d_gate_up), M, N);
+  return aki::check_launch();
+}

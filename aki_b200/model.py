@@ -243,6 +243,7 @@ class AkiPhi3SFT(nn.Module):
         replace_phi3_attention(self.lm)
         self.config = config
         self.fused_ce = True
+        self.fused_layers = True          # False: HF's Phi3DecoderLayer objects (the parity reference of the fused pass)
         rp = config.rope_parameters
         self.rope = LongRope(96, rp["rope_theta"], rp["short_factor"], rp["long_factor"], config.max_position_embeddings,
                              rp["original_max_position_embeddings"], device=device)
@@ -250,14 +251,32 @@ class AkiPhi3SFT(nn.Module):
     def forward(self, inputs_embeds: torch.Tensor, segs: Optional[ops.MMASegments], labels: torch.Tensor):
         B, T, _ = inputs_embeds.shape
         cos, sin = self.rope.tables(torch.arange(T, device=inputs_embeds.device)[None], max_position=T - 1)
+        layers = self.lm.model.layers
+        fused = (self.fused_layers and inputs_embeds.dtype == torch.float32 and inputs_embeds.shape[-1] % 256 == 0
+                 and inputs_embeds.shape[-1] <= 3072 and layers[0].input_layernorm.weight.dtype == torch.float32)
         with torch.autocast("cuda", dtype=torch.bfloat16):
-            h = inputs_embeds
-            for layer in self.lm.model.layers:
-                h = layer(h, attention_mask=None, position_ids=None, past_key_values=None, use_cache=False,
-                          position_embeddings=None, mma_segments=segs, mma_rope=(cos, sin))
-                if isinstance(h, tuple):
-                    h = h[0]
-            logits = self.lm.lm_head(self.lm.model.norm(h))
+            if fused:
+                # SURVEY 8 f-1 for the SFT step: residual add + RMSNorm + operand cast, and the SiLU gate, as fused forward /
+                # backward kernels in the amp layout (fp32 residual stream, bf16 GEMM operands) around the same Linears
+                eps = self.config.rms_norm_eps
+                h = inputs_embeds.contiguous()
+                _, x = ops.add_rmsnorm_amp(h, None, layers[0].input_layernorm.weight, eps)
+                for li, layer in enumerate(layers):
+                    a = layer.self_attn(x, position_embeddings=None, attention_mask=None, past_key_values=None,
+                                        mma_segments=segs, mma_rope=(cos, sin))[0]
+                    h, x = ops.add_rmsnorm_amp(h, a.contiguous(), layer.post_attention_layernorm.weight, eps)
+                    d = layer.mlp.down_proj(ops.swiglu_train(layer.mlp.gate_up_proj(x)))
+                    nxt = layers[li + 1].input_layernorm if li + 1 < len(layers) else self.lm.model.norm
+                    h, x = ops.add_rmsnorm_amp(h, d.contiguous(), nxt.weight, eps)
+                logits = self.lm.lm_head(x)
+            else:
+                h = inputs_embeds
+                for layer in layers:
+                    h = layer(h, attention_mask=None, position_ids=None, past_key_values=None, use_cache=False,
+                              position_embeddings=None, mma_segments=segs, mma_rope=(cos, sin))
+                    if isinstance(h, tuple):
+                        h = h[0]
+                logits = self.lm.lm_head(self.lm.model.norm(h))
         if self.fused_ce and logits.dtype == torch.bfloat16 and logits.shape[-1] % 8 == 0:
             # one kernel forward, one backward, no fp32 copy of the (B,T,32064) logits
             return ops.cross_entropy_shifted(logits, labels.contiguous())

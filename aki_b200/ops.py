@@ -543,3 +543,73 @@ def cross_entropy_shifted(logits: torch.Tensor, labels: torch.Tensor, ignore_ind
     assert logits.dim() == 3 and logits.dtype == torch.bfloat16 and logits.stride(2) == 1
     assert labels.shape == logits.shape[:2] and labels.dtype == torch.int64 and labels.stride(1) == 1
     return _ShiftedCrossEntropy.apply(logits, labels, ignore_index)
+
+
+# ---- training layout (amp_bf16: fp32 residual stream and norm weights, bf16 GEMM operands) ------------------------------
+class _AddRmsNormAmp(torch.autograd.Function):
+    """(h, a, w) -> (h + a, bf16(w * rmsnorm(h + a))); a may be None (then the first output is None too)."""
+
+    @staticmethod
+    def forward(ctx, h, a, w, eps):
+        K = h.shape[-1]
+        h2 = h.reshape(-1, K)
+        M = h2.shape[0]
+        a2 = a.reshape(-1, K) if a is not None else None
+        h_new = torch.empty_like(h2) if a is not None else None
+        x = torch.empty(M, K, dtype=torch.bfloat16, device=h.device)
+        r = torch.empty(M, dtype=torch.float32, device=h.device)
+        check(lib.aki_mma_add_rmsnorm_amp_fwd(_ptr(h2), _ptr(a2), _ptr(w), float(eps), _ptr(h_new), _ptr(x), _ptr(r), M, K,
+                                              _stream()), "aki_mma_add_rmsnorm_amp_fwd")
+        ctx.save_for_backward(h_new if a is not None else h2, r, w)
+        ctx.has_a, ctx.shape = a is not None, h.shape
+        if a is None:
+            return None, x.view(h.shape)
+        return h_new.view(h.shape), x.view(h.shape)
+
+    @staticmethod
+    def backward(ctx, d_h_new, d_x):
+        h, r, w = ctx.saved_tensors
+        M, K = h.shape
+        if d_x is None:
+            d_x = torch.zeros(M, K, dtype=torch.bfloat16, device=h.device)
+        d_x = d_x.reshape(M, K).contiguous()
+        dh_out = d_h_new.reshape(M, K).contiguous() if d_h_new is not None else None
+        n_part = lib.aki_mma_rmsnorm_amp_bwd_partials(M)
+        dw_p = torch.empty(n_part, K, dtype=torch.float32, device=h.device)
+        dh = torch.empty(M, K, dtype=torch.float32, device=h.device)
+        check(lib.aki_mma_rmsnorm_amp_bwd(_ptr(d_x), _ptr(dh_out), _ptr(h), _ptr(r), _ptr(w), _ptr(dh), _ptr(dw_p), M, K,
+                                          _stream()), "aki_mma_rmsnorm_amp_bwd")
+        dh = dh.view(ctx.shape)
+        return dh, (dh.to(torch.bfloat16) if ctx.has_a else None), dw_p.sum(0), None
+
+
+def add_rmsnorm_amp(h: torch.Tensor, a: _OT, weight: torch.Tensor, eps: float):
+    """Training-layout residual add + Phi3RMSNorm + autocast cast: h (..., K) fp32 residual stream, a (..., K) bf16 branch
+    output or None, weight (K) fp32.  Returns (h + a [None without a], x bf16) -- differentiable w.r.t. h, a and weight."""
+    _require_cuda(h, a, weight)
+    assert h.dtype == torch.float32 and weight.dtype == torch.float32 and h.is_contiguous() and weight.is_contiguous()
+    assert a is None or (a.dtype == torch.bfloat16 and a.shape == h.shape and a.is_contiguous())
+    return _AddRmsNormAmp.apply(h, a, weight, eps)
+
+
+class _SwiGLUTrain(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, gate_up):
+        ctx.save_for_backward(gate_up)
+        return swiglu(gate_up)
+
+    @staticmethod
+    def backward(ctx, d_out):
+        (gate_up,) = ctx.saved_tensors
+        N = gate_up.shape[-1] // 2
+        g2 = gate_up.reshape(-1, 2 * N)
+        d2 = d_out.reshape(-1, N).contiguous()
+        d_gu = torch.empty_like(g2)
+        check(lib.aki_mma_swiglu_bwd(_ptr(d2), _ptr(g2), _ptr(d_gu), g2.shape[0], N, _stream()), "aki_mma_swiglu_bwd")
+        return d_gu.view(gate_up.shape)
+
+
+def swiglu_train(gate_up: torch.Tensor) -> torch.Tensor:
+    """Differentiable ops.swiglu (bf16 in / out, eager autograd's rounding points in the backward)."""
+    assert gate_up.dtype == torch.bfloat16 and gate_up.is_contiguous()
+    return _SwiGLUTrain.apply(gate_up)

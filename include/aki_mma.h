@@ -253,6 +253,25 @@ int aki_mma_cross_entropy_bwd(const void* logits, int64_t stride_b, int64_t stri
                               const float* scale_dev, void* dlogits, int64_t d_stride_b, int64_t d_stride_t,
                               aki_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------------
+ * (9) The element-wise work of (7) in the TRAINING layout of the reference's amp_bf16 precision (configs/sft.yaml:55;
+ *     SURVEY 8 f-1 for the SFT step): fp32 residual stream and norm weights, bf16 GEMM operands; forward and backward.
+ *     add_rmsnorm_amp_fwd: h_out = h_in + float(a) (a (M,K) bf16 = o_proj / down_proj output; a and h_out both NULL:
+ *       no add), r_out (M) = rsqrt(mean(h^2) + eps), x (M,K) bf16 = bf16(weight * (h * r)) -- the residual add, the fp32
+ *       Phi3RMSNorm and the autocast cast of the next Linear's input in one pass.  All rows contiguous.  K % 256 == 0,
+ *       K <= 3072.
+ *     rmsnorm_amp_bwd: dh (M,K) fp32 = dh_out (NULL = 0) + gradient of the norm w.r.t. h given dx (M,K) bf16;
+ *       dw_partial (aki_mma_rmsnorm_amp_bwd_partials(M), K) fp32: per-warp partial sums of the weight gradient, to be
+ *       summed over dim 0 by the caller (no atomics: deterministic).
+ *     swiglu_bwd: d_gate_up (M,2N) bf16 from d_out (M,N) bf16 and gate_up (M,2N) bf16, with eager autograd's rounding
+ *       points. */
+int aki_mma_add_rmsnorm_amp_fwd(const float* h_in, const void* a, const float* weight, float eps, float* h_out, void* x,
+                                float* r_out, int M, int K, aki_stream_t stream);
+int aki_mma_rmsnorm_amp_bwd_partials(int M);
+int aki_mma_rmsnorm_amp_bwd(const void* dx, const float* dh_out, const float* h, const float* r, const float* weight,
+                            float* dh, float* dw_partial, int M, int K, aki_stream_t stream);
+int aki_mma_swiglu_bwd(const void* d_out, const void* gate_up, void* d_gate_up, int M, int N, aki_stream_t stream);
+
 /* Measurement hook (bench.py roofline): the NEXT aki_mma_attn_fwd / aki_mma_attn_bwd call of this host thread
  * records `ev_begin` right before and `ev_end` right after its tcgen05 attention kernel on the call's stream (the
  * preprocess / memset / finalize launches of the backward stay outside), then the hook clears itself.

@@ -705,3 +705,93 @@ def test_fused_cross_entropy_matches_hf_loss(B, T, V):
     assert float(d.max()) <= 2 ** -7 * float(a.grad.float().abs().max()) + 1e-12     # one bf16 ulp of the largest entry
     assert torch.equal(b.grad[:, -1], torch.zeros_like(b.grad[:, -1]))              # the last position has no target
     assert torch.equal(b.grad[:, : T // 3 - 1], torch.zeros_like(b.grad[:, : T // 3 - 1]))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("M,K,with_a", [(5, 3072, True), (2624, 3072, True), (33, 1024, False)])
+def test_add_rmsnorm_amp_forward_and_backward_match_eager_autograd(M, K, with_a):
+    """Training layout (amp_bf16): fp32 residual stream + bf16 branch output -> fp32 sum, fp32 Phi3RMSNorm, bf16 cast of the
+    next Linear's operand; gradients w.r.t. the stream, the branch output and the norm weight against eager autograd."""
+    from transformers.models.phi3.modeling_phi3 import Phi3RMSNorm
+    from aki_b200 import ops
+    g = torch.Generator(device=dev).manual_seed(M + K)
+    h0 = torch.randn(M, K, generator=g, device=dev) * 2
+    a0 = torch.randn(M, K, generator=g, device=dev).to(torch.bfloat16) if with_a else None
+    norm = Phi3RMSNorm(K, eps=1e-5).to(dev)                                   # fp32 master weight
+    with torch.no_grad():
+        norm.weight.copy_(1 + 0.1 * torch.randn(K, generator=g, device=dev))
+    gx = torch.randn(M, K, generator=g, device=dev).to(torch.bfloat16)        # gradient arriving at the bf16 operand
+    gh = torch.randn(M, K, generator=g, device=dev) * 0.1                      # gradient arriving at the residual stream
+
+    def run(fused):
+        h = h0.clone().requires_grad_(True)
+        a = a0.clone().requires_grad_(True) if with_a else None
+        norm.weight.grad = None
+        if fused:
+            hn, x = ops.add_rmsnorm_amp(h, a, norm.weight, 1e-5)
+        else:
+            hn = h + a if with_a else None
+            x = norm(hn if with_a else h).to(torch.bfloat16)
+        outs, grads = [x], [gx]
+        if with_a:
+            outs.append(hn); grads.append(gh)
+        torch.autograd.backward(outs, grads)
+        return x.detach(), (hn.detach() if with_a else None), h.grad, (a.grad if with_a else None), norm.weight.grad.clone()
+
+    x_r, hn_r, dh_r, da_r, dw_r = run(False)
+    x_f, hn_f, dh_f, da_f, dw_f = run(True)
+    if with_a:
+        assert torch.equal(hn_f, hn_r)
+    d = (x_f.float() - x_r.float()).abs()
+    assert float(d.max()) <= 2 ** -7 * float(x_r.float().abs().max()) and float((d > 0).float().mean()) < 0.01
+    rel = lambda u, v: float((u.float() - v.float()).norm() / v.float().norm())
+    assert rel(dh_f, dh_r) < 1e-5
+    assert rel(dw_f, dw_r) < 1e-4
+    if with_a:
+        assert da_f.dtype == torch.bfloat16 and rel(da_f, da_r) < 4e-3
+
+
+@pytest.mark.gpu
+def test_swiglu_train_backward_matches_eager_autograd():
+    from aki_b200 import ops
+    g = torch.Generator(device=dev).manual_seed(3)
+    gu0 = (torch.randn(77, 2 * 8192, generator=g, device=dev) * 2).to(torch.bfloat16)
+    go = torch.randn(77, 8192, generator=g, device=dev).to(torch.bfloat16)
+    a = gu0.clone().requires_grad_(True)
+    gate, up = a.chunk(2, dim=-1)
+    (up * torch.nn.functional.silu(gate)).backward(go)
+    b = gu0.clone().requires_grad_(True)
+    ops.swiglu_train(b).backward(go)
+    d = (b.grad.float() - a.grad.float()).abs()
+    assert float(d.max()) <= 2 ** -6 * float(a.grad.float().abs().max())
+    assert float((d > 0).float().mean()) < 0.02
+
+
+@pytest.mark.gpu
+def test_sft_step_with_fused_layer_kernels_matches_the_hf_layer_objects():
+    """AkiPhi3SFT with the fused training-layout kernels (residual add + RMSNorm + cast, SiLU gate, cross-entropy) against
+    the same model stepping through HF's Phi3DecoderLayer objects and F.cross_entropy: loss and every parameter gradient."""
+    import aki_b200
+    from aki_b200 import ops
+    from aki_b200.model import AkiPhi3SFT, phi35_mini_config
+    model = AkiPhi3SFT(phi35_mini_config(num_layers=2), device=dev, seed=1)
+    B, L, N = 2, 120, 48
+    lang, am = Hp.make_prompt(B, L, N, 1, pad_right=17)
+    segs = ops.build_segments(torch.from_numpy(lang).to(dev), torch.from_numpy(am).to(dev), N, Hp.MEDIA_ID)
+    T = segs.T
+    torch.manual_seed(2)
+    emb = torch.randn(B, T, 3072, device=dev) * 0.05
+    labels = torch.randint(0, 32000, (B, T), device=dev); labels[:, :40] = -100
+    res = []
+    for fused in (False, True):
+        model.fused_layers = fused; model.fused_ce = fused
+        model.zero_grad(set_to_none=True)
+        loss = model(emb, segs, labels)
+        loss.backward()
+        res.append((float(loss), {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None}))
+    (l0, g0), (l1, g1) = res
+    assert abs(l1 - l0) < 2e-3 * abs(l0), (l0, l1)
+    assert g0.keys() == g1.keys() and len(g0) > 10
+    for n in g0:
+        rel = float((g1[n].float() - g0[n].float()).norm() / (g0[n].float().norm() + 1e-12))
+        assert rel < 3e-2, (n, rel)
