@@ -76,6 +76,12 @@ def test_layer_kernel_argument_validation_without_gpu(lib):
     assert L.aki_mma_cross_entropy_fwd(None, 0, 0, None, 0, 1, 1, 8, -100, None, None, None) == -1
     assert L.aki_mma_cross_entropy_fwd(buf, 80, 40, buf, 2, 1, 2, 36, -100, buf, buf, None) == -3                 # V % 8
     assert L.aki_mma_cross_entropy_bwd(buf, 80, 40, buf, 2, 1, 2, 40, -100, buf, None, buf, 80, 40, None) == -1   # scale NULL
+    assert L.aki_mma_add_rmsnorm_amp_fwd(buf, None, buf, 1e-5, buf, buf, buf, 1, 256, None) == -1                 # h_out without a
+    assert L.aki_mma_add_rmsnorm_amp_fwd(buf, None, buf, 1e-5, None, buf, buf, 1, 4096, None) == -3               # K > 3072
+    assert L.aki_mma_rmsnorm_amp_bwd_partials(0) == 0 and L.aki_mma_rmsnorm_amp_bwd_partials(9) == 16
+    assert L.aki_mma_rmsnorm_amp_bwd_partials(10 ** 6) == 296 * 8
+    assert L.aki_mma_rmsnorm_amp_bwd(buf, None, buf, buf, buf, buf, None, 1, 256, None) == -1
+    assert L.aki_mma_swiglu_bwd(buf, buf, buf, 1, 12, None) == -3
 
 
 def test_fuse_phi3_elementwise_is_reversible_and_steps_aside_on_cpu():

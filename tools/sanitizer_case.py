@@ -38,5 +38,11 @@ ops.cross_entropy_shifted(lg, lab).backward()
 kc = torch.randn(2, H, 40, D, device=dev).to(torch.bfloat16); vc = torch.randn_like(kc)
 ops.decode_op(torch.randn(2, H, D, device=dev).to(torch.bfloat16), kc, vc, torch.tensor([33, 40], dtype=torch.int32, device=dev), 40,
               D ** -0.5, torch.tensor([5, 0], dtype=torch.int32, device=dev))
+hh = torch.randn(13, 1024, device=dev).requires_grad_(True); aa = torch.randn(13, 1024, device=dev).to(torch.bfloat16).requires_grad_(True)
+ww = torch.ones(1024, device=dev).requires_grad_(True)
+hn, xx = ops.add_rmsnorm_amp(hh, aa, ww, 1e-5)
+(xx.float().sum() + hn.sum()).backward()
+gg = torch.randn(13, 2 * 72, device=dev).to(torch.bfloat16).requires_grad_(True)
+ops.swiglu_train(gg).float().sum().backward()
 torch.cuda.synchronize()
 print("helper kernels ran")
