@@ -363,13 +363,7 @@ def sft_section(args, dev, rank, world, local, steps, warmup):
     bucket_mb = int(os.environ.get("AKI_DDP_BUCKET_MB", "256"))
     # 15.3 GB of fp32 gradients per step: large buckets (NCCL reaches its NVLink bandwidth only on >= 100 MB messages;
     # DDP's 25 MB default left 16.7 ms exposed on 2 GPUs), bucket views instead of copies, static graph
-    net = DDP(model, device_ids=[local], gradient_as_bucket_view=True, bucket_cap_mb=bucket_mb, static_graph=True) \
-        if world > 1 else model
-    if world > 1 and args.sft_bf16_reduce:
-        # gradients cross NVLink in bf16, as the reference's FSDP mixed-precision config reduces them
-        # (train/distributed.py:163-167); halves the 15.3 GB fp32 all-reduce but adds two cast passes per bucket
-        from torch.distributed.algorithms.ddp_comm_hooks import default_hooks
-        net.register_comm_hook(None, default_hooks.bf16_compress_hook)
+    net = model            # wrapped in DDP below, AFTER the compute-only timing of the bare module
     opt = torch.optim.AdamW(model.parameters(), lr=2e-5, weight_decay=1e-4, fused=True)
     g = np.random.default_rng(1000 + rank)
     me = type("M", (), {})()
@@ -409,10 +403,24 @@ def sft_section(args, dev, rank, world, local, steps, warmup):
         barrier()
         return a.elapsed_time(b_) / n
 
+    ms_nosync = None
+    if world > 1:
+        # this rank's compute-only step first, on the bare module (DDP's reducer hooks do not exist yet, so nothing of the
+        # all-reduce machinery is in the way), then the data-parallel step
+        for i in range(3):
+            step(i, False)
+        ms_nosync = timed(max(3, steps // 2), False)
+        net = DDP(model, device_ids=[local], gradient_as_bucket_view=True, bucket_cap_mb=bucket_mb, static_graph=True)
+        if args.sft_bf16_reduce:
+            # gradients cross NVLink in bf16, as the reference's FSDP mixed-precision config reduces them
+            # (train/distributed.py:163-167); halves the 15.3 GB fp32 all-reduce but adds two cast passes per bucket
+            from torch.distributed.algorithms.ddp_comm_hooks import default_hooks
+            net.register_comm_hook(None, default_hooks.bf16_compress_hook)
     for i in range(max(3, warmup)):
         step(i)
     ms = timed(steps, True)
-    ms_nosync = timed(max(3, steps // 2), False) if world > 1 else ms
+    if ms_nosync is None:
+        ms_nosync = ms
     # NCCL all-reduce alone on a 1 GiB fp32 buffer (the pool's measured reference: 725 GB/s bus bandwidth at 8 ranks)
     busbw = None
     if world > 1:
